@@ -1,0 +1,238 @@
+"""ctypes binding of oracle/liboracle.so (TEST INFRASTRUCTURE — the CPU restatement of the
+reference algorithm; see oracle/README.md).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
+
+NJ = 7
+NF = 7
+COMB = 36
+
+
+class OracleConfig(C.Structure):
+    _fields_ = [
+        ("num_time_steps", C.c_int),
+        ("k_range", C.c_double * 7),
+        ("mass_uncertainty", C.c_double),
+        ("inertia_uncertainty", C.c_double),
+        ("simplify_threshold", C.c_double),
+        ("num_threads", C.c_int),
+    ]
+
+
+def build_oracle(force=False):
+    src = [os.path.join(ORACLE_DIR, f) for f in ("oracle_armour.cpp", "oracle_pz.hpp", "Makefile")]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build_oracle()
+        L = C.CDLL(LIB_PATH)
+        L.oracle_create.restype = C.c_void_p
+        L.oracle_create.argtypes = [C.POINTER(OracleConfig)]
+        L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_build_ms.restype = C.c_double
+        L.oracle_build_ms.argtypes = [C.c_void_p]
+        L.oracle_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _up(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def _vec(x, n=None):
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+    if n is not None:
+        assert a.size == n, (a.size, n)
+    return a
+
+
+TABLES = {"cos_q": 0, "sin_q": 1, "R": 2, "R_t": 3, "qd_des": 4, "qda_des": 5, "qdda_des": 6, "links": 7, "u_nom": 8, "u_nom_int": 9}
+
+
+class Oracle:
+    """One planning problem on the CPU oracle.  Method names follow the reference's TNLP callbacks."""
+
+    def __init__(self, T=128, k_range=None, mass_uncertainty=0.03, inertia_uncertainty=0.03, threshold=5e-4, num_threads=0):
+        self.L = lib()
+        cfg = OracleConfig()
+        cfg.num_time_steps = T
+        kr = [np.pi / 48] * 7 if k_range is None else list(k_range)
+        for i in range(7):
+            cfg.k_range[i] = kr[i]
+        cfg.mass_uncertainty = mass_uncertainty
+        cfg.inertia_uncertainty = inertia_uncertainty
+        cfg.simplify_threshold = threshold
+        cfg.num_threads = num_threads
+        self.T = T
+        self.k_range = np.array(kr)
+        self.h = C.c_void_p(self.L.oracle_create(C.byref(cfg)))
+        self.n_obs = 0
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.oracle_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def build(self, q0, qd0, qdd0, obstacles):
+        obs = _vec(obstacles)
+        assert obs.size % 12 == 0
+        self.n_obs = obs.size // 12
+        rc = self.L.oracle_build(self.h, _dp(_vec(q0, 7)), _dp(_vec(qd0, 7)), _dp(_vec(qdd0, 7)), _dp(obs), C.c_int(self.n_obs))
+        if rc != 0:
+            raise RuntimeError("oracle_build failed: %d" % rc)
+        return self.L.oracle_build_ms(self.h)
+
+    def op_stats(self):
+        out = np.zeros(8, dtype=np.uint64)
+        self.L.oracle_op_stats(self.h, _up(out))
+        names = ["n_mul", "pair_products", "flops", "n_simplify", "simplify_in", "simplify_out", "max_simplify_in", "max_simplify_out"]
+        return dict(zip(names, (int(v) for v in out)))
+
+    def get_nlp_info(self):
+        n, m, nnz, nh = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self.L.oracle_get_nlp_info(self.h, C.byref(n), C.byref(m), C.byref(nnz), C.byref(nh))
+        return n.value, m.value, nnz.value, nh.value
+
+    @property
+    def m(self):
+        return self.get_nlp_info()[1]
+
+    def get_bounds_info(self):
+        m = self.m
+        xl, xu, gl, gu = np.zeros(7), np.zeros(7), np.zeros(m), np.zeros(m)
+        self.L.oracle_get_bounds_info(self.h, _dp(xl), _dp(xu), _dp(gl), _dp(gu))
+        return xl, xu, gl, gu
+
+    def get_starting_point(self):
+        x = np.ones(7)
+        self.L.oracle_get_starting_point(self.h, _dp(x))
+        return x
+
+    def eval_f(self, q_des, t_plan, x):
+        f = C.c_double()
+        self.L.oracle_eval_f(self.h, _dp(_vec(q_des, 7)), C.c_double(t_plan), _dp(_vec(x, 7)), C.byref(f))
+        return f.value
+
+    def eval_grad_f(self, q_des, t_plan, x):
+        g = np.zeros(7)
+        self.L.oracle_eval_grad_f(self.h, _dp(_vec(q_des, 7)), C.c_double(t_plan), _dp(_vec(x, 7)), _dp(g))
+        return g
+
+    def eval_g(self, x):
+        g = np.zeros(self.m)
+        self.L.oracle_eval_g(self.h, _dp(_vec(x, 7)), _dp(g))
+        return g
+
+    def eval_jac_g(self, x):
+        v = np.zeros(self.m * 7)
+        self.L.oracle_eval_jac_g(self.h, _dp(_vec(x, 7)), _dp(v))
+        return v.reshape(self.m, 7)
+
+    def jac_structure(self):
+        m = self.m
+        ir, jc = np.zeros(m * 7, dtype=np.int32), np.zeros(m * 7, dtype=np.int32)
+        self.L.oracle_jac_structure(self.h, _ip(ir), _ip(jc))
+        return ir, jc
+
+    def check_feasible(self, g):
+        return bool(self.L.oracle_check_feasible(self.h, _dp(_vec(g, self.m))))
+
+    def get_pz(self, which, idx, s):
+        w = TABLES[which] if isinstance(which, str) else which
+        dims = np.zeros(2, dtype=np.int32)
+        n = self.L.oracle_get_pz(self.h, w, idx, s, _ip(dims), None, None, None, None)
+        dim = int(dims[0] * dims[1])
+        keys = np.zeros(max(n, 1), dtype=np.uint64)
+        coeffs = np.zeros((max(n, 1), dim))
+        center, indep = np.zeros(dim), np.zeros(dim)
+        self.L.oracle_get_pz(self.h, w, idx, s, _ip(dims), _up(keys), _dp(coeffs), _dp(center), _dp(indep))
+        return dict(rows=int(dims[0]), cols=int(dims[1]), keys=keys[:n], coeffs=coeffs[:n], center=center, independent=indep)
+
+    def torque_radius(self):
+        out = np.zeros(self.T * NF)
+        self.L.oracle_get_torque_radius(self.h, _dp(out))
+        return out.reshape(self.T, NF)  # [t, joint]
+
+    def link_generators(self):
+        out = np.zeros(self.T * NJ * 18)
+        self.L.oracle_get_link_generators(self.h, _dp(out))
+        return out.reshape(self.T, NJ, 6, 3).transpose(0, 1, 3, 2)  # [t, link, row, col]
+
+    def taylor_remainders(self):
+        c, s = np.zeros(NF * self.T * 2), np.zeros(NF * self.T * 2)
+        self.L.oracle_get_taylor_remainders(self.h, _dp(c), _dp(s))
+        return c.reshape(NF, self.T, 2), s.reshape(NF, self.T, 2)
+
+    def hyperplanes(self):
+        n = self.T * NJ * self.n_obs * COMB
+        A, d, dl = np.zeros(n * 3), np.zeros(n), np.zeros(n)
+        self.L.oracle_get_hyperplanes(self.h, _dp(A), _dp(d), _dp(dl))
+        shp = (self.T, NJ, self.n_obs, COMB)
+        return A.reshape(shp + (3,)), d.reshape(shp), dl.reshape(shp)
+
+    def link_sliced_center(self):
+        out = np.zeros(self.T * NJ * 3)
+        self.L.oracle_get_link_sliced_center(self.h, _dp(out))
+        return out.reshape(self.T, NJ, 3)
+
+    def trace_interval(self, s, cap=20000):
+        out = np.zeros(cap * 8, dtype=np.int32)
+        n = self.L.oracle_trace_interval(self.h, s, cap, _ip(out))
+        return out.reshape(cap, 8)[: min(n, cap)]
+
+
+PZ_OPS = {"mul": 0, "add": 1, "sub": 2, "cross": 3, "simplify": 4, "reduce": 5, "transpose": 6}
+
+
+def pz_binary(op, a, b=None, threshold=5e-4, cap=1 << 16):
+    """a, b: dicts rows, cols, keys, coeffs[n, dim] (column-major flattening), center, independent."""
+    L = lib()
+
+    def flat(z):
+        if z is None:
+            return (0, 0, 0, None, None, None, None), []
+        keys = np.ascontiguousarray(z["keys"], dtype=np.uint64)
+        co = np.ascontiguousarray(z["coeffs"], dtype=np.float64)
+        ce, ind = _vec(z["center"]), _vec(z["independent"])
+        return (z["rows"], z["cols"], len(keys), _up(keys), _dp(co), _dp(ce), _dp(ind)), [keys, co, ce, ind]
+
+    fa, ka = flat(a)
+    fb, kb = flat(b)
+    dims = np.zeros(2, dtype=np.int32)
+    keys = np.zeros(cap, dtype=np.uint64)
+    coeffs = np.zeros(cap * 9)
+    center, indep = np.zeros(9), np.zeros(9)
+    n = L.oracle_pz_binary(PZ_OPS[op], C.c_double(threshold), *fa, *fb, cap, _ip(dims), _up(keys), _dp(coeffs), _dp(center), _dp(indep))
+    if n < 0:
+        raise RuntimeError("oracle_pz_binary: %d" % n)
+    dim = int(dims[0] * dims[1])
+    return dict(rows=int(dims[0]), cols=int(dims[1]), keys=keys[:n].copy(), coeffs=coeffs[: n * dim].reshape(n, dim).copy(),
+                center=center[:dim].copy(), independent=indep[:dim].copy())
