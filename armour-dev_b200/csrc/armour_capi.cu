@@ -1,0 +1,632 @@
+// C ABI of the B200-native ARMOUR reachability + constraint path (see include/armour_b200.h).
+// Host-side glue only: device memory, one stream per handle, pinned staging buffers, the cheap
+// host-side TNLP callbacks (bounds, objective) and table getters.  All heavy work is in
+// reach_kernels.cu / constraint_kernels.cu.  There is no CPU fallback anywhere in this file.
+#include "../../include/armour_b200.h"
+#include "armour_launch.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace armour;
+
+namespace {
+
+thread_local std::string g_last_error;
+int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) return fail(ARMOUR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+// Kinova Gen3 without gripper (KPR/KinovaWithoutGripperInfo.h:10-112)
+void kinova_model(RobotModel& m) {
+    memset(&m, 0, sizeof(m));
+    const int axes[NJ] = {3, 3, 3, 3, 3, 3, 3};
+    const double trans[(NJ + 1) * 3] = {0, 0, 0.15643, 0, 0.005375, -0.12838, 0, -0.21038, -0.006375, 0, 0.006375, -0.21038,
+                                        0, -0.20843, -0.006375, 0, 0.00017505, -0.10593, 0, -0.10593, -0.00017505, 0, 0, 0};
+    const double rots[NJ * 3] = {M_PI, 0, 0, M_PI * 0.5, 0, 0, -M_PI * 0.5, 0, 0, M_PI * 0.5, 0, 0, -M_PI * 0.5, 0, 0, M_PI * 0.5, 0, 0, -M_PI * 0.5, 0, 0};
+    const double mass[NJ] = {1.3773, 1.1636, 1.1636, 0.9302, 0.6781, 0.6781, 0.5};
+    const double com[NJ * 3] = {-0.000023, -0.010364, -0.07336, -0.000044, -0.09958, -0.013278, -0.000044, -0.006641, -0.117892, -0.000018, -0.075478, -0.015006,
+                                0.000001, -0.009432, -0.063883, 0.000001, -0.045483, -0.00965, 0.000281, 0.011402, -0.029798};
+    const double inertia[NJ * 9] = {0.00457, 0.000001, 0.000002, 0.000001, 0.004831, 0.000448, 0.000002, 0.000448, 0.001409,
+                                    0.011088, 0.000005, 0, 0.000005, 0.001072, -0.000691, 0, -0.000691, 0.011255,
+                                    0.010932, 0, -0.000007, 0, 0.011127, 0.000606, -0.000007, 0.000606, 0.001043,
+                                    0.008147, -0.000001, 0, -0.000001, 0.000631, -0.0005, 0, -0.0005, 0.008316,
+                                    0.001596, 0, 0, 0, 0.001607, 0.000256, 0, 0.000256, 0.000399,
+                                    0.001641, 0, 0, 0, 0.00041, -0.000278, 0, -0.000278, 0.001641,
+                                    0.000587, 0.000003, 0.000003, 0.000003, 0.000369, -0.000118, 0.000003, -0.000118, 0.000609};
+    const double armature[NJ] = {8.03, 11.9962024615303644, 9.0025427861751517, 11.5806439316706360, 8.4665040917914123, 8.8537069373742430, 8.8587303664685315};
+    const double lb[NF] = {-1000.0, -2.41, -1000.0, -2.66, -1000.0, -2.23, -1000.0};
+    const double ub[NF] = {1000.0, 2.41, 1000.0, 2.66, 1000.0, 2.23, 1000.0};
+    const double speed[NF] = {1.3963, 1.3963, 1.3963, 1.3963, 1.2218, 1.2218, 1.2218};
+    const double torque[NF] = {56.7, 56.7, 56.7, 56.7, 29.4, 29.4, 29.4};
+    const double lzc[NJ][3] = {{0.000000, -0.001297, -0.088375}, {0.000000, -0.089400, -0.007877}, {0.000000, -0.001502, -0.129375}, {0.000000, -0.087450, -0.013648},
+                               {0.000001, -0.009023, -0.071752}, {0.000000, -0.041661, -0.009251}, {0.000000, -0.018585, -0.033462}};
+    const double lzg[NJ][3] = {{0.046358, 0.047354, 0.086000}, {0.046000, 0.135400, 0.047501}, {0.046000, 0.047501, 0.127000}, {0.046000, 0.133450, 0.042293},
+                               {0.034999, 0.044023, 0.069252}, {0.035000, 0.076739, 0.044076}, {0.045500, 0.056085, 0.030963}};
+    for (int i = 0; i < NJ; i++) {
+        m.axes[i] = axes[i];
+        m.mass[i] = mass[i]; m.armature[i] = armature[i]; m.damping[i] = 0.0; m.friction[i] = 0.0;
+        for (int a = 0; a < 3; a++) { m.com[i][a] = com[3 * i + a]; m.link_c[i][a] = lzc[i][a]; m.link_g[i][a] = lzg[i][a]; }
+        for (int a = 0; a < 9; a++) m.inertia[i][a] = inertia[9 * i + a];
+        m.state_lb[i] = lb[i]; m.state_ub[i] = ub[i]; m.speed[i] = speed[i]; m.torque[i] = torque[i];
+    }
+    for (int i = 0; i <= NJ; i++) for (int a = 0; a < 3; a++) m.trans[i][a] = trans[3 * i + a];
+    // fixed frame rotations from roll/pitch/yaw, host libm like the reference (KPR/PZsparse.cu:160-176); column-major
+    for (int i = 0; i <= NJ; i++) {
+        const double roll = i < NJ ? rots[3 * i] : 0.0, pitch = i < NJ ? rots[3 * i + 1] : 0.0, yaw = i < NJ ? rots[3 * i + 2] : 0.0;
+        double* R = m.R0[i];
+        R[0 + 3 * 0] = cos(pitch) * cos(yaw);
+        R[0 + 3 * 1] = -cos(pitch) * sin(yaw);
+        R[0 + 3 * 2] = sin(pitch);
+        R[1 + 3 * 0] = cos(roll) * sin(yaw) + cos(yaw) * sin(pitch) * sin(roll);
+        R[1 + 3 * 1] = cos(roll) * cos(yaw) - sin(pitch) * sin(roll) * sin(yaw);
+        R[1 + 3 * 2] = -cos(pitch) * sin(roll);
+        R[2 + 3 * 0] = sin(roll) * sin(yaw) - cos(roll) * cos(yaw) * sin(pitch);
+        R[2 + 3 * 1] = cos(yaw) * sin(roll) + cos(roll) * sin(pitch) * sin(yaw);
+        R[2 + 3 * 2] = cos(pitch) * cos(roll);
+    }
+    m.gravity = 9.81;
+    m.alpha = 10.0; m.M_max = 15.79635774; m.M_min = 5.095620491878957;
+    const double V_m = 1e-2, K = 5.0;
+    m.eps = sqrt(2 * V_m / m.M_min);
+    m.qe = m.eps / K; m.qde = 2 * m.eps; m.qdae = m.eps; m.qddae = 2 * K * m.eps;
+    m.qdd_k_maxima = (0.5 - sqrt(3) / 6); m.qdd_k_minima = (0.5 + sqrt(3) / 6);   // KPR/Trajectory.h:7-8
+    m.qdd_k_maxima_val = (60 * m.qdd_k_maxima * (2 * pow(m.qdd_k_maxima, 2) - 3 * m.qdd_k_maxima + 1)) / 1.0 / 1.0;   // Trajectory.cu:202
+    m.qdd_k_minima_val = (60 * m.qdd_k_minima * (2 * pow(m.qdd_k_minima, 2) - 3 * m.qdd_k_minima + 1)) / 1.0 / 1.0;   // Trajectory.cu:210
+}
+
+const double TORQUE_THRESHOLD = 1e-2, COLLISION_THRESHOLD = 1e-4, COST_SCALE = 10.0;   // KPR/Parameters.h:38-44
+
+double wrap_to_pi(double angle) {   // KPR/NLPclass.cu:6-15
+    double w = angle;
+    while (w < -M_PI) w += 2 * M_PI;
+    while (w > M_PI) w -= 2 * M_PI;
+    return w;
+}
+double q_des_host(double q0, double a, double b, double k, double t) {   // KPR/Trajectory.cu:542-556
+    const double B0 = -pow(t - 1, 5), B1 = 5 * t * pow(t - 1, 4), B2 = -10 * pow(t, 2) * pow(t - 1, 3);
+    const double B3 = 10 * pow(t, 3) * pow(t - 1, 2), B4 = -5 * pow(t, 4) * (t - 1), B5 = pow(t, 5);
+    const double b0 = q0, b1 = q0 + a / 5, b2 = q0 + (2 * a) / 5 + b / 20, b3 = q0 + k;
+    return B0 * b0 + B1 * b1 + B2 * b2 + B3 * b3 + B4 * b3 + B5 * b3;
+}
+
+template <class T>
+cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T) > 0 ? count * sizeof(T) : 16); }
+
+}  // namespace
+
+struct armour_handle {
+    armour_config cfg;
+    int device = 0, sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    RobotModel model;
+    Tables tb;
+    int P = 1, T = 128, max_obs = 40;
+    int mcap = 1024, ncap = 4096, nt = 256;
+    char* arena = nullptr;
+    size_t arena_stride = 0;
+    int grid = 0;
+    // device buffers
+    double *d_state = nullptr, *d_obs = nullptr, *d_x = nullptr, *d_g = nullptr, *d_jac = nullptr, *d_link_center = nullptr;
+    int* d_err = nullptr;
+    // pinned host buffers
+    double *h_state = nullptr, *h_obs = nullptr, *h_x = nullptr, *h_g = nullptr, *h_jac = nullptr, *h_torque_radius = nullptr;
+    int* h_err = nullptr;
+    // state
+    int count = 0, n_obs = 0, sel = 0;
+    bool built = false, have_eval = false;
+    double last_x[NF];
+    float build_ms = 0, reach_ms = 0, hyper_ms = 0, eval_ms = 0;
+    uint64_t launches = 0;
+    // lazy host mirrors for getters
+    bool mirror_valid = false;
+    std::vector<SmallRec> m_traj;
+    std::vector<int> m_un, m_ln;
+    std::vector<unsigned long long> m_ukeys, m_lkeys;
+    std::vector<double> m_ucoef, m_ucenter, m_uind, m_dist, m_lcoef, m_lcenter, m_lind;
+    // pz_binary scratch
+    char* bin_buf = nullptr;
+    size_t bin_bytes = 0;
+};
+
+namespace {
+
+int m_of(const armour_handle* h) { return NF * h->T + NJ * h->T * h->n_obs + NF * 4; }
+
+void free_arena(armour_handle* h) { if (h->arena) cudaFree(h->arena); h->arena = nullptr; }
+int alloc_arena(armour_handle* h) {
+    free_arena(h);
+    h->arena_stride = arena_bytes(h->mcap, h->ncap);
+    int per_sm = reach_max_ctas_per_sm(h->nt, h->ncap);
+    if (per_sm < 1) return fail(ARMOUR_E_CUDA, "reach_build_kernel does not fit on an SM with these capacities");
+    const int n_work = h->P * h->T;
+    h->grid = std::min(n_work, per_sm * h->sm_count);
+    CU(cudaMalloc((void**)&h->arena, h->arena_stride * (size_t)h->grid));
+    return ARMOUR_OK;
+}
+
+int run_build(armour_handle* h) {   // kernels only; inputs already on the device
+    const int n_work = h->count * h->T;
+    Tables tb = h->tb;
+    tb.P = h->count; tb.n_obs = h->n_obs;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        CU(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
+        CU(cudaEventRecord(h->ev[0], h->stream));
+        CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, n_work, std::min(h->grid, n_work), h->nt, h->stream));
+        CU(cudaEventRecord(h->ev[1], h->stream));
+        CU(launch_hyperplanes(tb, h->stream));
+        CU(cudaEventRecord(h->ev[2], h->stream));
+        h->launches += (h->n_obs > 0) ? 2 : 1;
+        CU(cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->h_torque_radius, h->tb.torque_radius, sizeof(double) * (size_t)h->count * h->T * NF, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        cudaEventElapsedTime(&h->reach_ms, h->ev[0], h->ev[1]);
+        cudaEventElapsedTime(&h->hyper_ms, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&h->build_ms, h->ev[0], h->ev[2]);
+        const int err = *h->h_err;
+        if (err == 0) { h->built = true; h->have_eval = false; h->mirror_valid = false; return ARMOUR_OK; }
+        if (err & (8 | 16)) return fail(ARMOUR_E_NUMERIC, "reach-set build: unexpected monomial structure (error word " + std::to_string(err) + ")");
+        if (err & 4) return fail(ARMOUR_E_CAPACITY, "k-only monomial table capacity exceeded (UCAP/LCAP)");
+        // monomial / entry capacity exceeded: grow and retry (documented in armour_b200.h)
+        if (err & 1) h->ncap = std::min(h->ncap * 2, 65535 & ~1023);
+        if (err & 2) h->mcap *= 2;
+        if (h->ncap < 2 * h->mcap) h->ncap = std::min(2 * h->mcap, 65535 & ~1023);
+        if (reach_smem_bytes(h->ncap) > 200 * 1024) return fail(ARMOUR_E_CAPACITY, "candidate list does not fit in shared memory");
+        int rc = alloc_arena(h);
+        if (rc != ARMOUR_OK) return rc;
+    }
+    return fail(ARMOUR_E_CAPACITY, "monomial capacities exceeded after retries");
+}
+
+int run_eval(armour_handle* h, const double* x, bool copy_back) {
+    if (!h->built) return fail(ARMOUR_E_STATE, "eval before build");
+    const int m = m_of(h);
+    if (x) {
+        memcpy(h->h_x, x, sizeof(double) * NF);
+        CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * NF, cudaMemcpyHostToDevice, h->stream));
+    }
+    Tables tb = h->tb;
+    tb.P = h->count; tb.n_obs = h->n_obs;
+    CU(cudaEventRecord(h->ev[3], h->stream));
+    CU(launch_constraint_eval(tb, h->sel, h->d_x, h->d_g, h->d_jac, h->d_link_center, h->stream));
+    CU(cudaEventRecord(h->ev[4], h->stream));
+    h->launches += 1;
+    if (copy_back) {
+        CU(cudaMemcpyAsync(h->h_g, h->d_g, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->h_jac, h->d_jac, sizeof(double) * (size_t)m * NF, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->eval_ms, h->ev[3], h->ev[4]);
+    if (x && copy_back) { memcpy(h->last_x, x, sizeof(double) * NF); h->have_eval = true; }
+    return ARMOUR_OK;
+}
+
+int ensure_mirror(armour_handle* h) {
+    if (h->mirror_valid) return ARMOUR_OK;
+    if (!h->built) return fail(ARMOUR_E_STATE, "tables requested before build");
+    const size_t T = h->T, p = h->sel;
+    h->m_traj.resize(T * TRAJ_TABLES * NJ);
+    h->m_un.resize(T * NF); h->m_ln.resize(T * NJ);
+    h->m_ukeys.resize(T * NF * UCAP); h->m_ucoef.resize(T * NF * UCAP); h->m_ucenter.resize(T * NF); h->m_uind.resize(T * NF); h->m_dist.resize(T * NF);
+    h->m_lkeys.resize(T * NJ * LCAP); h->m_lcoef.resize(T * NJ * 3 * LCAP); h->m_lcenter.resize(T * NJ * 3); h->m_lind.resize(T * NJ * 3);
+    const Tables& tb = h->tb;
+    CU(cudaMemcpy(h->m_traj.data(), tb.traj + p * T * TRAJ_TABLES * NJ, sizeof(SmallRec) * h->m_traj.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->m_un.data(), tb.u_n + p * T * NF, sizeof(int) * T * NF, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->m_ln.data(), tb.l_n + p * T * NJ, sizeof(int) * T * NJ, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->m_ukeys.data(), tb.u_keys + p * T * NF * UCAP, 8 * h->m_ukeys.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->m_ucoef.data(), tb.u_coef + p * T * NF * UCAP, 8 * h->m_ucoef.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->m_ucenter.data(), tb.u_center + p * T * NF, 8 * T * NF, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->m_uind.data(), tb.u_ind + p * T * NF, 8 * T * NF, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->m_dist.data(), tb.dist_rad + p * T * NF, 8 * T * NF, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->m_lkeys.data(), tb.l_keys + p * T * NJ * LCAP, 8 * h->m_lkeys.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->m_lcoef.data(), tb.l_coef + p * T * NJ * 3 * LCAP, 8 * h->m_lcoef.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->m_lcenter.data(), tb.l_center + p * T * NJ * 3, 8 * T * NJ * 3, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->m_lind.data(), tb.l_ind + p * T * NJ * 3, 8 * T * NJ * 3, cudaMemcpyDeviceToHost));
+    h->mirror_valid = true;
+    return ARMOUR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* armour_last_error(void) { return g_last_error.c_str(); }
+
+void armour_default_config(armour_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->num_time_steps = 128;
+    for (int i = 0; i < 7; i++) cfg->k_range[i] = M_PI / 48;
+    cfg->mass_uncertainty = 0.03;
+    cfg->inertia_uncertainty = 0.03;
+    cfg->simplify_threshold = 5e-4;
+    cfg->max_obstacles = 40;
+    cfg->max_monomials = 1024;
+    cfg->max_entries = 4096;
+    cfg->threads_per_cta = 256;
+    cfg->device = -1;
+    cfg->batch = 1;
+}
+
+int armour_create(const armour_config* cfg_in, armour_handle** out) {
+    if (!cfg_in || !out) return fail(ARMOUR_E_INVALID, "null argument");
+    armour_config cfg = *cfg_in;
+    if (cfg.num_time_steps <= 0 || (cfg.num_time_steps & 1)) return fail(ARMOUR_E_INVALID, "num_time_steps must be a positive even number");
+    if (cfg.max_obstacles < 0) return fail(ARMOUR_E_INVALID, "max_obstacles < 0");
+    if (cfg.max_monomials <= 0) cfg.max_monomials = 1024;
+    if (cfg.max_entries <= 0) cfg.max_entries = 4096;
+    if (cfg.threads_per_cta != 128 && cfg.threads_per_cta != 512) cfg.threads_per_cta = 256;
+    if (cfg.batch <= 0) cfg.batch = 1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ARMOUR_E_CUDA, "no CUDA device: this library has no CPU fallback");
+    armour_handle* h = new armour_handle();
+    h->cfg = cfg;
+    if (cfg.device >= 0) { if (cudaSetDevice(cfg.device) != cudaSuccess) { delete h; return fail(ARMOUR_E_CUDA, "cudaSetDevice failed"); } }
+    cudaGetDevice(&h->device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) { delete h; return fail(ARMOUR_E_CUDA, "cudaGetDeviceProperties failed"); }
+    h->sm_count = prop.multiProcessorCount;
+    h->P = cfg.batch; h->T = cfg.num_time_steps; h->max_obs = cfg.max_obstacles;
+    h->mcap = cfg.max_monomials; h->ncap = std::min(cfg.max_entries, 65535 & ~1023); h->nt = cfg.threads_per_cta;
+    kinova_model(h->model);
+    *out = h;   // so that armour_destroy can clean up after a partial failure
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) CU(cudaEventCreate(&e));
+    CU(upload_robot_model(h->model));
+    const size_t P = h->P, T = h->T, O = std::max(h->max_obs, 1);
+    Tables& tb = h->tb;
+    memset(&tb, 0, sizeof(tb));
+    tb.T = h->T; tb.P = h->P; tb.n_obs = 0;
+    for (int i = 0; i < NF; i++) tb.k_range[i] = cfg.k_range[i];
+    tb.mass_unc = cfg.mass_uncertainty; tb.inertia_unc = cfg.inertia_uncertainty; tb.thr = cfg.simplify_threshold;
+    CU(dalloc(&h->d_state, P * 21)); CU(dalloc(&h->d_obs, P * O * 12));
+    tb.state = h->d_state; tb.obstacles = h->d_obs;
+    CU(dalloc(&tb.traj, P * T * TRAJ_TABLES * NJ));
+    CU(dalloc(&tb.cos_rem, P * NJ * T * 2)); CU(dalloc(&tb.sin_rem, P * NJ * T * 2));
+    CU(dalloc(&tb.u_n, P * T * NF)); CU(dalloc(&tb.u_keys, P * T * NF * UCAP)); CU(dalloc(&tb.u_coef, P * T * NF * UCAP));
+    CU(dalloc(&tb.u_center, P * T * NF)); CU(dalloc(&tb.u_ind, P * T * NF)); CU(dalloc(&tb.dist_rad, P * T * NF)); CU(dalloc(&tb.torque_radius, P * T * NF));
+    CU(dalloc(&tb.l_n, P * T * NJ)); CU(dalloc(&tb.l_keys, P * T * NJ * LCAP)); CU(dalloc(&tb.l_coef, P * T * NJ * 3 * LCAP));
+    CU(dalloc(&tb.l_center, P * T * NJ * 3)); CU(dalloc(&tb.l_ind, P * T * NJ * 3)); CU(dalloc(&tb.gens, P * T * NJ * 18));
+    CU(dalloc(&tb.A, P * T * NJ * O * COMB * 3)); CU(dalloc(&tb.d, P * T * NJ * O * COMB)); CU(dalloc(&tb.delta, P * T * NJ * O * COMB));
+    CU(dalloc(&h->d_err, 1)); tb.err = h->d_err;
+    const size_t mmax = NF * T + NJ * T * O + NF * 4;
+    CU(dalloc(&h->d_x, NF)); CU(dalloc(&h->d_g, mmax)); CU(dalloc(&h->d_jac, mmax * NF)); CU(dalloc(&h->d_link_center, T * NJ * 3));
+    CU(cudaMallocHost((void**)&h->h_state, sizeof(double) * P * 21)); CU(cudaMallocHost((void**)&h->h_obs, sizeof(double) * P * O * 12));
+    CU(cudaMallocHost((void**)&h->h_x, sizeof(double) * NF)); CU(cudaMallocHost((void**)&h->h_g, sizeof(double) * mmax));
+    CU(cudaMallocHost((void**)&h->h_jac, sizeof(double) * mmax * NF)); CU(cudaMallocHost((void**)&h->h_torque_radius, sizeof(double) * P * T * NF));
+    CU(cudaMallocHost((void**)&h->h_err, sizeof(int)));
+    int rc = alloc_arena(h);
+    if (rc != ARMOUR_OK) return rc;
+    return ARMOUR_OK;
+}
+
+void armour_destroy(armour_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    Tables& tb = h->tb;
+    void* dev[] = {h->d_state, h->d_obs, tb.traj, tb.cos_rem, tb.sin_rem, tb.u_n, tb.u_keys, tb.u_coef, tb.u_center, tb.u_ind, tb.dist_rad, tb.torque_radius,
+                   tb.l_n, tb.l_keys, tb.l_coef, tb.l_center, tb.l_ind, tb.gens, tb.A, tb.d, tb.delta, h->d_err, h->d_x, h->d_g, h->d_jac, h->d_link_center, h->arena, h->bin_buf};
+    for (void* p : dev) if (p) cudaFree(p);
+    void* pinned[] = {h->h_state, h->h_obs, h->h_x, h->h_g, h->h_jac, h->h_torque_radius, h->h_err};
+    for (void* p : pinned) if (p) cudaFreeHost(p);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int armour_upload_problems(armour_handle* h, int count, const double* q0, const double* qd0, const double* qdd0, const double* obstacles, int n_obs) {
+    if (!h || !q0 || !qd0 || !qdd0) return fail(ARMOUR_E_INVALID, "null argument");
+    if (count < 1 || count > h->P) return fail(ARMOUR_E_INVALID, "count outside [1, cfg.batch]");
+    if (n_obs < 0 || n_obs > h->max_obs) return fail(ARMOUR_E_INVALID, "number of obstacles outside [0, max_obstacles]");   // KPR/armour_main.cu:66-72
+    if (n_obs > 0 && !obstacles) return fail(ARMOUR_E_INVALID, "null obstacles");
+    CU(cudaSetDevice(h->device));
+    for (int p = 0; p < count; p++)
+        for (int i = 0; i < NF; i++) { h->h_state[p * 21 + i] = q0[p * NF + i]; h->h_state[p * 21 + 7 + i] = qd0[p * NF + i]; h->h_state[p * 21 + 14 + i] = qdd0[p * NF + i]; }
+    if (n_obs > 0) memcpy(h->h_obs, obstacles, sizeof(double) * (size_t)count * n_obs * 12);
+    h->count = count; h->n_obs = n_obs; h->sel = 0; h->built = false; h->have_eval = false; h->mirror_valid = false;
+    CU(cudaMemcpyAsync(h->d_state, h->h_state, sizeof(double) * (size_t)count * 21, cudaMemcpyHostToDevice, h->stream));
+    if (n_obs > 0) CU(cudaMemcpyAsync(h->d_obs, h->h_obs, sizeof(double) * (size_t)count * n_obs * 12, cudaMemcpyHostToDevice, h->stream));
+    return ARMOUR_OK;
+}
+int armour_build_resident(armour_handle* h) {
+    if (!h || h->count < 1) return fail(ARMOUR_E_STATE, "no problems uploaded");
+    CU(cudaSetDevice(h->device));
+    return run_build(h);
+}
+int armour_build_batch(armour_handle* h, int count, const double* q0, const double* qd0, const double* qdd0, const double* obstacles, int n_obs) {
+    int rc = armour_upload_problems(h, count, q0, qd0, qdd0, obstacles, n_obs);
+    if (rc != ARMOUR_OK) return rc;
+    return run_build(h);
+}
+int armour_build(armour_handle* h, const double* q0, const double* qd0, const double* qdd0, const double* obstacles, int n_obs) {
+    return armour_build_batch(h, 1, q0, qd0, qdd0, obstacles, n_obs);
+}
+int armour_select_problem(armour_handle* h, int p) {
+    if (!h || !h->built) return fail(ARMOUR_E_STATE, "select before build");
+    if (p < 0 || p >= h->count) return fail(ARMOUR_E_INVALID, "problem index out of range");
+    h->sel = p; h->have_eval = false; h->mirror_valid = false;
+    return ARMOUR_OK;
+}
+
+int armour_get_nlp_info(armour_handle* h, int* n, int* m, int* nnz_jac_g, int* nnz_h_lag) {
+    if (!h || !n || !m || !nnz_jac_g || !nnz_h_lag) return fail(ARMOUR_E_INVALID, "null argument");
+    *n = NF; *m = m_of(h); *nnz_jac_g = *m * NF; *nnz_h_lag = 0;
+    return ARMOUR_OK;
+}
+int armour_get_bounds_info(armour_handle* h, double* x_l, double* x_u, double* g_l, double* g_u) {
+    if (!h || !x_l || !x_u || !g_l || !g_u) return fail(ARMOUR_E_INVALID, "null argument");
+    if (!h->built) return fail(ARMOUR_E_STATE, "bounds before build");
+    const RobotModel& rm = h->model;
+    const int T = h->T;
+    const double* tr = h->h_torque_radius + (size_t)h->sel * T * NF;
+    for (int i = 0; i < NF; i++) { x_l[i] = -1.0; x_u[i] = 1.0; }
+    int offset = 0;
+    for (int i = 0; i < T; i++)
+        for (int j = 0; j < NF; j++) { g_l[i * NF + j] = -rm.torque[j] + tr[i * NF + j]; g_u[i * NF + j] = rm.torque[j] - tr[i * NF + j]; }
+    offset += NF * T;
+    for (int i = offset; i < offset + T * NJ * h->n_obs; i++) { g_l[i] = -1e19; g_u[i] = 0; }
+    offset += T * NJ * h->n_obs;
+    for (int rep = 0; rep < 2; rep++) { for (int i = 0; i < NF; i++) { g_l[offset + i] = rm.state_lb[i] + rm.qe; g_u[offset + i] = rm.state_ub[i] - rm.qe; } offset += NF; }
+    for (int rep = 0; rep < 2; rep++) { for (int i = 0; i < NF; i++) { g_l[offset + i] = -rm.speed[i] + rm.qde; g_u[offset + i] = rm.speed[i] - rm.qde; } offset += NF; }
+    return ARMOUR_OK;
+}
+int armour_get_starting_point(armour_handle* h, double* x) {
+    if (!h || !x) return fail(ARMOUR_E_INVALID, "null argument");
+    for (int i = 0; i < NF; i++) x[i] = 0.0;
+    return ARMOUR_OK;
+}
+int armour_eval_f(armour_handle* h, const double* q_des, double t_plan, const double* x, double* obj_value) {
+    if (!h || !q_des || !x || !obj_value) return fail(ARMOUR_E_INVALID, "null argument");
+    if (h->count < 1) return fail(ARMOUR_E_STATE, "no problem");
+    const double* st = h->h_state + (size_t)h->sel * 21;
+    double qp[NF];
+    for (int i = 0; i < NF; i++) qp[i] = q_des_host(st[i], st[7 + i], st[14 + i], h->cfg.k_range[i] * x[i], t_plan);
+    double v = pow(wrap_to_pi(q_des[0] - qp[0]), 2) + pow(wrap_to_pi(q_des[2] - qp[2]), 2) + pow(wrap_to_pi(q_des[4] - qp[4]), 2) + pow(wrap_to_pi(q_des[6] - qp[6]), 2) +
+               pow(q_des[1] - qp[1], 2) + pow(q_des[3] - qp[3], 2) + pow(q_des[5] - qp[5], 2);
+    *obj_value = v * COST_SCALE;
+    return ARMOUR_OK;
+}
+int armour_eval_grad_f(armour_handle* h, const double* q_des, double t_plan, const double* x, double* grad_f) {
+    if (!h || !q_des || !x || !grad_f) return fail(ARMOUR_E_INVALID, "null argument");
+    if (h->count < 1) return fail(ARMOUR_E_STATE, "no problem");
+    const double* st = h->h_state + (size_t)h->sel * 21;
+    for (int i = 0; i < NF; i++) {
+        const double qp = q_des_host(st[i], st[7 + i], st[14 + i], h->cfg.k_range[i] * x[i], t_plan);
+        const double dk = pow(t_plan, 3) * (6 * pow(t_plan, 2) - 15 * t_plan + 10) * h->cfg.k_range[i];
+        grad_f[i] = (i % 2 == 0) ? (2 * wrap_to_pi(qp - q_des[i]) * dk) : (2 * (qp - q_des[i]) * dk);
+        grad_f[i] *= COST_SCALE;
+    }
+    return ARMOUR_OK;
+}
+int armour_eval_g_jac(armour_handle* h, const double* x, double* g, double* values) {
+    if (!h || !x) return fail(ARMOUR_E_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    if (!(h->have_eval && memcmp(h->last_x, x, sizeof(double) * NF) == 0)) {
+        int rc = run_eval(h, x, true);
+        if (rc != ARMOUR_OK) return rc;
+    }
+    const int m = m_of(h);
+    if (g) memcpy(g, h->h_g, sizeof(double) * m);
+    if (values) memcpy(values, h->h_jac, sizeof(double) * (size_t)m * NF);
+    return ARMOUR_OK;
+}
+int armour_eval_g(armour_handle* h, const double* x, double* g) { if (!g) return fail(ARMOUR_E_INVALID, "null argument"); return armour_eval_g_jac(h, x, g, nullptr); }
+int armour_eval_jac_g(armour_handle* h, const double* x, double* values) { if (!values) return fail(ARMOUR_E_INVALID, "null argument"); return armour_eval_g_jac(h, x, nullptr, values); }
+int armour_eval_resident(armour_handle* h, const double* x) {
+    if (!h) return fail(ARMOUR_E_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    return run_eval(h, x, false);
+}
+int armour_jac_structure(armour_handle* h, int* iRow, int* jCol) {
+    if (!h || !iRow || !jCol) return fail(ARMOUR_E_INVALID, "null argument");
+    const int m = m_of(h);
+    for (int i = 0; i < m; i++) for (int j = 0; j < NF; j++) { iRow[i * NF + j] = i; jCol[i * NF + j] = j; }
+    return ARMOUR_OK;
+}
+int armour_check_feasible(armour_handle* h, const double* g, int* feasible) {
+    if (!h || !g || !feasible) return fail(ARMOUR_E_INVALID, "null argument");
+    if (!h->built) return fail(ARMOUR_E_STATE, "feasibility check before build");
+    const RobotModel& rm = h->model;
+    const int T = h->T;
+    const double* tr = h->h_torque_radius + (size_t)h->sel * T * NF;
+    *feasible = 0;
+    int offset = 0;
+    for (int i = 0; i < T; i++)
+        for (int j = 0; j < NF; j++) {
+            const double r = tr[i * NF + j];
+            if (g[i * NF + j] < -rm.torque[j] + r - TORQUE_THRESHOLD || g[i * NF + j] > rm.torque[j] - r + TORQUE_THRESHOLD) return ARMOUR_OK;
+        }
+    offset += NF * T;
+    for (int i = 0; i < NJ; i++) for (int j = 0; j < T; j++) for (int o = 0; o < h->n_obs; o++)
+        if (g[(i * T + j) * h->n_obs + o + offset] > COLLISION_THRESHOLD) return ARMOUR_OK;
+    offset += NJ * T * h->n_obs;
+    for (int rep = 0; rep < 2; rep++) { for (int i = 0; i < NF; i++) if (g[offset + i] < rm.state_lb[i] + rm.qe || g[offset + i] > rm.state_ub[i] - rm.qe) return ARMOUR_OK; offset += NF; }
+    for (int rep = 0; rep < 2; rep++) { for (int i = 0; i < NF; i++) if (g[offset + i] < -rm.speed[i] + rm.qde || g[offset + i] > rm.speed[i] - rm.qde) return ARMOUR_OK; offset += NF; }
+    *feasible = 1;
+    return ARMOUR_OK;
+}
+
+int armour_get_torque_radius(armour_handle* h, double* out) {
+    if (!h || !out) return fail(ARMOUR_E_INVALID, "null argument");
+    if (!h->built) return fail(ARMOUR_E_STATE, "not built");
+    memcpy(out, h->h_torque_radius + (size_t)h->sel * h->T * NF, sizeof(double) * h->T * NF);
+    return ARMOUR_OK;
+}
+int armour_get_link_generators(armour_handle* h, double* out) {
+    if (!h || !out) return fail(ARMOUR_E_INVALID, "null argument");
+    if (!h->built) return fail(ARMOUR_E_STATE, "not built");
+    CU(cudaMemcpy(out, h->tb.gens + (size_t)h->sel * h->T * NJ * 18, sizeof(double) * h->T * NJ * 18, cudaMemcpyDeviceToHost));
+    return ARMOUR_OK;
+}
+int armour_get_link_sliced_center(armour_handle* h, double* out) {
+    if (!h || !out) return fail(ARMOUR_E_INVALID, "null argument");
+    if (!h->have_eval) return fail(ARMOUR_E_STATE, "no evaluation yet");
+    CU(cudaMemcpy(out, h->d_link_center, sizeof(double) * h->T * NJ * 3, cudaMemcpyDeviceToHost));
+    return ARMOUR_OK;
+}
+int armour_get_hyperplanes(armour_handle* h, double* A, double* d, double* delta) {
+    if (!h || !A || !d || !delta) return fail(ARMOUR_E_INVALID, "null argument");
+    if (!h->built) return fail(ARMOUR_E_STATE, "not built");
+    const size_t n = (size_t)h->T * NJ * h->n_obs * COMB, off = (size_t)h->sel * n;
+    if (n == 0) return ARMOUR_OK;
+    CU(cudaMemcpy(A, h->tb.A + off * 3, 8 * n * 3, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(d, h->tb.d + off, 8 * n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(delta, h->tb.delta + off, 8 * n, cudaMemcpyDeviceToHost));
+    return ARMOUR_OK;
+}
+int armour_get_taylor_remainders(armour_handle* h, double* cos_rem, double* sin_rem) {
+    if (!h || !cos_rem || !sin_rem) return fail(ARMOUR_E_INVALID, "null argument");
+    if (!h->built) return fail(ARMOUR_E_STATE, "not built");
+    const size_t n = (size_t)NJ * h->T * 2, off = (size_t)h->sel * n;
+    CU(cudaMemcpy(cos_rem, h->tb.cos_rem + off, 8 * n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(sin_rem, h->tb.sin_rem + off, 8 * n, cudaMemcpyDeviceToHost));
+    return ARMOUR_OK;
+}
+
+int armour_get_pz(armour_handle* h, int which, int idx, int t, int* dims, uint64_t* keys, double* coeffs, double* center, double* independent) {
+    if (!h) return fail(ARMOUR_E_INVALID, "null argument");
+    if (t < 0 || t >= h->T || idx < 0) return fail(ARMOUR_E_INVALID, "index out of range");
+    int rc = ensure_mirror(h);
+    if (rc != ARMOUR_OK) return rc;
+    const int T = h->T;
+    if (which >= 0 && which <= 6) {
+        if (which == 2 && idx == NJ) {   // R(NUM_JOINTS) = identity (KPR/Trajectory.cu:253)
+            if (dims) { dims[0] = 3; dims[1] = 3; }
+            for (int c = 0; c < 9; c++) { if (center) center[c] = h->model.R0[NJ][c]; if (independent) independent[c] = 0.0; }
+            return 0;
+        }
+        if (idx >= NJ) return fail(ARMOUR_E_INVALID, "joint index out of range");
+        const SmallRec& r = h->m_traj[((size_t)t * TRAJ_TABLES + which) * NJ + idx];
+        const int dim = r.dim;
+        if (dims) { dims[0] = dim == 9 ? 3 : 1; dims[1] = dim == 9 ? 3 : 1; }
+        for (int i = 0; i < r.n; i++) { if (keys) keys[i] = r.keys[i]; if (coeffs) for (int c = 0; c < dim; c++) coeffs[(size_t)i * dim + c] = r.coef[i][c]; }
+        for (int c = 0; c < dim; c++) { if (center) center[c] = r.center[c]; if (independent) independent[c] = r.ind[c]; }
+        return r.n;
+    }
+    if (idx >= NJ) return fail(ARMOUR_E_INVALID, "joint index out of range");
+    const size_t rec = (size_t)t * NJ + idx;
+    if (which == 7) {
+        const int n = h->m_ln[rec];
+        if (dims) { dims[0] = 3; dims[1] = 1; }
+        for (int i = 0; i < n; i++) { if (keys) keys[i] = h->m_lkeys[rec * LCAP + i]; if (coeffs) for (int c = 0; c < 3; c++) coeffs[(size_t)i * 3 + c] = h->m_lcoef[(rec * 3 + c) * LCAP + i]; }
+        for (int c = 0; c < 3; c++) { if (center) center[c] = h->m_lcenter[rec * 3 + c]; if (independent) independent[c] = h->m_lind[rec * 3 + c]; }
+        return n;
+    }
+    if (which == 8) {
+        const int n = h->m_un[rec];
+        if (dims) { dims[0] = 1; dims[1] = 1; }
+        for (int i = 0; i < n; i++) { if (keys) keys[i] = h->m_ukeys[rec * UCAP + i]; if (coeffs) coeffs[i] = h->m_ucoef[rec * UCAP + i]; }
+        if (center) center[0] = h->m_ucenter[rec];
+        if (independent) independent[0] = h->m_uind[rec];
+        return n;
+    }
+    if (which == 9) {   // u_nom_int - u_nom: the polynomial parts cancel exactly, only the radius survives
+        if (dims) { dims[0] = 1; dims[1] = 1; }
+        if (center) center[0] = 0.0;
+        if (independent) independent[0] = h->m_dist[rec];
+        return 0;
+    }
+    (void)T;
+    return fail(ARMOUR_E_INVALID, "unknown table");
+}
+
+int armour_pz_binary(armour_handle* h, int op,
+                     int a_rows, int a_cols, int a_n, const uint64_t* a_keys, const double* a_coeffs, const double* a_center, const double* a_independent,
+                     int b_rows, int b_cols, int b_n, const uint64_t* b_keys, const double* b_coeffs, const double* b_center, const double* b_independent,
+                     int cap, int* dims, uint64_t* keys, double* coeffs, double* center, double* independent) {
+    if (!h || !dims || !keys || !coeffs || !center || !independent || !a_center || !b_center || !a_independent || !b_independent) return fail(ARMOUR_E_INVALID, "null argument");
+    if (op < 0 || op > 3 || a_n < 0 || b_n < 0) return fail(ARMOUR_E_INVALID, "bad op");
+    CU(cudaSetDevice(h->device));
+    const int da = a_rows * a_cols, db = b_rows * b_cols;
+    const int rcap = std::max(cap, 1), ncap = h->ncap;
+    // layout of one staging buffer: A keys/coef/center/ind | B ... | R ... | out | tmp | err
+    auto pz_bytes = [](int n, int d) { return (size_t)std::max(n, 1) * 8 * (1 + d) + 18 * 8; };
+    const size_t need = pz_bytes(a_n, da) + pz_bytes(b_n, db) + pz_bytes(rcap, 9) + 64 + (size_t)9 * ncap * 8 + 64;
+    if (need > h->bin_bytes) { if (h->bin_buf) cudaFree(h->bin_buf); h->bin_buf = nullptr; CU(cudaMalloc((void**)&h->bin_buf, need)); h->bin_bytes = need; }
+    std::vector<char> host(need, 0);
+    char* base = h->bin_buf;
+    size_t off = 0;
+    auto place = [&](int n, int d, const uint64_t* k, const double* c, const double* cen, const double* ind, FlatPZ& f) {
+        const int capn = std::max(n, 1);
+        f.n = n; f.dim = d; f.cap = capn;
+        f.keys = (u64*)(base + off);
+        if (k) memcpy(host.data() + off, k, (size_t)n * 8);
+        off += (size_t)capn * 8;
+        f.coef = (double*)(base + off);
+        if (c) for (int i = 0; i < n; i++) for (int e = 0; e < d; e++) ((double*)(host.data() + off))[(size_t)e * capn + i] = c[(size_t)i * d + e];   // AoS -> SoA planes
+        off += (size_t)capn * 8 * d;
+        f.center = (double*)(base + off);
+        if (cen) memcpy(host.data() + off, cen, 8 * d);
+        off += 9 * 8;
+        f.ind = (double*)(base + off);
+        if (ind) memcpy(host.data() + off, ind, 8 * d);
+        off += 9 * 8;
+    };
+    FlatPZ fa, fb, fr;
+    place(a_n, da, a_keys, a_coeffs, a_center, a_independent, fa);
+    place(b_n, db, b_keys, b_coeffs, b_center, b_independent, fb);
+    const size_t r_off = off;
+    place(rcap, 9, nullptr, nullptr, nullptr, nullptr, fr);
+    fr.n = 0; fr.cap = rcap;
+    FlatOut* d_out = (FlatOut*)(base + off); const size_t out_off = off; off += 64;
+    double* d_tmp = (double*)(base + off); off += (size_t)9 * ncap * 8;
+    int* d_err = (int*)(base + off); const size_t err_off = off; off += 64;
+    CU(cudaMemcpyAsync(base, host.data(), need, cudaMemcpyHostToDevice, h->stream));
+    CU(launch_pz_binary(op, fa, fb, fr, d_out, d_tmp, ncap, h->cfg.simplify_threshold, d_err, h->stream));
+    h->launches += 1;
+    CU(cudaMemcpyAsync(host.data(), base, need, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const int err = *(int*)(host.data() + err_off);
+    const FlatOut o = *(FlatOut*)(host.data() + out_off);
+    if (err & 2) return fail(ARMOUR_E_CAPACITY, "result does not fit in cap");
+    if (err) return fail(ARMOUR_E_CAPACITY, "candidate list exceeds max_entries");
+    if (o.n < 0) return fail(ARMOUR_E_INVALID, "unsupported operand shapes");
+    const int d = o.dim;
+    dims[0] = d == 9 ? 3 : d; dims[1] = d == 9 ? 3 : 1;
+    const char* r = host.data() + r_off;
+    memcpy(keys, r, (size_t)o.n * 8);
+    const double* rc = (const double*)(r + (size_t)rcap * 8);
+    for (int i = 0; i < o.n; i++) for (int e = 0; e < d; e++) coeffs[(size_t)i * d + e] = rc[(size_t)e * rcap + i];
+    const double* rcen = (const double*)(r + (size_t)rcap * 8 * 10);
+    memcpy(center, rcen, 8 * d);
+    memcpy(independent, rcen + 9, 8 * d);
+    return o.n;
+}
+
+int armour_last_build_ms(armour_handle* h, float* total_ms, float* reach_kernel_ms, float* hyperplane_kernel_ms) {
+    if (!h) return fail(ARMOUR_E_INVALID, "null argument");
+    if (total_ms) *total_ms = h->build_ms;
+    if (reach_kernel_ms) *reach_kernel_ms = h->reach_ms;
+    if (hyperplane_kernel_ms) *hyperplane_kernel_ms = h->hyper_ms;
+    return ARMOUR_OK;
+}
+int armour_last_eval_ms(armour_handle* h, float* kernel_ms) {
+    if (!h || !kernel_ms) return fail(ARMOUR_E_INVALID, "null argument");
+    *kernel_ms = h->eval_ms;
+    return ARMOUR_OK;
+}
+int armour_kernel_launches(armour_handle* h, uint64_t* launches) {
+    if (!h || !launches) return fail(ARMOUR_E_INVALID, "null argument");
+    *launches = h->launches;
+    return ARMOUR_OK;
+}
+int armour_measure_fp64_peak(int device, double* tflops) {
+    if (!tflops) return fail(ARMOUR_E_INVALID, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ARMOUR_E_CUDA, "no CUDA device");
+    if (device >= 0) CU(cudaSetDevice(device));
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev));
+    *tflops = measure_fp64_tflops(prop.multiProcessorCount);
+    return *tflops > 0 ? ARMOUR_OK : fail(ARMOUR_E_CUDA, "fp64 micro-benchmark failed");
+}
+
+}  // extern "C"

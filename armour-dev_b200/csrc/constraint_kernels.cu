@@ -1,0 +1,310 @@
+// Constraint path kernels.
+//   hyperplane_kernel       Obstacles::initializeHyperPlane = bufferObstaclesKernel + polytope_PH
+//                           (KPR/CollisionChecking.cu:74-88, 136-228), one launch for all links
+//   constraint_eval_kernel  armtd_NLP::eval_g + eval_jac_g fused (KPR/NLPclass.cu:272-396):
+//                           PZsparse::slice value + gradient (KPR/PZsparse.cu:404-555) of the torque and
+//                           link PZs at k, checkCollisionKernel (KPR/CollisionChecking.cu:230-299) for all
+//                           seven links, and the joint position / velocity limit rows
+//                           (KPR/Trajectory.cu:256-540), one launch per Ipopt iteration.
+#include "armour_types.cuh"
+
+namespace armour {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+
+// pair (a, b), a < b, of the 9 buffered generators in the reference's enumeration order
+// (KPR/CollisionChecking.cu:26-39)
+__device__ __forceinline__ void pair_of(int p, int& a, int& b) {
+    int rem = p;
+    a = 0;
+    int row = 8;
+    while (rem >= row) { rem -= row; a++; row--; }
+    b = a + 1 + rem;
+}
+
+// one thread per (problem, t, link, obs, pair)
+__global__ void hyperplane_kernel(Tables tb) {
+    const size_t total = (size_t)tb.P * tb.T * NJ * tb.n_obs * COMB;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int p = (int)(idx % COMB);
+        size_t r = idx / COMB;
+        const int o = (int)(r % tb.n_obs); r /= tb.n_obs;
+        const int link = (int)(r % NJ); r /= NJ;
+        const int t = (int)(r % tb.T);
+        const int prob = (int)(r / tb.T);
+        const double* ob = tb.obstacles + ((size_t)prob * tb.n_obs + o) * 12;
+        const double* lg = tb.gens + (((size_t)prob * tb.T + t) * NJ + link) * 18;
+        // buffered generators: 3 obstacle generators then the link's 3x6 block (bufferObstaclesKernel)
+        auto gen = [&](int g, int a) -> double { return g < 3 ? ob[(g + 1) * 3 + a] : lg[(g - 3) * 3 + a]; };
+        int ia, ib;
+        pair_of(p, ia, ib);
+        double ga[3], gb[3];
+        for (int a = 0; a < 3; a++) { ga[a] = gen(ia, a); gb[a] = gen(ib, a); }
+        double cr[3];
+        cr[0] = dadd(dmul(ga[1], gb[2]), -dmul(ga[2], gb[1]));
+        cr[1] = dadd(dmul(ga[2], gb[0]), -dmul(ga[0], gb[2]));
+        cr[2] = dadd(dmul(ga[0], gb[1]), -dmul(ga[1], gb[0]));
+        const double nrm = __dsqrt_rn(dadd(dadd(dmul(cr[0], cr[0]), dmul(cr[1], cr[1])), dmul(cr[2], cr[2])));
+        double C[3] = {0, 0, 0};
+        if (nrm > 0) for (int a = 0; a < 3; a++) C[a] = __ddiv_rn(cr[a], nrm);
+        tb.A[idx * 3 + 0] = C[0]; tb.A[idx * 3 + 1] = C[1]; tb.A[idx * 3 + 2] = C[2];
+        tb.d[idx] = dadd(dadd(dmul(C[0], ob[0]), dmul(C[1], ob[1])), dmul(C[2], ob[2]));
+        double dl = 0.0;
+        for (int j = 0; j < 9; j++) dl = dadd(dl, fabs(dadd(dadd(dmul(C[0], gen(j, 0)), dmul(C[1], gen(j, 1))), dmul(C[2], gen(j, 2)))));
+        tb.delta[idx] = dl;
+    }
+}
+
+// ---- Bezier curve pieces used by the limit rows (KPR/Trajectory.cu:542-599) -----------------------
+__device__ double q_des_func(double q0, double a, double b, double k, double t) {
+    const double tm = t - 1, tm2 = tm * tm, tm3 = tm2 * tm, tm4 = tm2 * tm2, tm5 = tm4 * tm;
+    const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2, t5 = t4 * t;
+    const double B0 = -tm5, B1 = 5 * t * tm4, B2 = -10 * t2 * tm3, B3 = 10 * t3 * tm2, B4 = -5 * t4 * tm, B5 = t5;
+    const double b0 = q0, b1 = q0 + a / 5, b2 = q0 + (2 * a) / 5 + b / 20, b3 = q0 + k;
+    return B0 * b0 + B1 * b1 + B2 * b2 + B3 * b3 + B4 * b3 + B5 * b3;
+}
+__device__ double qd_des_func(double q0, double a, double b, double k, double t) {
+    const double tm = t - 1.0, tm2 = tm * tm, tm3 = tm2 * tm, tm4 = tm2 * tm2;
+    const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2;
+    const double dB0 = tm4 * -5.0;
+    const double dB1 = t * tm3 * 2.0E+1 + tm4 * 5.0;
+    const double dB2 = t * tm3 * -2.0E+1 - t2 * tm2 * 3.0E+1;
+    const double dB3 = t3 * (t * 2.0 - 2.0) * 1.0E+1 + t2 * tm2 * 3.0E+1;
+    const double dB4 = t3 * tm * -2.0E+1 - t4 * 5.0;
+    const double dB5 = t4 * 5.0;
+    const double b0 = q0, b1 = q0 + a / 5, b2 = q0 + (2 * a) / 5 + b / 20, b3 = q0 + k;
+    return dB0 * b0 + dB1 * b1 + dB2 * b2 + dB3 * b3 + dB4 * b3 + dB5 * b3;
+}
+__device__ double qdd_des_func(double q0, double a, double b, double k, double t) {
+    const double t3 = t * t, t4 = t3 * t, t5 = t - 1.0, t6 = t * 2.0 - 2.0, t7 = t4 * 2.0E+1, t8 = t5 * t5, t9 = t8 * t5;
+    const double t11 = t * t8 * 6.0E+1, t12 = -(t9 * 2.0E+1);
+    const double ddB0 = t12, ddB1 = t9 * 4.0E+1 + t11, ddB2 = t12 - t * t8 * 1.2E+2 - t3 * t6 * 3.0E+1;
+    const double ddB3 = t7 + t11 + t3 * t6 * 6.0E+1, ddB4 = t4 * -4.0E+1 - t3 * t5 * 6.0E+1, ddB5 = t7;
+    const double b0 = q0, b1 = q0 + a / 5, b2 = q0 + (2 * a) / 5 + b / 20, b3 = q0 + k;
+    return ddB0 * b0 + ddB1 * b1 + ddB2 * b2 + ddB3 * b3 + ddB4 * b3 + ddB5 * b3;
+}
+
+// min / max of q_des (velocity = false) or qd_des (true) over t in [0,1] and the k-derivative of the
+// selected branch (returnJoint{Position,Velocity}Extremum[Gradient], KPR/Trajectory.cu:256-540).
+// The reference's generated derivative expressions (:601-810) are the total derivative of the value at
+// the interior stationary point t*(k); here that is evaluated as  d/dk = dF/dk|_t + dF/dt * dt*/dk.
+__device__ void joint_extremum(double q0, double a, double b, double k, bool velocity, double* mn, double* mx, double* gmn, double* gmx) {
+    double e2, e3, de2, de3;
+    const double den = 6 * a - 12 * k + b;
+    if (!velocity) {
+        const double D = 64 * (a * a) + 14 * a * b - 120 * k * a + (b * b);
+        const double rt = sqrt(D);
+        const double n2 = 2 * a + b + rt, n3 = 2 * a + b - rt;
+        e2 = n2 / (5 * den); e3 = n3 / (5 * den);
+        const double drt = -60 * a / rt;   // d sqrt(D) / dk
+        de2 = (drt * den + 12 * n2) / (5 * den * den);
+        de3 = (-drt * den + 12 * n3) / (5 * den * den);
+    }
+    else {
+        const double E = 150 * (k * k) - 180 * k * a - 20 * k * b + 54 * (a * a) + 14 * a * b + (b * b);
+        const double rt = sqrt(6 * E);
+        const double n2 = 18 * a - 30 * k + 4 * b + rt, n3 = 18 * a - 30 * k + 4 * b - rt;
+        e2 = n2 / (10 * den); e3 = n3 / (10 * den);
+        const double drt = 3 * (300 * k - 180 * a - 20 * b) / rt;   // d sqrt(6E) / dk
+        de2 = ((-30 + drt) * den + 12 * n2) / (10 * den * den);
+        de3 = ((-30 - drt) * den + 12 * n3) / (10 * den * den);
+    }
+    const double v1 = velocity ? qd_des_func(q0, a, b, k, 0.0) : q_des_func(q0, a, b, k, 0.0);
+    const double v2 = velocity ? qd_des_func(q0, a, b, k, e2) : q_des_func(q0, a, b, k, e2);
+    const double v3 = velocity ? qd_des_func(q0, a, b, k, e3) : q_des_func(q0, a, b, k, e3);
+    const double v4 = velocity ? qd_des_func(q0, a, b, k, 1.0) : q_des_func(q0, a, b, k, 1.0);
+    double vmn, vmx; int imn, imx;
+    if (v1 < v4) { vmn = v1; imn = 1; vmx = v4; imx = 4; } else { vmn = v4; imn = 4; vmx = v1; imx = 1; }
+    if (0 <= e2 && e2 <= 1) { if (v2 < vmn) { vmn = v2; imn = 2; } if (vmx < v2) { vmx = v2; imx = 2; } }
+    if (0 <= e3 && e3 <= 1) { if (v3 < vmn) { vmn = v3; imn = 3; } if (vmx < v3) { vmx = v3; imx = 3; } }
+    auto dk = [&](int id) -> double {
+        if (id == 1) return 0.0;
+        if (id == 4) return 1.0;
+        const double t = (id == 2) ? e2 : e3, dt = (id == 2) ? de2 : de3;
+        const double tm = t - 1.0, t2 = t * t;
+        if (!velocity) {
+            const double dFdk = 10 * t2 * t * tm * tm - 5 * t2 * t2 * tm + t2 * t2 * t;   // B3 + B4 + B5
+            return dFdk + qd_des_func(q0, a, b, k, t) * dt;
+        }
+        const double dFdk = (t2 * t * (t * 2.0 - 2.0) * 10.0 + t2 * tm * tm * 30.0) + (t2 * t * tm * -20.0 - t2 * t2 * 5.0) + t2 * t2 * 5.0;
+        return dFdk + qdd_des_func(q0, a, b, k, t) * dt;
+    };
+    *mn = vmn; *mx = vmx; *gmn = dk(imn); *gmx = dk(imx);
+}
+
+// x^d for d in 0..3 the way std::pow returns it for these exponents (exact products of x)
+__device__ __forceinline__ double powi(double x, int d) { return d == 0 ? 1.0 : d == 1 ? x : d == 2 ? x * x : x * x * x; }
+
+// term and k-gradient of one k-only monomial at x (PZsparse::slice, KPR/PZsparse.cu:404-555):
+//   value:   coeff * prod_j pow(x_j, d_j)            (multiplied in j order)
+//   grad[k]: coeff * prod_j (j == k ? d_j pow(x_j, d_j - 1) : pow(x_j, d_j)),  0 when d_k == 0
+__device__ __forceinline__ double slice_term(double coef, u64 key, const double* x, int which) {
+    double r = coef;
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        const int d = (int)((key >> (2 * j)) & 3);
+        if (j == which) {
+            if (d == 0) r = 0.0;
+            else r = r * ((double)d * powi(x[j], d - 1));
+        }
+        else r = r * powi(x[j], d);
+    }
+    return r;
+}
+
+constexpr int EVAL_NT = 256;
+// grid: P_sel * (T * NJ + 1) blocks for the selected problem: block (t, j) handles torque row (t, j), link j
+// at interval t against every obstacle; the extra block handles the 28 limit rows.
+__global__ void __launch_bounds__(EVAL_NT) constraint_eval_kernel(Tables tb, int prob, const double* __restrict__ xdev, double* __restrict__ g, double* __restrict__ jac,
+                                                                  double* __restrict__ link_center_out) {
+    __shared__ double x[NF];
+    __shared__ double terms[24][LCAP];      // link: 3 values + 21 gradients per monomial; torque rows reuse [0..7][UCAP/...]
+    __shared__ double uterms[8][UCAP];
+    __shared__ double lc[3], ldk[NF][3];
+    const int T = tb.T, n_obs = tb.n_obs;
+    const int tid = threadIdx.x;
+    if (tid < NF) x[tid] = xdev[tid];
+    __syncthreads();
+    const int blk = blockIdx.x;
+    const size_t off_obs = (size_t)NF * T, off_lim = off_obs + (size_t)NJ * T * n_obs;
+    if (blk == T * NJ) {   // limit rows (KPR/NLPclass.cu:319-320, 393-394)
+        if (tid < 2 * NF) {
+            const int i = tid % NF;
+            const bool velocity = tid >= NF;
+            const double* st = tb.state + (size_t)prob * 21;
+            const double kr = tb.k_range[i];
+            double mn, mx, gmn, gmx;
+            joint_extremum(st[i], st[7 + i], st[14 + i], kr * x[i], velocity, &mn, &mx, &gmn, &gmx);
+            const size_t r0 = off_lim + (velocity ? 2 * NF : 0) + i, r1 = r0 + NF;
+            g[r0] = mn; g[r1] = mx;   // DURATION == 1
+            for (int j = 0; j < NF; j++) { jac[r0 * NF + j] = (i == j) ? gmn * kr : 0.0; jac[r1 * NF + j] = (i == j) ? gmx * kr : 0.0; }
+        }
+        return;
+    }
+    const int t = blk / NJ, j = blk - t * NJ;
+    const size_t rec = ((size_t)prob * T + t) * NJ + j;
+    // ---- torque row ------------------------------------------------------------------------------
+    const int un = tb.u_n[rec];
+    for (int e = tid; e < un * 8; e += EVAL_NT) {
+        const int m = e >> 3, w = e & 7;
+        uterms[w][m] = slice_term(tb.u_coef[rec * UCAP + m], tb.u_keys[rec * UCAP + m], x, w == 0 ? -1 : w - 1);
+    }
+    // ---- link slice ------------------------------------------------------------------------------
+    const int ln = tb.l_n[rec];
+    for (int e = tid; e < ln * 24; e += EVAL_NT) {
+        const int m = e / 24, w = e - m * 24;
+        const int c = w % 3, which = w / 3;   // which 0: value, 1..7: d/dk_{which-1}
+        terms[w][m] = slice_term(tb.l_coef[(rec * 3 + c) * LCAP + m], tb.l_keys[rec * LCAP + m], x, which - 1);
+    }
+    __syncthreads();
+    if (tid < 8) {   // sequential sums in key order, like the reference's loop over the monomial list
+        double s = (tid == 0) ? tb.u_center[rec] : 0.0;
+        for (int m = 0; m < un; m++) s = s + uterms[tid][m];
+        const size_t row = (size_t)t * NF + j;
+        if (tid == 0) {
+            const double r = tb.u_ind[rec];
+            g[row] = ((s - r) + (s + r)) * 0.5;   // getCenter(Interval(c - r, c + r))
+        }
+        else jac[row * NF + (tid - 1)] = s;
+    }
+    else if (tid >= 32 && tid < 32 + 24) {
+        const int w = tid - 32, c = w % 3, which = w / 3;
+        double s = (which == 0) ? tb.l_center[rec * 3 + c] : 0.0;
+        for (int m = 0; m < ln; m++) s = s + terms[w][m];
+        if (which == 0) {
+            const double r = tb.l_ind[rec * 3 + c];
+            const double v = ((s - r) + (s + r)) * 0.5;
+            lc[c] = v;
+            if (link_center_out) link_center_out[((size_t)t * NJ + j) * 3 + c] = v;
+        }
+        else ldk[which - 1][c] = s;
+    }
+    __syncthreads();
+    // ---- obstacle rows: one warp per obstacle (checkCollisionKernel) ---------------------------------
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int o = warp; o < n_obs; o += EVAL_NT / 32) {
+        const size_t base = (rec * n_obs + o) * COMB;
+        double best = -100000000.0;
+        int best_e = 0x7fffffff;   // order index 2*pair + (neg ? 1 : 0): the reference scans pos_0, neg_0, pos_1, ... and keeps the first maximum
+        for (int p = lane; p < COMB; p += 32) {
+            const double a0 = tb.A[(base + p) * 3], a1 = tb.A[(base + p) * 3 + 1], a2 = tb.A[(base + p) * 3 + 2];
+            double pos = -100000000.0, neg = -100000000.0;
+            if (__dsqrt_rn(dadd(dadd(dmul(a0, a0), dmul(a1, a1)), dmul(a2, a2))) > 0) {
+                const double dot = dadd(dadd(dmul(a0, lc[0]), dmul(a1, lc[1])), dmul(a2, lc[2]));
+                const double dd = tb.d[base + p], dl = tb.delta[base + p];
+                pos = dadd(dot, -dadd(dd, dl));
+                neg = dadd(-dot, -dadd(-dd, dl));
+            }
+            if (pos > best) { best = pos; best_e = 2 * p; }
+            if (neg > best) { best = neg; best_e = 2 * p + 1; }
+        }
+        // lanes whose candidates never beat the sentinel keep best_e = INT_MAX; the reference's thread 0 then
+        // reports max_id 0 / pos, i.e. order index 0
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, sft);
+            const int oe = __shfl_xor_sync(0xffffffffu, best_e, sft);
+            if (ob > best || (ob == best && oe < best_e)) { best = ob; best_e = oe; }
+        }
+        if (best_e == 0x7fffffff) best_e = 0;
+        const size_t row = off_obs + ((size_t)j * T + t) * n_obs + o;
+        if (lane == 0) g[row] = -best;
+        if (lane < NF) {
+            const int p = best_e >> 1;
+            const bool neg = best_e & 1;
+            const double a0 = tb.A[(base + p) * 3], a1 = tb.A[(base + p) * 3 + 1], a2 = tb.A[(base + p) * 3 + 2];
+            const double dot = dadd(dadd(dmul(a0, ldk[lane][0]), dmul(a1, ldk[lane][1])), dmul(a2, ldk[lane][2]));
+            jac[row * NF + lane] = neg ? dot : -dot;
+        }
+    }
+}
+
+cudaError_t launch_hyperplanes(const Tables& tb, cudaStream_t stream) {
+    const size_t total = (size_t)tb.P * tb.T * NJ * tb.n_obs * COMB;
+    if (total == 0) return cudaSuccess;
+    const int nt = 288;
+    const int grid = (int)((total + nt - 1) / nt);
+    hyperplane_kernel<<<grid, nt, 0, stream>>>(tb);
+    return cudaGetLastError();
+}
+cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* xdev, double* g, double* jac, double* link_center, cudaStream_t stream) {
+    constraint_eval_kernel<<<tb.T * NJ + 1, EVAL_NT, 0, stream>>>(tb, prob, xdev, g, jac, link_center);
+    return cudaGetLastError();
+}
+
+// ---- fp64 FMA micro-benchmark: denominator of the fp64 roofline -----------------------------------------
+__global__ void fp64_fma_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+double measure_fp64_tflops(int sm_count) {
+    const int nt = 512, grid = sm_count * 4, iters = 1 << 14;
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * nt * grid) != cudaSuccess) return -1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    fp64_fma_kernel<<<grid, nt>>>(out, iters);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int r = 0; r < 5; r++) {
+        cudaEventRecord(e0);
+        fp64_fma_kernel<<<grid, nt>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    const double flops = 2.0 * 8 * (double)iters * nt * grid;
+    return flops / (best * 1e-3) / 1e12;
+}
+
+}  // namespace armour

@@ -1,0 +1,630 @@
+// Reach-set build kernel: one CTA per (problem, time interval).
+//
+// Stages, all on the device, for one interval s of one planning problem:
+//   A  joint reach sets as PZs      BezierCurve::BezierCurve + makePolyZono   KPR/Trajectory.cu:15-254
+//   B  PZ forward kinematics        KinematicsDynamics::fk                     KPR/Dynamics.cu:69-81
+//      + reduce_link_PZ                                                        KPR/PZsparse.cu:370-402
+//   C  PZ-RNEA                      KinematicsDynamics::rnea                   KPR/Dynamics.cu:83-181
+//      The reference runs it twice (nominal / +-3 % inertial parameters, KPR/armour_main.cu:129-132).
+//      Centres and monomials of the two runs are identical — the uncertainty only enters the interval
+//      radius (KPR/PZsparse.cu:93-98, 944-989) — so one pass carries two radii.
+//   M  disturbance radius, reduce(), torque radius                             KPR/armour_main.cu:135-205
+// The half-space tables (stage D) are built by hyperplane_kernel in constraint_kernels.cu.
+#include "armour_launch.h"
+#include "pz_engine.cuh"
+
+namespace armour {
+
+__constant__ RobotModel c_robot;
+
+// ---------------------------------------------------------------------------------------------
+// Directed-rounding interval arithmetic (replaces boost::numeric::interval with
+// rounded_transc_std<double>, KPR/Headers.h:30-36).  cos/sin endpoints are widened outward so the
+// device enclosure contains the host libm one whatever the last-bit differences.
+// ---------------------------------------------------------------------------------------------
+struct Itv { double lo, hi; };
+__device__ __forceinline__ Itv itv(double l, double h) { Itv r; r.lo = l; r.hi = h; return r; }
+__device__ __forceinline__ Itv iadd(Itv a, Itv b) { return itv(__dadd_rd(a.lo, b.lo), __dadd_ru(a.hi, b.hi)); }
+__device__ __forceinline__ Itv iadd(double a, Itv b) { return itv(__dadd_rd(a, b.lo), __dadd_ru(a, b.hi)); }
+__device__ __forceinline__ Itv isub(Itv a, Itv b) { return itv(__dadd_rd(a.lo, -b.hi), __dadd_ru(a.hi, -b.lo)); }
+__device__ __forceinline__ Itv isub(Itv a, double b) { return itv(__dadd_rd(a.lo, -b), __dadd_ru(a.hi, -b)); }
+__device__ __forceinline__ Itv ineg(Itv a) { return itv(-a.hi, -a.lo); }
+__device__ __forceinline__ Itv imul(double x, Itv y) {
+    if (x < 0) return itv(__dmul_rd(x, y.hi), __dmul_ru(x, y.lo));
+    if (x == 0) return itv(0.0, 0.0);
+    return itv(__dmul_rd(x, y.lo), __dmul_ru(x, y.hi));
+}
+__device__ __forceinline__ Itv imul(Itv x, Itv y) {
+    const double l = fmin(fmin(__dmul_rd(x.lo, y.lo), __dmul_rd(x.lo, y.hi)), fmin(__dmul_rd(x.hi, y.lo), __dmul_rd(x.hi, y.hi)));
+    const double u = fmax(fmax(__dmul_ru(x.lo, y.lo), __dmul_ru(x.lo, y.hi)), fmax(__dmul_ru(x.hi, y.lo), __dmul_ru(x.hi, y.hi)));
+    return itv(l, u);
+}
+__device__ __forceinline__ Itv ipow2(Itv x) {
+    if (x.hi < 0) return itv(__dmul_rd(-x.hi, -x.hi), __dmul_ru(-x.lo, -x.lo));
+    if (x.lo < 0) { const double m = fmax(-x.lo, x.hi); return itv(0.0, __dmul_ru(m, m)); }
+    return itv(__dmul_rd(x.lo, x.lo), __dmul_ru(x.hi, x.hi));
+}
+// outward widening of a device libm value: CUDA cos/sin are within 2 ulp, glibc within 1 ulp of the true
+// value, and the argument itself may differ from the host's by an ulp; 2^-50 relative + 2^-50 absolute
+// covers all three with margin and is ~1e-15, far inside the 1e-9 tolerance on radii.
+__device__ __forceinline__ double widen_dn(double v) { return fmax(-1.0, __dadd_rd(__dadd_rd(v, -fabs(v) * 0x1p-50), -0x1p-50)); }
+__device__ __forceinline__ double widen_up(double v) { return fmin(1.0, __dadd_ru(__dadd_ru(v, fabs(v) * 0x1p-50), 0x1p-50)); }
+__device__ __forceinline__ Itv point_trig(double v) { return itv(widen_dn(v), widen_up(v)); }
+
+#define PI_LO 0x1.921fb54442d18p+1
+#define PI_HI 0x1.921fb54442d19p+1
+#define PI_HALF_LO 0x1.921fb54442d18p+0
+#define PI_HALF_HI 0x1.921fb54442d19p+0
+#define PI2_LO 0x1.921fb54442d18p+2
+#define PI2_HI 0x1.921fb54442d19p+2
+
+__device__ Itv icos(Itv x, int depth = 0) {   // boost::numeric::cos(interval), restated in oracle/oracle_pz.hpp
+    const double yb = (x.lo < 0) ? PI2_LO : PI2_HI;
+    const double n = floor(__ddiv_rd(x.lo, yb));
+    const Itv tmp = isub(x, imul(n, itv(PI2_LO, PI2_HI)));
+    if (__dadd_ru(tmp.hi, -tmp.lo) >= PI2_LO) return itv(-1.0, 1.0);
+    if (tmp.lo >= PI_HI) {   // -cos(tmp - pi); the shifted argument starts below pi, so this recurses once
+        if (depth > 2) return itv(-1.0, 1.0);
+        return ineg(icos(isub(tmp, itv(PI_LO, PI_HI)), depth + 1));
+    }
+    const double l = tmp.lo, u = tmp.hi;
+    if (u <= PI_LO) return itv(widen_dn(cos(u)), widen_up(cos(l)));
+    if (u <= PI2_LO) return itv(-1.0, widen_up(cos(fmin(__dadd_rd(PI2_LO, -u), l))));
+    return itv(-1.0, 1.0);
+}
+__device__ __forceinline__ Itv isin(Itv x) { return icos(isub(x, itv(PI_HALF_LO, PI_HALF_HI))); }
+
+// ---- Bezier pieces (KPR/Trajectory.cu:812-822), expression order preserved ------------------
+__device__ __forceinline__ double q_des_k_indep(double q0, double a, double b, double s) {
+    const double s2 = s * s, s3 = s2 * s, s4 = s2 * s2, s5 = s4 * s;
+    return q0 + a * s - 6 * a * s3 + 8 * a * s4 - 3 * a * s5 + (b * s2) * 0.5 - (3 * b * s3) * 0.5 + (3 * b * s4) * 0.5 - (b * s5) * 0.5;
+}
+__device__ __forceinline__ double qd_des_k_indep(double a, double b, double s) {
+    const double sm1 = s - 1, s2 = s * s;
+    return ((sm1 * sm1) * (2 * a + 4 * a * s + 2 * b * s - 30 * a * s2 - 5 * b * s2)) * 0.5;
+}
+__device__ __forceinline__ double qdd_des_k_indep(double a, double b, double s) {
+    return -(s - 1.0) * (b - (36 * a + 8 * b) * s + (60 * a + 10 * b) * (s * s));
+}
+__device__ __forceinline__ void bound_k_indep(double lbv, double ubv, double s_lb, double s_ub, double e1, double v1, double e2, double v2, double& lo, double& hi) {
+    lo = lbv; hi = ubv;
+    if (lo > hi) { const double t = lo; lo = hi; hi = t; }
+    if (s_lb < e1 && e1 < s_ub) { lo = fmin(lo, v1); hi = fmax(hi, v1); }
+    if (s_lb < e2 && e2 < s_ub) { lo = fmin(lo, v2); hi = fmax(hi, v2); }
+}
+
+// scalar PZ from (centre, {k_i: c0, key1: c1}) with simplify()  (KPR/PZsparse.cu:120-136)
+__device__ void small_scalar(PZ<1>& z, double center, u64 k0, double c0, u64 k1, double c1, double thr) {
+    int n = 0;
+    double ind = 0.0, abss = 0.0;
+    if (norm1(&c0) > thr) { z.keys[n] = k0; z.coef[n] = c0; abss = __dadd_ru(abss, fabs(c0)); n++; } else ind = __dadd_ru(ind, fabs(c0));
+    if (norm1(&c1) > thr) { z.keys[n] = k1; z.coef[n] = c1; abss = __dadd_ru(abss, fabs(c1)); n++; } else ind = __dadd_ru(ind, fabs(c1));
+    z.n = n; z.center[0] = center; z.ind[0][0] = ind; z.ind[1][0] = ind; z.abss[0] = abss;
+}
+template <int D>
+__device__ void export_small(SmallRec& r, const PZ<D>& z) {
+    r.n = z.n; r.dim = D;
+    for (int i = 0; i < z.n && i < SMALL_CAP; i++) { r.keys[i] = z.keys[i]; for (int c = 0; c < D; c++) r.coef[i][c] = z.coef[c * z.cap + i]; }
+    for (int c = 0; c < D; c++) { r.center[c] = z.center[c]; r.ind[c] = z.ind[0][c]; }
+}
+
+// joint i, interval s: everything makePolyZono produces for that joint (KPR/Trajectory.cu:63-254)
+__device__ void make_poly_zono_joint(const Tables& tb, int prob, int s, int i, PZ<9>& R, PZ<9>& Rt, PZ<1>& qd, PZ<1>& qda, PZ<1>& qdda,
+                                     PZ<1>& cosq, PZ<1>& sinq, double thr) {
+    const RobotModel& rm = c_robot;
+    const double* st = tb.state + (size_t)prob * 21;
+    const double q0 = st[i], a = st[7 + i] * 1.0, b = st[14 + i] * 1.0 * 1.0;   // Tqd0, TTqdd0 with DURATION = 1
+    const double ds = 1.0 / tb.T;
+    const double s_lb = s * ds, s_ub = (s + 1) * ds;
+    const double kr = tb.k_range[i];
+    // k-independent stationary points (BezierCurve ctor, Trajectory.cu:36-58)
+    double ext[6], extv[6];
+    {
+        const double den5 = 5 * (6 * a + b), den10 = 10 * (6 * a + b);
+        const double r1 = sqrt(64 * (a * a) + 14 * a * b + (b * b));
+        ext[0] = (2 * a + b + r1) / den5; ext[1] = (2 * a + b - r1) / den5;
+        const double r2 = sqrt(6 * (54 * (a * a) + 14 * a * b + (b * b)));
+        ext[2] = (18 * a + 4 * b + r2) / den10; ext[3] = (18 * a + 4 * b - r2) / den10;
+        const double r3 = sqrt(2 * (152 * (a * a) + 42 * a * b + 3 * (b * b)));
+        ext[4] = (32 * a + 6 * b + r3) / den10; ext[5] = (32 * a + 6 * b - r3) / den10;
+        extv[0] = q_des_k_indep(q0, a, b, ext[0]); extv[1] = q_des_k_indep(q0, a, b, ext[1]);
+        extv[2] = qd_des_k_indep(a, b, ext[2]); extv[3] = qd_des_k_indep(a, b, ext[3]);
+        extv[4] = qdd_des_k_indep(a, b, ext[4]); extv[5] = qdd_des_k_indep(a, b, ext[5]);
+    }
+    // Part 1: q_des
+    const double sl2 = s_lb * s_lb, sl3 = sl2 * s_lb, su2 = s_ub * s_ub, su3 = su2 * s_ub;
+    double kd_lb = sl3 * (6 * sl2 - 15 * s_lb + 10);
+    double kd_ub = su3 * (6 * su2 - 15 * s_ub + 10);
+    double kd_center = (kd_ub + kd_lb) * 0.5;
+    double kd_radius = (kd_ub - kd_lb) * 0.5 * kr;
+    double ki_lb, ki_ub;
+    bound_k_indep(q_des_k_indep(q0, a, b, s_lb), q_des_k_indep(q0, a, b, s_ub), s_lb, s_ub, ext[0], extv[0], ext[1], extv[1], ki_lb, ki_ub);
+    double ki_radius = (ki_ub - ki_lb) * 0.5;
+    const double qc = (ki_lb + ki_ub) * 0.5;
+    const double rq = kd_radius + ki_radius + rm.qe;
+    const Itv q_rad = itv(-kd_radius - ki_radius - rm.qe, rq);
+    const Itv kspan = imul(kd_center, itv(-kr, kr));
+    const double cqc = cos(qc), sqc = sin(qc);
+    // Part 1.a / 1.b: first-order Taylor expansion with Lagrange remainder in interval arithmetic
+    Itv cos_rad = isub(imul(ineg(q_rad), point_trig(sqc)), imul(imul(0.5, icos(iadd(iadd(qc, kspan), q_rad))), ipow2(iadd(q_rad, kspan))));
+    Itv sin_rad = isub(imul(q_rad, point_trig(cqc)), imul(imul(0.5, isin(iadd(iadd(qc, kspan), q_rad))), ipow2(iadd(q_rad, kspan))));
+    if (tb.cos_rem) {
+        double* cr = tb.cos_rem + (((size_t)prob * NJ + i) * tb.T + s) * 2;
+        double* sr = tb.sin_rem + (((size_t)prob * NJ + i) * tb.T + s) * 2;
+        cr[0] = cos_rad.lo; cr[1] = cos_rad.hi; sr[0] = sin_rad.lo; sr[1] = sin_rad.hi;
+    }
+    const double cmid = (cos_rad.lo + cos_rad.hi) * 0.5;
+    const double cos_center = cqc + cmid;
+    cos_rad = isub(cos_rad, cmid);
+    const double cos_c0 = -kd_center * kr * sqc, cos_c1 = (cos_rad.hi - cos_rad.lo) * 0.5;
+    const double smid = (sin_rad.lo + sin_rad.hi) * 0.5;
+    const double sin_center = sqc + smid;
+    sin_rad = isub(sin_rad, smid);
+    const double sin_c0 = kd_center * kr * cqc, sin_c1 = (sin_rad.hi - sin_rad.lo) * 0.5;
+    small_scalar(cosq, cos_center, key_k(i), cos_c0, key_cosqe(i), cos_c1, thr);
+    small_scalar(sinq, sin_center, key_k(i), sin_c0, key_sinqe(i), sin_c1, thr);
+
+    // R = R0(rpy) * Rz(cos, sin)   (Trajectory.cu:136-144; 3x3 ctor PZsparse.cu:179-205; operator* :864-994)
+    {
+        const int axis = rm.axes[i];
+        const double* R0 = rm.R0[i];
+        double Rzc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        double Mk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, Mc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, Ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        // index pairs of the rotation block for axis x / y / z (makeRotationMatrix, PZsparse.cu:211-250)
+        int pcc0 = 0, pcc1 = 4, pns = 3, pps = 1;   // z: (0,0),(1,1) cos; (0,1) -sin; (1,0) +sin
+        if (axis == 1) { pcc0 = 4; pcc1 = 8; pns = 7; pps = 5; }        // x: (1,1),(2,2); (1,2) -sin; (2,1) +sin
+        else if (axis == 2) { pcc0 = 0; pcc1 = 8; pns = 2; pps = 6; }   // y: (0,0),(2,2); (2,0) -sin; (0,2) +sin
+        int n = 0;
+        double zind[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        u64 zk[3]; double zc[3][9];
+        if (axis != 0) {
+            Rzc[pcc0] = cos_center; Rzc[pcc1] = cos_center; Rzc[pns] = -sin_center; Rzc[pps] = sin_center;
+            Mk[pcc0] = cos_c0; Mk[pcc1] = cos_c0; Mk[pns] = -sin_c0; Mk[pps] = sin_c0;   // k_i terms of cos and sin merge
+            Mc[pcc0] = cos_c1; Mc[pcc1] = cos_c1;
+            Ms[pns] = -sin_c1; Ms[pps] = sin_c1;
+            const double* cand[3] = {Mk, Mc, Ms};
+            const u64 ck[3] = {key_k(i), key_cosqe(i), key_sinqe(i)};
+            for (int m = 0; m < 3; m++) {
+                if (norm9(cand[m]) <= thr) { for (int c = 0; c < 9; c++) zind[c] = __dadd_ru(zind[c], fabs(cand[m][c])); }
+                else { zk[n] = ck[m]; for (int c = 0; c < 9; c++) zc[n][c] = cand[m][c]; n++; }
+            }
+        }
+        double cen[9], ind[9], absR0[9], abss[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        matmat_rn(R0, Rzc, cen);
+        for (int c = 0; c < 9; c++) absR0[c] = fabs(R0[c]);
+        matmat_ru(absR0, zind, ind);
+        int nr = 0;
+        for (int m = 0; m < n; m++) {
+            double pm[9];
+            matmat_rn(R0, zc[m], pm);
+            if (norm9(pm) <= thr) { for (int c = 0; c < 9; c++) ind[c] = __dadd_ru(ind[c], fabs(pm[c])); }
+            else {
+                R.keys[nr] = zk[m];
+                for (int c = 0; c < 9; c++) { R.coef[c * R.cap + nr] = pm[c]; abss[c] = __dadd_ru(abss[c], fabs(pm[c])); }
+                nr++;
+            }
+        }
+        R.n = nr;
+        for (int c = 0; c < 9; c++) { R.center[c] = cen[c]; R.ind[0][c] = ind[c]; R.ind[1][c] = ind[c]; R.abss[c] = abss[c]; }
+        // R_t = R.transpose()
+        Rt.n = nr;
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) {
+                const int src = r + 3 * c, dstp = c + 3 * r;
+                Rt.center[dstp] = cen[src]; Rt.ind[0][dstp] = ind[src]; Rt.ind[1][dstp] = ind[src]; Rt.abss[dstp] = abss[src];
+                for (int m = 0; m < nr; m++) Rt.coef[dstp * Rt.cap + m] = R.coef[src * R.cap + m];
+            }
+        for (int m = 0; m < nr; m++) Rt.keys[m] = R.keys[m];
+    }
+
+    // Part 2: qd_des
+    {
+        const double slm1 = s_lb - 1, sum1 = s_ub - 1;
+        kd_lb = 30 * sl2 * (slm1 * slm1);
+        kd_ub = 30 * su2 * (sum1 * sum1);
+        if (kd_ub < kd_lb) { const double t = kd_lb; kd_lb = kd_ub; kd_ub = t; }
+        kd_center = (kd_ub + kd_lb) * 0.5 * kr;
+        kd_radius = (kd_ub - kd_lb) * 0.5 * kr;
+        bound_k_indep(qd_des_k_indep(a, b, s_lb), qd_des_k_indep(a, b, s_ub), s_lb, s_ub, ext[2], extv[2], ext[3], extv[3], ki_lb, ki_ub);
+        ki_radius = (ki_ub - ki_lb) * 0.5;
+        const double c = (ki_lb + ki_ub) * 0.5;
+        small_scalar(qd, c, key_k(i), kd_center, key_qde(i), kd_radius + ki_radius + rm.qde, thr);
+        small_scalar(qda, c, key_k(i), kd_center, key_qdae(i), kd_radius + ki_radius + rm.qdae, thr);
+    }
+    // Part 3: qdd_des
+    {
+        const double t_lb = 60 * s_lb * (2 * sl2 - 3 * s_lb + 1);
+        const double t_ub = 60 * s_ub * (2 * su2 - 3 * s_ub + 1);
+        if (s_ub <= rm.qdd_k_maxima) { kd_lb = t_lb; kd_ub = t_ub; }
+        else if (s_lb <= rm.qdd_k_maxima) { kd_lb = fmin(t_lb, t_ub); kd_ub = rm.qdd_k_maxima_val; }
+        else if (s_ub <= rm.qdd_k_minima) { kd_lb = t_ub; kd_ub = t_lb; }
+        else if (s_lb <= rm.qdd_k_minima) { kd_lb = rm.qdd_k_minima_val; kd_ub = fmax(t_lb, t_ub); }
+        else { kd_lb = t_lb; kd_ub = t_ub; }
+        kd_center = (kd_ub + kd_lb) * 0.5 * kr;
+        kd_radius = (kd_ub - kd_lb) * 0.5 * kr;
+        bound_k_indep(qdd_des_k_indep(a, b, s_lb), qdd_des_k_indep(a, b, s_ub), s_lb, s_ub, ext[4], extv[4], ext[5], extv[5], ki_lb, ki_ub);
+        ki_radius = (ki_ub - ki_lb) * 0.5;
+        const double c = (ki_lb + ki_ub) * 0.5;
+        small_scalar(qdda, c, key_k(i), kd_center, key_qddae(i), kd_radius + ki_radius + rm.qddae, thr);
+    }
+}
+
+// reduce_link_PZ + export (KPR/PZsparse.cu:370-402, armour_main.cu:123-126)
+template <int NT>
+__device__ void export_link(Scratch& S, const Tables& tb, size_t rec, PZ<3>& L) {
+    __syncthreads();
+    const int n = L.n;
+    u16* flag = S.sidx[0];
+    double red[3] = {0, 0, 0};
+    double* gens = tb.gens + rec * 18;
+    for (int i = threadIdx.x; i < 18; i += NT) gens[i] = 0.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += NT) {
+        const u64 k = L.keys[i];
+        u16 f = 0;
+        if (k < KEY_K_ONLY) f = 1;
+        else if (k < KEY_K_LINKS_ONLY && (k & KEY_K_MASK) == 0) {
+            // pure link-box generator: keys qde_0, qdae_0, qddae_0 in ascending order -> columns 0, 1, 2
+            const int col = (k == key_qde(0)) ? 0 : (k == key_qdae(0)) ? 1 : (k == key_qddae(0)) ? 2 : -1;
+            if (col < 0) set_err(S, ERR_LINK_GEN);
+            else for (int c = 0; c < 3; c++) gens[col * 3 + c] = L.coef[c * L.cap + i];
+        }
+        else for (int c = 0; c < 3; c++) red[c] = __dadd_ru(red[c], fabs(L.coef[c * L.cap + i]));
+        flag[i] = f;
+    }
+    __syncthreads();
+    // the link-generator columns must be packed in order of appearance (j++ in the reference): with the
+    // three fixed keys all present (checked on the host model) appearance order equals column order.
+    const int ipt = (n + NT - 1) / NT;
+    const int g0 = min(threadIdx.x * ipt, n), g1 = min(g0 + ipt, n);
+    int cnt = 0;
+    for (int g = g0; g < g1; g++) cnt += flag[g];
+    int total;
+    int off = block_excl_scan<NT>(S, cnt, total);
+    if (total > LCAP) { if (threadIdx.x == 0) set_err(S, ERR_TABLE_CAP); total = 0; }
+    else {
+        u64* ok = tb.l_keys + rec * LCAP;
+        double* oc = tb.l_coef + rec * 3 * LCAP;
+        for (int g = g0; g < g1; g++)
+            if (flag[g]) { ok[off] = L.keys[g]; for (int c = 0; c < 3; c++) oc[c * LCAP + off] = L.coef[c * L.cap + g]; off++; }
+    }
+    block_sum_ru<NT, 3>(S, red);
+    if (threadIdx.x == 0) {
+        tb.l_n[rec] = total;
+        for (int c = 0; c < 3; c++) {
+            // final radius: inflate by 2^-40 so that last-bit libm differences upstream cannot make it
+            // smaller than the host restatement's (see DESIGN.md "soundness of radii")
+            const double r = __dmul_ru(__dadd_ru(L.ind[0][c], inflate(red[c], n)), 1.0 + 0x1p-40);
+            tb.l_center[rec * 3 + c] = L.center[c];
+            tb.l_ind[rec * 3 + c] = r;
+            gens[(3 + c) * 3 + c] = r;
+        }
+    }
+    __syncthreads();
+}
+
+// disturbance radius, reduce() and export of one torque PZ (KPR/armour_main.cu:135-142, PZsparse.cu:352-368)
+template <int NT>
+__device__ void export_torque(Scratch& S, const Tables& tb, size_t rec, PZ<1>& U) {
+    __syncthreads();
+    const int n = U.n;
+    u16* flag = S.sidx[0];
+    double red[1] = {0};
+    for (int i = threadIdx.x; i < n; i += NT) {
+        const u64 k = U.keys[i];
+        const u16 f = (k < KEY_K_ONLY) ? 1 : 0;
+        if (!f) red[0] = __dadd_ru(red[0], fabs(U.coef[i]));
+        flag[i] = f;
+    }
+    __syncthreads();
+    const int ipt = (n + NT - 1) / NT;
+    const int g0 = min(threadIdx.x * ipt, n), g1 = min(g0 + ipt, n);
+    int cnt = 0;
+    for (int g = g0; g < g1; g++) cnt += flag[g];
+    int total;
+    int off = block_excl_scan<NT>(S, cnt, total);
+    if (total > UCAP) { if (threadIdx.x == 0) set_err(S, ERR_TABLE_CAP); total = 0; }
+    else {
+        u64* ok = tb.u_keys + rec * UCAP;
+        double* oc = tb.u_coef + rec * UCAP;
+        for (int g = g0; g < g1; g++)
+            if (flag[g]) { ok[off] = U.keys[g]; oc[off] = U.coef[g]; off++; }
+    }
+    block_sum_ru<NT, 1>(S, red);
+    if (threadIdx.x == 0) {
+        tb.u_n[rec] = total;
+        tb.u_center[rec] = U.center[0];
+        tb.dist_rad[rec] = __dmul_ru(__dadd_ru(U.ind[1][0], U.ind[0][0]), 1.0 + 0x1p-40);
+        tb.u_ind[rec] = __dmul_ru(__dadd_ru(U.ind[0][0], inflate(red[0], n)), 1.0 + 0x1p-40);
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Slots {
+    PZ<3> W, WD, WA, LA, T1, T2, T3, T4, T5, F[NJ], N[NJ], Fv, Nv, FKT, LINK[NJ], link0[NJ];
+    PZ<9> FKR, R[NJ + 1], Rt[NJ];
+    PZ<1> qd[NJ], qda[NJ], qdda[NJ], u[NJ], cosq[NJ], sinq[NJ];
+};
+
+size_t arena_bytes(int mcap, int ncap) {
+    size_t b = 0;
+    b += (size_t)(9 + 2 * NJ + 2 + 1 + NJ) * mcap * (8 + 3 * 8);   // big 3-vectors
+    b += (size_t)NJ * SMALL_CAP * (8 + 3 * 8);                    // link0
+    b += (size_t)mcap * (8 + 9 * 8);                              // FK_R
+    b += (size_t)(2 * NJ + 1) * SMALL_CAP * (8 + 9 * 8);          // R, R_t
+    b += (size_t)5 * NJ * SMALL_CAP * 16;                         // qd, qda, qdda, cos, sin
+    b += (size_t)NJ * mcap * 16;                                  // u
+    b += (size_t)9 * ncap * 8;                                    // tmp
+    return (b + 255) & ~(size_t)255;
+}
+
+template <int D>
+__device__ char* carve(PZ<D>& z, char* p, int cap) {
+    z.cap = cap; z.n = 0;
+    z.keys = (u64*)p; p += (size_t)cap * 8;
+    z.coef = (double*)p; p += (size_t)cap * 8 * D;
+    for (int c = 0; c < D; c++) { z.center[c] = 0; z.ind[0][c] = 0; z.ind[1][c] = 0; z.abss[c] = 0; }
+    return p;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) reach_build_kernel(Tables tb, char* arena, size_t arena_stride, int mcap, int ncap, int n_work) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ Scratch S;
+    __shared__ Slots Z;
+    const RobotModel& rm = c_robot;
+    if (threadIdx.x == 0) {
+        unsigned char* p = smem_raw;
+        S.skey[0] = (u64*)p; p += (size_t)ncap * 8;
+        S.skey[1] = (u64*)p; p += (size_t)ncap * 8;
+        S.sidx[0] = (u16*)p; p += (size_t)ncap * 2;
+        S.sidx[1] = (u16*)p; p += (size_t)ncap * 2;
+        S.ncap = ncap; S.thr = tb.thr; S.gerr = tb.err;
+        char* g = arena + (size_t)blockIdx.x * arena_stride;
+        PZ<3>* big3[] = {&Z.W, &Z.WD, &Z.WA, &Z.LA, &Z.T1, &Z.T2, &Z.T3, &Z.T4, &Z.T5, &Z.Fv, &Z.Nv, &Z.FKT};
+        for (PZ<3>* z : big3) g = carve<3>(*z, g, mcap);
+        for (int i = 0; i < NJ; i++) { g = carve<3>(Z.F[i], g, mcap); g = carve<3>(Z.N[i], g, mcap); g = carve<3>(Z.LINK[i], g, mcap); g = carve<3>(Z.link0[i], g, SMALL_CAP); }
+        g = carve<9>(Z.FKR, g, mcap);
+        for (int i = 0; i <= NJ; i++) g = carve<9>(Z.R[i], g, SMALL_CAP);
+        for (int i = 0; i < NJ; i++) g = carve<9>(Z.Rt[i], g, SMALL_CAP);
+        for (int i = 0; i < NJ; i++) {
+            g = carve<1>(Z.qd[i], g, SMALL_CAP); g = carve<1>(Z.qda[i], g, SMALL_CAP); g = carve<1>(Z.qdda[i], g, SMALL_CAP);
+            g = carve<1>(Z.cosq[i], g, SMALL_CAP); g = carve<1>(Z.sinq[i], g, SMALL_CAP);
+            g = carve<1>(Z.u[i], g, mcap);
+        }
+        S.tmp = (double*)g;
+    }
+    __syncthreads();
+    const double zero3[3] = {0, 0, 0};
+
+    for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+        const int prob = work / tb.T, s = work - prob * tb.T;
+        __syncthreads();
+        // ---- stage A: joint reach sets (one thread per joint; tiny scalar work) -------------------
+        if (threadIdx.x < NJ) {
+            const int i = threadIdx.x;
+            make_poly_zono_joint(tb, prob, s, i, Z.R[i], Z.Rt[i], Z.qd[i], Z.qda[i], Z.qdda[i], Z.cosq[i], Z.sinq[i], S.thr);
+            if (tb.traj) {
+                SmallRec* rec = tb.traj + (((size_t)prob * tb.T + s) * TRAJ_TABLES) * NJ;
+                export_small<1>(rec[TRAJ_COS * NJ + i], Z.cosq[i]); export_small<1>(rec[TRAJ_SIN * NJ + i], Z.sinq[i]);
+                export_small<9>(rec[TRAJ_R * NJ + i], Z.R[i]); export_small<9>(rec[TRAJ_RT * NJ + i], Z.Rt[i]);
+                export_small<1>(rec[TRAJ_QD * NJ + i], Z.qd[i]); export_small<1>(rec[TRAJ_QDA * NJ + i], Z.qda[i]);
+                export_small<1>(rec[TRAJ_QDDA * NJ + i], Z.qdda[i]);
+            }
+            // original link boxes: stack of three scalar PZs, one generator each (KPR/Dynamics.cu:51-66)
+            PZ<3>& L0 = Z.link0[i];
+            int n = 0;
+            double ind[3] = {0, 0, 0}, abss[3] = {0, 0, 0};
+            const u64 gk[3] = {key_qde(0), key_qdae(0), key_qddae(0)};
+            for (int j = 0; j < 3; j++) {
+                const double g = rm.link_g[i][j];
+                if (norm1(&g) > S.thr) {   // both the scalar ctor's simplify and stack()'s see |g|
+                    L0.keys[n] = gk[j];
+                    for (int c = 0; c < 3; c++) L0.coef[c * L0.cap + n] = (c == j) ? g : 0.0;
+                    abss[j] = fabs(g);
+                    n++;
+                }
+                else ind[j] = fabs(g);
+            }
+            L0.n = n;
+            for (int c = 0; c < 3; c++) { L0.center[c] = rm.link_c[i][c]; L0.ind[0][c] = ind[c]; L0.ind[1][c] = ind[c]; L0.abss[c] = abss[c]; }
+        }
+        if (threadIdx.x == NJ) {   // R(NUM_JOINTS) = identity
+            PZ<9>& R = Z.R[NJ];
+            R.n = 0;
+            for (int c = 0; c < 9; c++) { R.center[c] = rm.R0[NJ][c]; R.ind[0][c] = 0; R.ind[1][c] = 0; R.abss[c] = 0; }
+        }
+        __syncthreads();
+
+        // ---- stage B: forward kinematics (KPR/Dynamics.cu:69-81) ------------------------------------
+        pz_set_const<9>(Z.FKR, rm.R0[NJ]);
+        pz_set_const<3>(Z.FKT, zero3);
+        for (int i = 0; i < NJ; i++) {
+            pz_const_right<NT>(S, Z.T1, Z.FKR, rm.trans[i]);          // FK_R * P
+            pz_add3<NT>(S, Z.FKT, Z.FKT, Z.T1);                       // FK_T = FK_T + FK_R * P
+            pz_mul<NT, 9, 9, 9>(S, Z.FKR, Z.FKR, Z.R[i]);             // FK_R = FK_R * R_i
+            pz_mul<NT, 9, 3, 3>(S, Z.T2, Z.FKR, Z.link0[i]);          // FK_R * link_i
+            pz_add3<NT>(S, Z.LINK[i], Z.T2, Z.FKT);                   //          + FK_T
+            export_link<NT>(S, tb, ((size_t)prob * tb.T + s) * NJ + i, Z.LINK[i]);
+        }
+
+        // ---- stage C: RNEA forward recursion (KPR/Dynamics.cu:83-155) -------------------------------
+        pz_set_const<3>(Z.W, zero3); pz_set_const<3>(Z.WD, zero3); pz_set_const<3>(Z.WA, zero3);
+        { const double g3[3] = {0, 0, rm.gravity}; pz_set_const<3>(Z.LA, g3); }
+        for (int i = 0; i < NJ; i++) {
+            const int axis = rm.axes[i];
+            const int row = (axis < 0 ? -axis : axis) - 1;
+            // linear_acc = R_t * (linear_acc + cross(wdot, trans) + cross(w, cross(w_aux, trans)))   (line 16)
+            pz_cross_const<NT>(S, Z.T1, Z.WD, rm.trans[i], false);
+            pz_cross_const<NT>(S, Z.T2, Z.WA, rm.trans[i], false);
+            pz_cross_pp<NT>(S, Z.T3, Z.W, Z.T2);
+            pz_add3<NT>(S, Z.T4, Z.LA, Z.T1);
+            pz_add3<NT>(S, Z.T4, Z.T4, Z.T3);
+            pz_mul<NT, 9, 3, 3>(S, Z.LA, Z.Rt[i], Z.T4);
+            // w = R_t * w (+ qd_des on the joint axis)                                               (line 13)
+            pz_mul<NT, 9, 3, 3>(S, Z.W, Z.Rt[i], Z.W);
+            if (axis != 0) pz_add_one_dim<NT>(S, Z.W, Z.W, Z.qd[i], row);
+            // w_aux = R_t * w_aux                                                                     (line 14)
+            pz_mul<NT, 9, 3, 3>(S, Z.WA, Z.Rt[i], Z.WA);
+            // wdot = R_t * wdot (+ cross(w_aux, qd_des * z) + qdda_des on the axis)                   (line 15)
+            pz_mul<NT, 9, 3, 3>(S, Z.WD, Z.Rt[i], Z.WD);
+            if (axis != 0) {
+                pz_set_const<3>(Z.T1, zero3);
+                pz_add_one_dim<NT>(S, Z.T1, Z.T1, Z.qd[i], row);
+                pz_cross_pp<NT>(S, Z.T2, Z.WA, Z.T1);
+                pz_add3<NT>(S, Z.WD, Z.WD, Z.T2);
+                pz_add_one_dim<NT>(S, Z.WD, Z.WD, Z.qdda[i], row);
+                pz_add_one_dim<NT>(S, Z.WA, Z.WA, Z.qda[i], row);
+            }
+            // F = m * (linear_acc + cross(wdot, com) + cross(w, cross(w_aux, com)))                  (lines 23 & 27)
+            pz_cross_const<NT>(S, Z.T1, Z.WD, rm.com[i], false);
+            pz_cross_const<NT>(S, Z.T2, Z.WA, rm.com[i], false);
+            pz_cross_pp<NT>(S, Z.T3, Z.W, Z.T2);
+            pz_add3<NT>(S, Z.T4, Z.LA, Z.T1);
+            pz_add3<NT>(S, Z.T4, Z.T4, Z.T3);
+            {
+                const double m0 = 0.0, m1 = __dmul_ru(tb.mass_unc, fabs(rm.mass[i]));
+                pz_const_left<NT>(S, Z.F[i], &rm.mass[i], &m0, &m1, true, Z.T4);
+            }
+            // N = I * wdot + cross(w_aux, I * w)                                                      (line 29)
+            {
+                double I0[9], I1[9];
+                for (int c = 0; c < 9; c++) { I0[c] = 0.0; I1[c] = __dmul_ru(tb.inertia_unc, fabs(rm.inertia[i][c])); }
+                pz_const_left<NT>(S, Z.T1, rm.inertia[i], I0, I1, false, Z.WD);
+                pz_const_left<NT>(S, Z.T2, rm.inertia[i], I0, I1, false, Z.W);
+            }
+            pz_cross_pp<NT>(S, Z.T3, Z.WA, Z.T2);
+            pz_add3<NT>(S, Z.N[i], Z.T1, Z.T3);
+        }
+
+        // ---- RNEA reverse recursion (KPR/Dynamics.cu:157-180) ---------------------------------------
+        pz_set_const<3>(Z.Fv, zero3); pz_set_const<3>(Z.Nv, zero3);
+        for (int i = NJ - 1; i >= 0; i--) {
+            const int axis = rm.axes[i];
+            const int row = (axis < 0 ? -axis : axis) - 1;
+            // n = N + R * n + cross(com, F) + cross(trans_{i+1}, R * f)                              (line 29)
+            pz_mul<NT, 9, 3, 3>(S, Z.T1, Z.R[i + 1], Z.Nv);
+            pz_add3<NT>(S, Z.T2, Z.N[i], Z.T1);
+            pz_cross_const<NT>(S, Z.T3, Z.F[i], rm.com[i], true);
+            pz_add3<NT>(S, Z.T2, Z.T2, Z.T3);
+            pz_mul<NT, 9, 3, 3>(S, Z.T4, Z.R[i + 1], Z.Fv);             // R * f (the reference evaluates it twice)
+            pz_cross_const<NT>(S, Z.T3, Z.T4, rm.trans[i + 1], true);
+            pz_add3<NT>(S, Z.Nv, Z.T2, Z.T3);
+            // f = R * f + F                                                                           (line 28)
+            pz_add3<NT>(S, Z.Fv, Z.T4, Z.F[i]);
+            if (axis != 0) {
+                // u = n(axis) + armature * qdda_des + damping * qd_des
+                pz_merge<NT, 3, 1, 1>(S, Z.u[i], view_extract(Z.Nv, row), view_scaled(Z.qdda[i], rm.armature[i]), false);
+                pz_merge<NT, 1, 1, 1>(S, Z.u[i], view(Z.u[i]), view_scaled(Z.qd[i], rm.damping[i]), false);
+            }
+        }
+
+        // ---- stage M: disturbance, reduce(), torque radius (KPR/armour_main.cu:135-205) -------------
+        for (int i = 0; i < NF; i++) export_torque<NT>(S, tb, ((size_t)prob * tb.T + s) * NF + i, Z.u[i]);
+        if (threadIdx.x == 0) {
+            const size_t base = ((size_t)prob * tb.T + s) * NF;
+            // rho = sqrt(sum_i [-r_i, r_i]^2): only the upper end is used; everything rounded up
+            double rho = 0.0;
+            for (int i = 0; i < NF; i++) { const double r = tb.dist_rad[base + i]; rho = __dadd_ru(rho, __dmul_ru(r, r)); }
+            rho = __dsqrt_ru(rho);
+            const double c0 = __dmul_ru(__dmul_ru(rm.alpha, __dadd_ru(rm.M_max, -rm.M_min)), rm.eps);
+            for (int i = 0; i < NF; i++) {
+                double tr = __dadd_ru(c0, __dmul_ru(0.5, tb.dist_rad[base + i]));
+                tr = __dadd_ru(tr, __dmul_ru(0.5, rho));
+                tr = __dadd_ru(tr, tb.u_ind[base + i]);
+                tr = __dadd_ru(tr, rm.friction[i]);
+                tb.torque_radius[base + i] = tr;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- stand-alone PZsparse arithmetic (PZsparse facade / primitive parity tests) -----------------------
+// Flat operand record in global memory: [n, dim] ints, then keys[cap], coef[dim][cap], center[9], ind[9]
+template <int D>
+__device__ void load_flat(PZ<D>& z, const FlatPZ& f) {
+    if (threadIdx.x == 0) {
+        z.n = f.n; z.cap = f.cap; z.keys = f.keys; z.coef = f.coef;
+        for (int c = 0; c < D; c++) {
+            z.center[c] = f.center[c]; z.ind[0][c] = f.ind[c]; z.ind[1][c] = f.ind[c];
+            double s = 0.0;
+            for (int i = 0; i < f.n; i++) s = __dadd_ru(s, fabs(f.coef[c * f.cap + i]));
+            z.abss[c] = s;
+        }
+    }
+}
+template <int D>
+__device__ void store_flat(FlatPZ& f, const PZ<D>& z) {
+    if (threadIdx.x == 0) { f.n = z.n; f.dim = D; for (int c = 0; c < D; c++) { f.center[c] = z.center[c]; f.ind[c] = z.ind[0][c]; } }
+}
+template <int NT>
+__global__ void __launch_bounds__(NT) pz_binary_kernel(int op, FlatPZ a, FlatPZ b, FlatPZ r, FlatOut* out, double* tmp, int ncap, double thr, int* err) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ Scratch S;
+    __shared__ PZ<1> a1, b1, r1;
+    __shared__ PZ<3> a3, b3, r3;
+    __shared__ PZ<9> a9, b9, r9;
+    if (threadIdx.x == 0) {
+        unsigned char* p = smem_raw;
+        S.skey[0] = (u64*)p; p += (size_t)ncap * 8;
+        S.skey[1] = (u64*)p; p += (size_t)ncap * 8;
+        S.sidx[0] = (u16*)p; p += (size_t)ncap * 2;
+        S.sidx[1] = (u16*)p;
+        S.ncap = ncap; S.thr = thr; S.gerr = err; S.tmp = tmp;
+        r1.cap = r3.cap = r9.cap = r.cap; r1.keys = r3.keys = r9.keys = r.keys; r1.coef = r3.coef = r9.coef = r.coef;
+    }
+    __syncthreads();
+    FlatOut o; o.n = -1; o.dim = 0;
+    if (op == 0) {
+        if (a.dim == 9 && b.dim == 3) { load_flat<9>(a9, a); load_flat<3>(b3, b); pz_mul<NT, 9, 3, 3>(S, r3, a9, b3); o.n = r3.n; o.dim = 3; store_flat<3>(r, r3); }
+        else if (a.dim == 9 && b.dim == 9) { load_flat<9>(a9, a); load_flat<9>(b9, b); pz_mul<NT, 9, 9, 9>(S, r9, a9, b9); o.n = r9.n; o.dim = 9; store_flat<9>(r, r9); }
+        else if (a.dim == 1 && b.dim == 1) { load_flat<1>(a1, a); load_flat<1>(b1, b); pz_mul<NT, 1, 1, 1>(S, r1, a1, b1); o.n = r1.n; o.dim = 1; store_flat<1>(r, r1); }
+    }
+    else if (op == 1 || op == 2) {
+        if (a.dim == 3 && b.dim == 3) { load_flat<3>(a3, a); load_flat<3>(b3, b); pz_merge<NT, 3, 3, 3>(S, r3, view(a3), view(b3), op == 2); o.n = r3.n; o.dim = 3; store_flat<3>(r, r3); }
+        else if (a.dim == 1 && b.dim == 1) { load_flat<1>(a1, a); load_flat<1>(b1, b); pz_merge<NT, 1, 1, 1>(S, r1, view(a1), view(b1), op == 2); o.n = r1.n; o.dim = 1; store_flat<1>(r, r1); }
+    }
+    else if (op == 3 && a.dim == 3 && b.dim == 3) { load_flat<3>(a3, a); load_flat<3>(b3, b); pz_cross_pp<NT>(S, r3, a3, b3); o.n = r3.n; o.dim = 3; store_flat<3>(r, r3); }
+    __syncthreads();
+    if (threadIdx.x == 0) { if (o.dim == 1) o.n = r1.n; else if (o.dim == 3) o.n = r3.n; else if (o.dim == 9) o.n = r9.n; *out = o; }
+}
+
+// ---- host-side launch helpers -----------------------------------------------------------------
+cudaError_t upload_robot_model(const RobotModel& rm) { return cudaMemcpyToSymbol(c_robot, &rm, sizeof(RobotModel)); }
+
+size_t reach_smem_bytes(int ncap) { return (size_t)ncap * 20; }
+
+cudaError_t launch_reach_build(const Tables& tb, char* arena, size_t arena_stride, int mcap, int ncap, int n_work, int grid, int nt, cudaStream_t stream) {
+    const size_t smem = reach_smem_bytes(ncap);
+    cudaError_t e;
+#define ARMOUR_LAUNCH(NTV)                                                                                          \
+    e = cudaFuncSetAttribute(reach_build_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    if (e != cudaSuccess) return e;                                                                                 \
+    reach_build_kernel<NTV><<<grid, NTV, smem, stream>>>(tb, arena, arena_stride, mcap, ncap, n_work);
+    if (nt == 128) { ARMOUR_LAUNCH(128) }
+    else if (nt == 512) { ARMOUR_LAUNCH(512) }
+    else { ARMOUR_LAUNCH(256) }
+#undef ARMOUR_LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pz_binary(int op, const FlatPZ& a, const FlatPZ& b, const FlatPZ& r, FlatOut* out, double* tmp, int ncap, double thr, int* err, cudaStream_t stream) {
+    const size_t smem = reach_smem_bytes(ncap);
+    cudaError_t e = cudaFuncSetAttribute(pz_binary_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pz_binary_kernel<256><<<1, 256, smem, stream>>>(op, a, b, r, out, tmp, ncap, thr, err);
+    return cudaGetLastError();
+}
+
+int reach_max_ctas_per_sm(int nt, int ncap) {
+    int n = 0;
+    const size_t smem = reach_smem_bytes(ncap);
+    if (nt == 128) { cudaFuncSetAttribute(reach_build_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reach_build_kernel<128>, 128, smem); }
+    else if (nt == 512) { cudaFuncSetAttribute(reach_build_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reach_build_kernel<512>, 512, smem); }
+    else { cudaFuncSetAttribute(reach_build_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reach_build_kernel<256>, 256, smem); }
+    return n;
+}
+
+}  // namespace armour
