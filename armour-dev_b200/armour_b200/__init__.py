@@ -26,7 +26,7 @@ EXPORTS = [
     "armour_eval_grad_f", "armour_eval_g", "armour_eval_jac_g", "armour_eval_g_jac", "armour_jac_structure", "armour_check_feasible",
     "armour_get_torque_radius", "armour_get_link_generators", "armour_get_link_sliced_center", "armour_get_hyperplanes",
     "armour_get_taylor_remainders", "armour_get_pz", "armour_pz_binary", "armour_last_build_ms", "armour_last_eval_ms",
-    "armour_kernel_launches", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_measure_fp64_peak",
+    "armour_kernel_launches", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_upload_x", "armour_measure_fp64_peak",
 ]
 
 
@@ -191,6 +191,9 @@ class Planner:
     def eval_resident(self, x=None):
         self._ck(self.L.armour_eval_resident(self.h, _dp(_vec(x, 7)) if x is not None else None))
 
+    def upload_x(self, x):
+        self._ck(self.L.armour_upload_x(self.h, _dp(_vec(x, 7))))
+
     def select_problem(self, p):
         self._ck(self.L.armour_select_problem(self.h, C.c_int(p)))
 
@@ -275,6 +278,7 @@ class Planner:
         keys = np.zeros(256, dtype=np.uint64)
         coeffs = np.zeros(256 * 9)
         center, indep = np.zeros(9), np.zeros(9)
+        idx, s = int(idx), int(s)
         n = self._ck(self.L.armour_get_pz(self.h, w, idx, s, _ip(dims), _up(keys), _dp(coeffs), _dp(center), _dp(indep)))
         dim = int(dims[0] * dims[1])
         return dict(rows=int(dims[0]), cols=int(dims[1]), keys=keys[:n].copy(), coeffs=coeffs[: n * dim].reshape(n, dim).copy(),

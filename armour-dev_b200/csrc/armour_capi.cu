@@ -425,6 +425,15 @@ int armour_eval_resident(armour_handle* h, const double* x) {
     CU(cudaSetDevice(h->device));
     return run_eval(h, x, false);
 }
+int armour_upload_x(armour_handle* h, const double* x) {
+    if (!h || !x) return fail(ARMOUR_E_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    memcpy(h->h_x, x, sizeof(double) * NF);
+    CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * NF, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_eval = false;
+    return ARMOUR_OK;
+}
 int armour_jac_structure(armour_handle* h, int* iRow, int* jCol) {
     if (!h || !iRow || !jCol) return fail(ARMOUR_E_INVALID, "null argument");
     const int m = m_of(h);

@@ -58,18 +58,21 @@ __device__ __forceinline__ Itv point_trig(double v) { return itv(widen_dn(v), wi
 #define PI2_LO 0x1.921fb54442d18p+2
 #define PI2_HI 0x1.921fb54442d19p+2
 
-__device__ Itv icos(Itv x, int depth = 0) {   // boost::numeric::cos(interval), restated in oracle/oracle_pz.hpp
-    const double yb = (x.lo < 0) ? PI2_LO : PI2_HI;
-    const double n = floor(__ddiv_rd(x.lo, yb));
-    const Itv tmp = isub(x, imul(n, itv(PI2_LO, PI2_HI)));
-    if (__dadd_ru(tmp.hi, -tmp.lo) >= PI2_LO) return itv(-1.0, 1.0);
-    if (tmp.lo >= PI_HI) {   // -cos(tmp - pi); the shifted argument starts below pi, so this recurses once
-        if (depth > 2) return itv(-1.0, 1.0);
-        return ineg(icos(isub(tmp, itv(PI_LO, PI_HI)), depth + 1));
+__device__ Itv icos(Itv x) {   // boost::numeric::cos(interval), restated in oracle/oracle_pz.hpp
+    bool negate = false;   // the library recurses once through -cos(x - pi); unrolled here (no device recursion)
+    for (int it = 0; it < 3; it++) {
+        const double yb = (x.lo < 0) ? PI2_LO : PI2_HI;
+        const double n = floor(__ddiv_rd(x.lo, yb));
+        const Itv tmp = isub(x, imul(n, itv(PI2_LO, PI2_HI)));
+        if (__dadd_ru(tmp.hi, -tmp.lo) >= PI2_LO) return itv(-1.0, 1.0);
+        if (tmp.lo >= PI_HI) { x = isub(tmp, itv(PI_LO, PI_HI)); negate = !negate; continue; }
+        const double l = tmp.lo, u = tmp.hi;
+        Itv r;
+        if (u <= PI_LO) r = itv(widen_dn(cos(u)), widen_up(cos(l)));
+        else if (u <= PI2_LO) r = itv(-1.0, widen_up(cos(fmin(__dadd_rd(PI2_LO, -u), l))));
+        else r = itv(-1.0, 1.0);
+        return negate ? ineg(r) : r;
     }
-    const double l = tmp.lo, u = tmp.hi;
-    if (u <= PI_LO) return itv(widen_dn(cos(u)), widen_up(cos(l)));
-    if (u <= PI2_LO) return itv(-1.0, widen_up(cos(fmin(__dadd_rd(PI2_LO, -u), l))));
     return itv(-1.0, 1.0);
 }
 __device__ __forceinline__ Itv isin(Itv x) { return icos(isub(x, itv(PI_HALF_LO, PI_HALF_HI))); }
@@ -99,6 +102,7 @@ __device__ void small_scalar(PZ<1>& z, double center, u64 k0, double c0, u64 k1,
     double ind = 0.0, abss = 0.0;
     if (norm1(&c0) > thr) { z.keys[n] = k0; z.coef[n] = c0; abss = __dadd_ru(abss, fabs(c0)); n++; } else ind = __dadd_ru(ind, fabs(c0));
     if (norm1(&c1) > thr) { z.keys[n] = k1; z.coef[n] = c1; abss = __dadd_ru(abss, fabs(c1)); n++; } else ind = __dadd_ru(ind, fabs(c1));
+    ind = __dmul_ru(ind, 1.0 + 0x1p-40);   // a dropped coefficient built from device libm values may be an ulp below the host's
     z.n = n; z.center[0] = center; z.ind[0][0] = ind; z.ind[1][0] = ind; z.abss[0] = abss;
 }
 template <int D>
@@ -141,8 +145,11 @@ __device__ void make_poly_zono_joint(const Tables& tb, int prob, int s, int i, P
     bound_k_indep(q_des_k_indep(q0, a, b, s_lb), q_des_k_indep(q0, a, b, s_ub), s_lb, s_ub, ext[0], extv[0], ext[1], extv[1], ki_lb, ki_ub);
     double ki_radius = (ki_ub - ki_lb) * 0.5;
     const double qc = (ki_lb + ki_ub) * 0.5;
-    const double rq = kd_radius + ki_radius + rm.qe;
-    const Itv q_rad = itv(-kd_radius - ki_radius - rm.qe, rq);
+    // The reference's bound of the k-independent part may use an interior stationary value computed with
+    // libm pow (Trajectory.cu:812-814); the device evaluates the same polynomial with products, so the radius
+    // can differ in the last bit.  It only feeds the interval remainders below: widen it by 2^-51 (sound).
+    const double rq = __dmul_ru(kd_radius + ki_radius + rm.qe, 1.0 + 0x1p-51);
+    const Itv q_rad = itv(-rq, rq);
     const Itv kspan = imul(kd_center, itv(-kr, kr));
     const double cqc = cos(qc), sqc = sin(qc);
     // Part 1.a / 1.b: first-order Taylor expansion with Lagrange remainder in interval arithmetic
@@ -185,7 +192,7 @@ __device__ void make_poly_zono_joint(const Tables& tb, int prob, int s, int i, P
             const double* cand[3] = {Mk, Mc, Ms};
             const u64 ck[3] = {key_k(i), key_cosqe(i), key_sinqe(i)};
             for (int m = 0; m < 3; m++) {
-                if (norm9(cand[m]) <= thr) { for (int c = 0; c < 9; c++) zind[c] = __dadd_ru(zind[c], fabs(cand[m][c])); }
+                if (norm9(cand[m]) <= thr) { for (int c = 0; c < 9; c++) zind[c] = __dadd_ru(zind[c], __dmul_ru(fabs(cand[m][c]), 1.0 + 0x1p-40)); }
                 else { zk[n] = ck[m]; for (int c = 0; c < 9; c++) zc[n][c] = cand[m][c]; n++; }
             }
         }
@@ -197,7 +204,7 @@ __device__ void make_poly_zono_joint(const Tables& tb, int prob, int s, int i, P
         for (int m = 0; m < n; m++) {
             double pm[9];
             matmat_rn(R0, zc[m], pm);
-            if (norm9(pm) <= thr) { for (int c = 0; c < 9; c++) ind[c] = __dadd_ru(ind[c], fabs(pm[c])); }
+            if (norm9(pm) <= thr) { for (int c = 0; c < 9; c++) ind[c] = __dadd_ru(ind[c], __dmul_ru(fabs(pm[c]), 1.0 + 0x1p-40)); }
             else {
                 R.keys[nr] = zk[m];
                 for (int c = 0; c < 9; c++) { R.coef[c * R.cap + nr] = pm[c]; abss[c] = __dadd_ru(abss[c], fabs(pm[c])); }

@@ -135,7 +135,8 @@ int armour_kernel_launches(armour_handle* h, uint64_t* launches);
  * used by bench.py's device-resident timing */
 int armour_upload_problems(armour_handle* h, int count, const double* q0, const double* qd0, const double* qdd0, const double* obstacles, int n_obs);
 int armour_build_resident(armour_handle* h);
-int armour_eval_resident(armour_handle* h, const double* x);
+int armour_eval_resident(armour_handle* h, const double* x); /* x == NULL: reuse the x uploaded by armour_upload_x */
+int armour_upload_x(armour_handle* h, const double* x);
 /* fp64 FMA micro-benchmark (TFLOP/s) used as the fp64 roofline denominator */
 int armour_measure_fp64_peak(int device, double* tflops);
 

@@ -168,6 +168,7 @@ class Oracle:
     def get_pz(self, which, idx, s):
         w = TABLES[which] if isinstance(which, str) else which
         dims = np.zeros(2, dtype=np.int32)
+        idx, s = int(idx), int(s)
         n = self.L.oracle_get_pz(self.h, w, idx, s, _ip(dims), None, None, None, None)
         dim = int(dims[0] * dims[1])
         keys = np.zeros(max(n, 1), dtype=np.uint64)

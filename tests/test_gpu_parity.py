@@ -1,0 +1,249 @@
+"""GPU parity tests (run on the B200 with `-m gpu`): the CUDA path through the C ABI against the CPU
+oracle on the same seeded inputs.
+
+Tolerances are the ones BASELINE.json's north_star states:
+  * monomial keys and keep/drop (generator reduction) choices: bit-exact
+  * reach-set centres, coefficients (generators) and interval radii: 1e-9 relative; device radii and
+    interval enclosures must additionally contain the oracle's (>=, <= on the end points)
+  * constraint values and Jacobians: 1e-8
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+import _oracle
+import armour_b200 as ab
+from problems import DEBUG_K, DEBUG_Q0, DEBUG_QD0, DEBUG_QDD0, EXAMPLE_OBS, EXAMPLE_Q0, make_problem
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9      # reach sets
+CTOL = 1e-8     # constraints, Jacobians
+TABLE_NAMES = ("cos_q", "sin_q", "R", "R_t", "qd_des", "qda_des", "qdda_des", "links", "u_nom", "u_nom_int")
+
+
+def assert_pz_equal(a, b, what):
+    """a = oracle, b = device."""
+    assert (a["rows"], a["cols"]) == (b["rows"], b["cols"]), what
+    assert np.array_equal(a["keys"], b["keys"]), "%s: monomial keys / reduction choices differ" % what
+    scale = max(1.0, float(np.abs(a["center"]).max()))
+    assert np.abs(a["center"] - b["center"]).max() <= REL * scale, what
+    if len(a["keys"]):
+        cs = max(scale, float(np.abs(a["coeffs"]).max()))
+        assert np.abs(a["coeffs"] - b["coeffs"]).max() <= REL * cs, what
+    ia, ib = a["independent"], b["independent"]
+    assert np.all(ib >= ia), "%s: device radius does not contain the oracle's" % what
+    assert np.all(ib - ia <= REL * np.maximum(np.abs(ia), 1e-12)), what
+
+
+def compare_build(o, p, T):
+    for name in TABLE_NAMES:
+        for s in range(T):
+            for i in range(7):
+                assert_pz_equal(o.get_pz(name, i, s), p.get_pz(name, i, s), "%s[%d,%d]" % (name, i, s))
+    tr_o, tr_g = o.torque_radius(), p.torque_radius()
+    assert np.all(tr_g >= tr_o) and np.all(tr_g - tr_o <= REL * tr_o)
+    lg_o, lg_g = o.link_generators(), p.link_generators()
+    assert np.abs(lg_o - lg_g).max() <= REL * max(1.0, np.abs(lg_o).max())
+    d = np.arange(3)
+    assert np.all(lg_g[:, :, d, 3 + d] >= lg_o[:, :, d, 3 + d])      # diagonal block holds the interval radii
+    (co, so), (cg, sg) = o.taylor_remainders(), p.taylor_remainders()
+    for ref, dev in ((co, cg), (so, sg)):   # Boost-interval enclosures: device must contain the oracle's
+        assert np.all(dev[..., 0] <= ref[..., 0]) and np.all(dev[..., 1] >= ref[..., 1])
+        assert np.abs(dev - ref).max() <= REL * max(1e-3, np.abs(ref).max())
+
+
+def compare_eval(o, p, x):
+    go, Jo = o.eval_g(x), o.eval_jac_g(x)
+    gg, Jg = p.eval_g_jac(x)
+    assert np.abs(go - gg).max() <= CTOL * max(1.0, np.abs(go).max())
+    assert np.abs(Jo - Jg).max() <= CTOL * max(1.0, np.abs(Jo).max())
+    assert np.abs(o.link_sliced_center() - p.link_sliced_center()).max() <= REL
+    # separate entry points serve the same numbers
+    assert np.array_equal(p.eval_g(x), gg) and np.array_equal(p.eval_jac_g(x), Jg)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_config1_T128_10_obstacles(seed, gpu_lib):
+    q0, qd0, qdd0, q_des, obs = make_problem(seed, 10)
+    o = _oracle.Oracle(T=128)
+    o.build(q0, qd0, qdd0, obs)
+    p = ab.Planner(T=128)
+    p.build(q0, qd0, qdd0, obs)
+    assert o.get_nlp_info() == p.get_nlp_info() == (7, 9884, 69188, 0)
+    compare_build(o, p, 128)
+    Ao, do_, dlo = o.hyperplanes()
+    Ag, dg, dlg = p.hyperplanes()
+    assert max(np.abs(Ao - Ag).max(), np.abs(do_ - dg).max(), np.abs(dlo - dlg).max()) <= REL
+    rng = np.random.default_rng(1234 + seed)
+    for x in (np.zeros(7), DEBUG_K, rng.uniform(-1, 1, 7), rng.uniform(-1, 1, 7)):
+        compare_eval(o, p, x)
+    for a, b in zip(o.get_bounds_info(), p.get_bounds_info()):
+        assert np.abs(a - b).max() <= REL * 100
+    assert np.array_equal(o.get_starting_point(), p.get_starting_point())
+    assert abs(o.eval_f(q_des, 0.5, DEBUG_K) - p.eval_f(q_des, 0.5, DEBUG_K)) <= 1e-12
+    assert np.abs(o.eval_grad_f(q_des, 0.5, DEBUG_K) - p.eval_grad_f(q_des, 0.5, DEBUG_K)).max() <= 1e-12
+    ir_o, jc_o = o.jac_structure()
+    ir_g, jc_g = p.jac_structure()
+    assert np.array_equal(ir_o, ir_g) and np.array_equal(jc_o, jc_g)
+    g = p.eval_g(np.zeros(7))
+    assert o.check_feasible(g) == p.check_feasible(g)
+
+
+def test_config2_20_obstacles_reference_harness_state(gpu_lib):
+    """State of KPR/debug_script.m:29-31, slice point of KPR/PZ_tests.cu:198, 20 obstacles (m = 18844)."""
+    _, _, _, _, obs = make_problem(77, 20)
+    o = _oracle.Oracle(T=128)
+    o.build(DEBUG_Q0, DEBUG_QD0, DEBUG_QDD0, obs)
+    p = ab.Planner(T=128)
+    p.build(DEBUG_Q0, DEBUG_QD0, DEBUG_QDD0, obs)
+    assert p.get_nlp_info() == (7, 18844, 131908, 0)
+    compare_build(o, p, 128)
+    rng = np.random.default_rng(1234)
+    for x in [DEBUG_K] + [rng.uniform(-1, 1, 7) for _ in range(4)]:
+        compare_eval(o, p, x)
+
+
+def test_reference_example_input(gpu_lib):
+    """The commented example in KPR/armour_main.cu:19-34: zero initial velocity and acceleration, which makes the
+    k-independent stationary points 0/0 = NaN (KPR/Trajectory.cu:36-58) — comparisons with NaN must stay false."""
+    z = np.zeros(7)
+    o = _oracle.Oracle(T=128)
+    o.build(EXAMPLE_Q0, z, z, EXAMPLE_OBS)
+    p = ab.Planner(T=128)
+    p.build(EXAMPLE_Q0, z, z, EXAMPLE_OBS)
+    compare_build(o, p, 128)
+    for x in (np.zeros(7), DEBUG_K, -DEBUG_K):
+        compare_eval(o, p, x)
+
+
+def test_config4_T512_five_percent_uncertainty(gpu_lib):
+    q0, qd0, qdd0, _, obs = make_problem(5, 4)
+    kw = dict(T=512, mass_uncertainty=0.05, inertia_uncertainty=0.05)
+    o = _oracle.Oracle(**kw)
+    o.build(q0, qd0, qdd0, obs)
+    p = ab.Planner(**kw)
+    p.build(q0, qd0, qdd0, obs)
+    compare_build(o, p, 512)
+    compare_eval(o, p, DEBUG_K)
+
+
+def test_wide_k_range_grows_capacities(gpu_lib):
+    """k_range = pi/24 (KPR/debug_script.m:35) produces lists beyond the default capacities: the build must grow
+    them and still match, not fail or truncate."""
+    kr = [np.pi / 24] * 7
+    T = 16
+    o = _oracle.Oracle(T=T, k_range=kr)
+    o.build(DEBUG_Q0, DEBUG_QD0, DEBUG_QDD0, [])
+    p = ab.Planner(T=T, k_range=kr, max_monomials=256, max_entries=1024)
+    p.build(DEBUG_Q0, DEBUG_QD0, DEBUG_QDD0, [])
+    compare_build(o, p, T)
+    compare_eval(o, p, DEBUG_K)
+
+
+def test_no_obstacles_and_max_obstacles(gpu_lib):
+    q0, qd0, qdd0, _, obs40 = make_problem(9, 40)
+    T = 8
+    for obs in ([], obs40):
+        o = _oracle.Oracle(T=T)
+        o.build(q0, qd0, qdd0, obs)
+        p = ab.Planner(T=T)
+        p.build(q0, qd0, qdd0, obs)
+        assert o.get_nlp_info() == p.get_nlp_info()
+        compare_eval(o, p, DEBUG_K)
+    p = ab.Planner(T=T)
+    with pytest.raises(ab.ArmourError) as e:   # > MAX_OBSTACLE_NUM is rejected like KPR/armour_main.cu:66-72
+        p.build(q0, qd0, qdd0, np.zeros(41 * 12))
+    assert e.value.code == -1
+
+
+def test_call_order_errors(gpu_lib):
+    p = ab.Planner(T=8)
+    with pytest.raises(ab.ArmourError) as e:
+        p.eval_g(np.zeros(7))
+    assert e.value.code == -4
+    with pytest.raises(ab.ArmourError):
+        ab.Planner(T=7)   # NUM_TIME_STEPS must be even (KPR/Parameters.h:16)
+
+
+def test_batch_equals_single_builds(gpu_lib):
+    """Independent problems in one launch give bit-identical tables to one-at-a-time builds."""
+    probs = [make_problem(s, 6) for s in (11, 12, 13)]
+    T = 32
+    pb = ab.Planner(T=T, batch=3)
+    pb.build_batch(np.concatenate([q[0] for q in probs]), np.concatenate([q[1] for q in probs]), np.concatenate([q[2] for q in probs]),
+                   np.concatenate([q[4] for q in probs]), 6)
+    x = DEBUG_K
+    for i, (q0, qd0, qdd0, _, obs) in enumerate(probs):
+        ps = ab.Planner(T=T)
+        ps.build(q0, qd0, qdd0, obs)
+        pb.select_problem(i)
+        g1, J1 = ps.eval_g_jac(x)
+        g2, J2 = pb.eval_g_jac(x)
+        assert np.array_equal(g1, g2) and np.array_equal(J1, J2)
+        assert np.array_equal(ps.torque_radius(), pb.torque_radius())
+        for s in (0, T // 2, T - 1):
+            a, b = ps.get_pz("u_nom", 3, s), pb.get_pz("u_nom", 3, s)
+            assert np.array_equal(a["keys"], b["keys"]) and np.array_equal(a["coeffs"], b["coeffs"])
+
+
+def test_build_is_deterministic(gpu_lib):
+    q0, qd0, qdd0, _, obs = make_problem(21, 10)
+    p = ab.Planner(T=128)
+    p.build(q0, qd0, qdd0, obs)
+    g1, J1 = p.eval_g_jac(DEBUG_K)
+    tr1 = p.torque_radius().copy()
+    p.build(q0, qd0, qdd0, obs)
+    g2, J2 = p.eval_g_jac(DEBUG_K)
+    assert np.array_equal(g1, g2) and np.array_equal(J1, J2) and np.array_equal(tr1, p.torque_radius())
+
+
+# ---- primitive-level parity: PZsparse arithmetic on random operands -------------------------------------------
+def random_pz(rng, rows, cols, n, nvars=6):
+    dim = rows * cols
+    keys = set()
+    while len(keys) < n:
+        k = 0
+        for v in rng.choice(42, size=rng.integers(1, nvars), replace=False):
+            shift = 2 * v if v < 7 else (14 + (v - 7)) if v < 28 else 35 + 2 * (v - 28)
+            k |= 1 << int(shift)
+        keys.add(k)
+    keys = np.array(sorted(keys), dtype=np.uint64)
+    mag = 10.0 ** rng.uniform(-5, 0.5, size=(n, 1))     # straddles the 5e-4 threshold
+    coeffs = rng.standard_normal((n, dim)) * mag
+    coeffs[rng.random((n, dim)) < 0.25] = 0.0            # structural zeros as produced by element extraction
+    return dict(rows=rows, cols=cols, keys=keys, coeffs=coeffs, center=rng.standard_normal(dim), independent=np.abs(rng.standard_normal(dim)) * 1e-2)
+
+
+@pytest.mark.parametrize("op,shape_a,shape_b,na,nb", [
+    ("mul", (3, 3), (3, 1), 3, 200), ("mul", (3, 3), (3, 1), 40, 60), ("mul", (3, 3), (3, 3), 30, 3), ("mul", (1, 1), (1, 1), 90, 20),
+    ("mul", (3, 3), (3, 1), 0, 50), ("mul", (3, 3), (3, 1), 5, 0), ("mul", (1, 1), (1, 1), 0, 0),
+    ("add", (3, 1), (3, 1), 150, 70), ("sub", (3, 1), (3, 1), 10, 300), ("add", (1, 1), (1, 1), 0, 12), ("sub", (1, 1), (1, 1), 33, 33),
+    ("cross", (3, 1), (3, 1), 60, 25), ("cross", (3, 1), (3, 1), 2, 400), ("cross", (3, 1), (3, 1), 0, 7),
+])
+def test_pz_primitives(op, shape_a, shape_b, na, nb, gpu_lib):
+    rng = np.random.default_rng(zlib.crc32(repr((op, shape_a, shape_b, na, nb)).encode()))
+    p = ab.Planner(T=2)
+    for trial in range(3):
+        a = random_pz(rng, shape_a[0], shape_a[1], na)
+        b = random_pz(rng, shape_b[0], shape_b[1], nb)
+        if op in ("add", "sub") and trial == 1 and na and nb:   # force shared keys so that merging and cancellation happen
+            m = min(na, nb) // 2
+            b["keys"][:m] = a["keys"][:m]
+            order = np.argsort(b["keys"], kind="stable")
+            uniq = np.concatenate([[True], np.diff(b["keys"][order]) != 0])
+            order = order[uniq]
+            b["keys"], b["coeffs"] = b["keys"][order], b["coeffs"][order]
+        ref = _oracle.pz_binary(op, a, b)
+        dev = p.pz_binary(op, a, b)
+        assert_pz_equal(ref, dev, "%s trial %d" % (op, trial))
+
+
+def test_pz_self_subtraction_cancels(gpu_lib):
+    rng = np.random.default_rng(5)
+    a = random_pz(rng, 3, 1, 100)
+    p = ab.Planner(T=2)
+    r = p.pz_binary("sub", a, a)
+    assert len(r["keys"]) == 0 and np.all(r["center"] == 0)
+    assert np.all(r["independent"] >= 2 * a["independent"])
