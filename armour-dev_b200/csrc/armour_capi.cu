@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -109,7 +110,7 @@ struct armour_handle {
     RobotModel model;
     Tables tb;
     int P = 1, T = 128, max_obs = 40;
-    int mcap = 1024, ncap = 4096, nt = 256;
+    int mcap = 1024, ncap = 4096, nt = 256, minb = 1;
     char* arena = nullptr;
     size_t arena_stride = 0;
     int grid = 0;
@@ -144,7 +145,7 @@ void free_arena(armour_handle* h) { if (h->arena) cudaFree(h->arena); h->arena =
 int alloc_arena(armour_handle* h) {
     free_arena(h);
     h->arena_stride = arena_bytes(h->mcap, h->ncap);
-    int per_sm = reach_max_ctas_per_sm(h->nt, h->ncap);
+    int per_sm = reach_max_ctas_per_sm(h->nt, h->minb, h->ncap);
     if (per_sm < 1) return fail(ARMOUR_E_CUDA, "reach_build_kernel does not fit on an SM with these capacities");
     const int n_work = h->P * h->T;
     h->grid = std::min(n_work, per_sm * h->sm_count);
@@ -159,7 +160,7 @@ int run_build(armour_handle* h) {   // kernels only; inputs already on the devic
     for (int attempt = 0; attempt < 4; attempt++) {
         CU(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
         CU(cudaEventRecord(h->ev[0], h->stream));
-        CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, n_work, std::min(h->grid, n_work), h->nt, h->stream));
+        CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, n_work, std::min(h->grid, n_work), h->nt, h->minb, h->stream));
         CU(cudaEventRecord(h->ev[1], h->stream));
         CU(launch_hyperplanes(tb, h->stream));
         CU(cudaEventRecord(h->ev[2], h->stream));
@@ -275,6 +276,9 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     h->P = cfg.batch; h->T = cfg.num_time_steps; h->max_obs = cfg.max_obstacles;
     h->mcap = cfg.max_monomials; h->ncap = std::min(cfg.max_entries, 65535 & ~1023); h->nt = cfg.threads_per_cta;
+    // register budget: one plan is latency-bound (1 CTA/SM, all registers); a batch wants more resident CTAs
+    h->minb = cfg.batch > 1 ? 2 : 1;
+    if (const char* e = getenv("ARMOUR_TUNE_MINB")) h->minb = atoi(e);
     kinova_model(h->model);
     *out = h;   // so that armour_destroy can clean up after a partial failure
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));

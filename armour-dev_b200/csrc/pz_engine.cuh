@@ -59,15 +59,32 @@ struct PZ {
 
 // per-CTA scratch (shared memory) ------------------------------------------------------------
 struct Scratch {
-    u64* skey[2];     // [ncap] sort ping-pong
-    u16* sidx[2];     // [ncap]
+    // Sort ping-pong buffers live in dynamic shared memory.  They are kept as shared-window addresses and
+    // turned back into pointers with __cvta_shared_to_generic at each use, so that the compiler emits
+    // LDS/STS instead of generic loads (a pointer loaded from a struct has no known address space).
+    unsigned skey_a[2];   // u64[ncap]
+    unsigned sidx_a[2];   // u16[ncap]
     double* tmp;      // global [9][ncap]: per-key results before compaction
     int ncap;
     double thr;
     int* gerr;        // global error word
-    double red[32 * 18];
-    double redout[18];
+    double red[32 * 32];
     int iscan[34];
+    __device__ __forceinline__ u64* skey(int b) const { return (u64*)__cvta_shared_to_generic((size_t)skey_a[b]); }
+    __device__ __forceinline__ u16* sidx(int b) const { return (u16*)__cvta_shared_to_generic((size_t)sidx_a[b]); }
+    __device__ void bind(unsigned char* smem, int ncap_) {
+        const unsigned base = (unsigned)__cvta_generic_to_shared(smem);
+        skey_a[0] = base; skey_a[1] = base + (unsigned)ncap_ * 8;
+        sidx_a[0] = base + (unsigned)ncap_ * 16; sidx_a[1] = base + (unsigned)ncap_ * 18;
+        ncap = ncap_;
+    }
+};
+
+// exact n / d for n, d < 2^16 with one multiply: q = (n * M) >> 32, M = floor((2^32 - 1) / d) + 1
+struct FastDiv {
+    u64 M; int d;
+    __device__ __forceinline__ explicit FastDiv(int d_) : M((u64)(0xFFFFFFFFu / (unsigned)(d_ > 0 ? d_ : 1)) + 1), d(d_ > 0 ? d_ : 1) {}
+    __device__ __forceinline__ int div(int n) const { return (int)(((u64)(unsigned)n * M) >> 32); }
 };
 
 __device__ __forceinline__ void set_err(Scratch& S, int e) { atomicOr(S.gerr, e); }
@@ -122,70 +139,80 @@ __device__ __forceinline__ void matmat_ru(const double* A, const double* B, doub
 // dominates the reference's value whatever the order.
 __device__ __forceinline__ double inflate(double s, int n) { return __dmul_ru(s, __dadd_ru(1.0, (double)(n + 2) * 0x1p-52)); }
 
-// ---- block-wide reductions / scans ----------------------------------------------------------
-template <int NT, int K>
-__device__ void block_sum_ru(Scratch& S, double (&v)[K]) {   // result in v on every thread
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// ---- block-wide aggregation ---------------------------------------------------------------------
+// Warp-level sum of V values per lane, rounded up, with a transposing butterfly: at each of the first
+// log2(VP) steps a lane keeps one half of its values and trades the other half with its partner, so the
+// whole reduction costs VP - 1 + (5 - log2 VP) exchanges instead of 5 * V.  Afterwards lane L holds in
+// v[0] the warp total of value index L >> (5 - log2 VP).  The summation order is fixed (deterministic).
+template <int VP>
+__device__ __forceinline__ void warp_multi_sum_ru(double (&v)[VP]) {
+    const int lane = threadIdx.x & 31;
+    int off = 16;
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-        double x = v[k];
+    for (int half = VP / 2; half >= 1; half >>= 1, off >>= 1) {
+        const bool hi = (lane & off) != 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x = __dadd_ru(x, __shfl_down_sync(0xffffffffu, x, o));
-        if (lane == 0) S.red[warp * K + k] = x;
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            double x = (lane < NT / 32) ? S.red[lane * K + k] : 0.0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x = __dadd_ru(x, __shfl_down_sync(0xffffffffu, x, o));
-            if (lane == 0) S.redout[k] = x;
+        for (int i = 0; i < half; i++) {
+            const double send = hi ? v[i] : v[i + half];
+            const double keep = hi ? v[i + half] : v[i];
+            v[i] = __dadd_ru(keep, __shfl_xor_sync(0xffffffffu, send, off));
         }
     }
-    __syncthreads();
 #pragma unroll
-    for (int k = 0; k < K; k++) v[k] = S.redout[k];
-    __syncthreads();   // redout may be rewritten by the next reduction
+    for (; off >= 1; off >>= 1) v[0] = __dadd_ru(v[0], __shfl_xor_sync(0xffffffffu, v[0], off));
 }
+template <int V> struct Pow2Ceil { static constexpr int value = V <= 1 ? 1 : V <= 2 ? 2 : V <= 4 ? 4 : V <= 8 ? 8 : V <= 16 ? 16 : 32; };
+template <int VP> struct Log2 { static constexpr int value = VP == 1 ? 0 : VP == 2 ? 1 : VP == 4 ? 2 : VP == 8 ? 3 : VP == 16 ? 4 : 5; };
 
-// exclusive scan of one int per thread; returns this thread's offset, total through `total`
-template <int NT>
-__device__ int block_excl_scan(Scratch& S, int v, int& total) {
+// One barrier: exclusive scan of `cnt` over the block and block-wide round-up sums of red[0..V).
+// Returns this thread's scan offset; `total` is the block total.  After the call, value k's per-warp partial
+// sums are in S.red[w * VP + k] for w < NT/32 (block_total() adds them up).
+template <int NT, int V>
+__device__ __forceinline__ int block_scan_sum(Scratch& S, int cnt, const double (&red)[V], int& total) {
+    constexpr int VP = Pow2Ceil<V>::value;
+    constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int x = v;
+    int incl = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) S.iscan[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-        int w = (lane < NT / 32) ? S.iscan[lane] : 0;
-        int xs = w;
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    double v[VP];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, xs, o); if (lane >= o) xs += y; }
-        S.iscan[lane] = xs - w;
-        if (lane == 31) S.iscan[32] = xs;
-    }
+    for (int k = 0; k < VP; k++) v[k] = k < V ? red[k] : 0.0;
+    warp_multi_sum_ru<VP>(v);
+    if (lane == 31) S.iscan[warp] = incl;
+    if ((lane & ((32 >> Log2<VP>::value) - 1)) == 0) S.red[warp * VP + (lane >> (5 - Log2<VP>::value))] = v[0];
     __syncthreads();
-    const int off = S.iscan[warp] + x - v;
-    total = S.iscan[32];
-    __syncthreads();
-    return off;
+    int before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) { const int t = S.iscan[w]; all += t; if (w < warp) before += t; }
+    total = all;
+    return before + incl - cnt;
+}
+template <int NT, int V>
+__device__ __forceinline__ double block_total(const Scratch& S, int k) {
+    constexpr int VP = Pow2Ceil<V>::value;
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; w++) s = __dadd_ru(s, S.red[w * VP + k]);
+    return s;
 }
 
 // ---- run-structured merge sort on (key, idx) ------------------------------------------------
 // Buffer 0 holds N entries laid out as sorted runs of width W (the last run may be shorter).
-// Returns the buffer that holds the fully sorted sequence.  All (key, idx) pairs are distinct.
+// Returns the buffer that holds the fully sorted sequence.  All (key, idx) pairs are distinct, so
+// ordering by (key, idx) equals a stable sort by key of the list in origin order.
 template <int NT>
-__device__ int merge_sort_runs(Scratch& S, int N, int W) {
+__device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W) {
     int cur = 0;
-    for (int w = W; w < N; w <<= 1) {
-        const u64* ki = S.skey[cur];
-        const u16* ii = S.sidx[cur];
-        u64* ko = S.skey[cur ^ 1];
-        u16* io = S.sidx[cur ^ 1];
+    const FastDiv fd(W);
+    int level = 0;
+    for (int w = W; w < N; w <<= 1, level++) {
+        const u64* ki = S.skey(cur);
+        const u16* ii = S.sidx(cur);
+        u64* ko = S.skey(cur ^ 1);
+        u16* io = S.sidx(cur ^ 1);
         for (int g = threadIdx.x; g < N; g += NT) {
-            const int r = g / w;
+            const int r = fd.div(g) >> level;      // g / (W << level)
             const int base = r * w;
             const int sb = (r ^ 1) * w;
             const u64 k = ki[g];
@@ -215,14 +242,15 @@ __device__ int merge_sort_runs(Scratch& S, int N, int W) {
 //   static constexpr int NACC;                          accumulators per key
 //   void first(unsigned idx, double* acc);              acc  = contribution of the segment's first entry
 //   void next (unsigned idx, double* acc);              acc += contribution (round-to-nearest, in order)
-//   bool finish(const double* acc, double* out, double* drop);   threshold logic; out[DOUT]; drop[DOUT] += |dropped|
-// After the call dst holds keys/coefs/n/abss; `drop` (block-wide sums, rounded up) is returned to the
-// caller, who owns centre and radii.
+//   bool finish(const double* acc, double* out, double* drop);   threshold logic; out[DOUT]; drop[DOUT] = |dropped|
+// cen / rad: centre and the two radii of the result before the dropped monomials are added (computed by the
+// caller from the operands before anything is written, because dst may alias an operand).
+// Barriers: one after the segment pass, one inside block_scan_sum, one at the end.
 template <int NT, int DOUT, class Op>
-__device__ void reduce_emit(Scratch& S, int buf, int N, Op& op, PZ<DOUT>& dst, double (&drop)[DOUT]) {
-    const u64* key = S.skey[buf];
-    const u16* idx = S.sidx[buf];
-    u16* flag = S.sidx[buf ^ 1];
+__device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, PZ<DOUT>& dst, const double* cen, const double (*rad)[DOUT]) {
+    const u64* key = S.skey(buf);
+    const u16* idx = S.sidx(buf);
+    u16* flag = S.sidx(buf ^ 1);
     double* tmp = S.tmp;
     const int ncap = S.ncap;
     double red[2 * DOUT];
@@ -251,40 +279,45 @@ __device__ void reduce_emit(Scratch& S, int buf, int N, Op& op, PZ<DOUT>& dst, d
         flag[g] = f;
     }
     __syncthreads();
-    // scan of keep flags (blocked ranges)
+    // compaction of the kept keys (blocked ranges keep the order)
     const int ipt = (N + NT - 1) / NT;
     const int g0 = min(threadIdx.x * ipt, N), g1 = min(g0 + ipt, N);
     int cnt = 0;
     for (int g = g0; g < g1; g++) cnt += flag[g];
     int total;
-    int off = block_excl_scan<NT>(S, cnt, total);
-    if (total > dst.cap) { if (threadIdx.x == 0) set_err(S, ERR_MONO_CAP); total = 0; }
+    int off = block_scan_sum<NT, 2 * DOUT>(S, cnt, red, total);
+    const int dcap = dst.cap;
+    if (total > dcap) { if (threadIdx.x == 0) set_err(S, ERR_MONO_CAP); total = 0; }
     else {
+        u64* dk = dst.keys;
+        double* dc = dst.coef;
         for (int g = g0; g < g1; g++) {
             if (flag[g]) {
-                dst.keys[off] = key[g];
+                dk[off] = key[g];
 #pragma unroll
-                for (int c = 0; c < DOUT; c++) dst.coef[c * dst.cap + off] = tmp[c * ncap + g];
+                for (int c = 0; c < DOUT; c++) dc[c * dcap + off] = tmp[c * ncap + g];
                 off++;
             }
         }
     }
-    block_sum_ru<NT, 2 * DOUT>(S, red);   // contains the barriers that order the writes above
-    if (threadIdx.x == 0) {
-        dst.n = total;
-#pragma unroll
-        for (int c = 0; c < DOUT; c++) dst.abss[c] = inflate(red[DOUT + c], total);
+    if (threadIdx.x < DOUT) {   // scalar epilogue, one component per thread
+        const int c = threadIdx.x;
+        const double drop = inflate(block_total<NT, 2 * DOUT>(S, c), N);
+        dst.abss[c] = inflate(block_total<NT, 2 * DOUT>(S, DOUT + c), total);
+        dst.center[c] = cen[c];
+        dst.ind[0][c] = __dadd_ru(rad[0][c], drop);
+        dst.ind[1][c] = __dadd_ru(rad[1][c], drop);
+        if (c == 0) dst.n = total;
     }
-#pragma unroll
-    for (int c = 0; c < DOUT; c++) drop[c] = inflate(red[c], N);
+    __syncthreads();
 }
 
 // elementwise variant: no sort, keys are those of `src` in order; op computes out from index i.
 //   bool Op::finish(int i, double* out, double* drop)
 template <int NT, int DOUT, class Op>
-__device__ void elementwise_emit(Scratch& S, int n, const u64* src_keys, Op& op, PZ<DOUT>& dst, double (&drop)[DOUT]) {
-    u16* flag = S.sidx[0];
-    u64* kcopy = S.skey[0];
+__device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* src_keys, Op& op, PZ<DOUT>& dst, const double* cen, const double (*rad)[DOUT]) {
+    u16* flag = S.sidx(0);
+    u64* kcopy = S.skey(0);
     double* tmp = S.tmp;
     const int ncap = S.ncap;
     double red[2 * DOUT];
@@ -311,26 +344,31 @@ __device__ void elementwise_emit(Scratch& S, int n, const u64* src_keys, Op& op,
     int cnt = 0;
     for (int g = g0; g < g1; g++) cnt += flag[g];
     int total;
-    int off = block_excl_scan<NT>(S, cnt, total);
-    if (total > dst.cap) { if (threadIdx.x == 0) set_err(S, ERR_MONO_CAP); total = 0; }
+    int off = block_scan_sum<NT, 2 * DOUT>(S, cnt, red, total);
+    const int dcap = dst.cap;
+    if (total > dcap) { if (threadIdx.x == 0) set_err(S, ERR_MONO_CAP); total = 0; }
     else {
+        u64* dk = dst.keys;
+        double* dc = dst.coef;
         for (int g = g0; g < g1; g++) {
             if (flag[g]) {
-                dst.keys[off] = kcopy[g];
+                dk[off] = kcopy[g];
 #pragma unroll
-                for (int c = 0; c < DOUT; c++) dst.coef[c * dst.cap + off] = tmp[c * ncap + g];
+                for (int c = 0; c < DOUT; c++) dc[c * dcap + off] = tmp[c * ncap + g];
                 off++;
             }
         }
     }
-    block_sum_ru<NT, 2 * DOUT>(S, red);
-    if (threadIdx.x == 0) {
-        dst.n = total;
-#pragma unroll
-        for (int c = 0; c < DOUT; c++) dst.abss[c] = inflate(red[DOUT + c], total);
+    if (threadIdx.x < DOUT) {
+        const int c = threadIdx.x;
+        const double drop = inflate(block_total<NT, 2 * DOUT>(S, c), n);
+        dst.abss[c] = inflate(block_total<NT, 2 * DOUT>(S, DOUT + c), total);
+        dst.center[c] = cen[c];
+        dst.ind[0][c] = __dadd_ru(rad[0][c], drop);
+        dst.ind[1][c] = __dadd_ru(rad[1][c], drop);
+        if (c == 0) dst.n = total;
     }
-#pragma unroll
-    for (int c = 0; c < DOUT; c++) drop[c] = inflate(red[c], n);
+    __syncthreads();
 }
 
 // load coefficient vector i of a PZ
@@ -356,9 +394,10 @@ struct MulOp {
     const PZ<DA>& A;
     const PZ<DB>& B;
     int na, nb;
+    FastDiv fdb;
     double thr;
     double ca[DA], cb[DB];
-    __device__ MulOp(const PZ<DA>& a, const PZ<DB>& b, double t) : A(a), B(b), na(a.n), nb(b.n), thr(t) {
+    __device__ MulOp(const PZ<DA>& a, const PZ<DB>& b, double t) : A(a), B(b), na(a.n), nb(b.n), fdb(b.n), thr(t) {
 #pragma unroll
         for (int c = 0; c < DA; c++) ca[c] = a.center[c];
 #pragma unroll
@@ -370,7 +409,7 @@ struct MulOp {
         else if ((int)idx < na + nb) { ldc<DB>(B, idx - na, b); coef_mul<DA, DB, DO>(ca, b, o); }
         else {
             const int p = idx - na - nb;
-            const int i = p / nb, j = p - i * nb;
+            const int i = fdb.div(p), j = p - i * nb;
             ldc<DA>(A, i, a); ldc<DB>(B, j, b);
             coef_mul<DA, DB, DO>(a, b, o);
         }
@@ -398,8 +437,8 @@ struct MulOp {
 template <int NT>
 __device__ int fill_product_keys(Scratch& S, const u64* ka, int na, const u64* kb, int nb, int& W) {
     const int N = na + nb + na * nb;
-    u64* key = S.skey[0];
-    u16* idx = S.sidx[0];
+    u64* key = S.skey(0);
+    u16* idx = S.sidx(0);
     if (na == 0 || nb == 0) {   // single sorted run
         W = N > 0 ? N : 1;
         for (int g = threadIdx.x; g < N; g += NT) { key[g] = na ? ka[g] : kb[g]; idx[g] = (u16)g; }
@@ -407,8 +446,9 @@ __device__ int fill_product_keys(Scratch& S, const u64* ka, int na, const u64* k
     }
     if (nb >= na) {   // runs: i = 0..na-1 (width nb), then B's own list (nb), then A's own list (na <= nb, last)
         W = nb;
+        const FastDiv fd(nb);
         for (int g = threadIdx.x; g < na * nb; g += NT) {
-            const int i = g / nb, j = g - i * nb;
+            const int i = fd.div(g), j = g - i * nb;
             key[g] = ka[i] + kb[j];   // degrees add; no carry by construction (KPR/PZsparse.cu:938-940)
             idx[g] = (u16)(na + nb + g);
         }
@@ -419,8 +459,9 @@ __device__ int fill_product_keys(Scratch& S, const u64* ka, int na, const u64* k
     }
     else {            // runs: j = 0..nb-1 (width na), then A's own list (na), then B's own list (nb < na, last)
         W = na;
+        const FastDiv fd(na);
         for (int g = threadIdx.x; g < na * nb; g += NT) {
-            const int j = g / na, i = g - j * na;
+            const int j = fd.div(g), i = g - j * na;
             key[g] = ka[i] + kb[j];
             idx[g] = (u16)(na + nb + i * nb + j);
         }
@@ -454,30 +495,23 @@ __device__ void product_radius(const double* ca, const double* abssa, const doub
 }
 
 template <int NT, int DA, int DB, int DO>
-__device__ void pz_mul(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, const PZ<DB>& B) {
-    __syncthreads();
+__device__ __noinline__ void pz_mul(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, const PZ<DB>& B) {
     const int na = A.n, nb = B.n;
     int N = na + nb + na * nb;
     if (N > S.ncap || N > 65535) { if (threadIdx.x == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
     int W = 1;
     if (N > 0) fill_product_keys<NT>(S, A.keys, na, B.keys, nb, W);
-    __syncthreads();
-    const int buf = merge_sort_runs<NT>(S, N, W);
+    // everything the scalar epilogue needs from A and B is read before dst (which may alias) is written
     MulOp<DA, DB, DO> op(A, B, S.thr);
-    // everything the scalar epilogue needs from A and B must be read before dst (may alias) is written
     double cen[DO], rad[2][DO];
     double drop0[DO];
 #pragma unroll
     for (int c = 0; c < DO; c++) drop0[c] = 0.0;
     coef_mul<DA, DB, DO>(op.ca, op.cb, cen);
     for (int v = 0; v < 2; v++) product_radius<DA, DB, DO>(A.center, A.abss, A.ind[v], B.center, B.abss, B.ind[v], drop0, rad[v]);
-    double drop[DO];
-    reduce_emit<NT, DO, MulOp<DA, DB, DO>>(S, buf, N, op, dst, drop);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int c = 0; c < DO; c++) { dst.center[c] = cen[c]; dst.ind[0][c] = __dadd_ru(rad[0][c], drop[c]); dst.ind[1][c] = __dadd_ru(rad[1][c], drop[c]); }
-    }
     __syncthreads();
+    const int buf = merge_sort_runs<NT>(S, N, W);
+    reduce_emit<NT, DO, MulOp<DA, DB, DO>>(S, buf, N, op, dst, cen, rad);
 }
 
 // =============================================================================================
@@ -548,18 +582,32 @@ struct MergeOp {
     }
 };
 // dst = A (+/-) B through views.  The centre of the VIEW_PLACE / VIEW_EXTRACT source is mapped the same way.
+template <int D, int DO>
+__device__ __forceinline__ void view_radius(const View<D>& v, const double* ind, double* o) {   // radii are non-negative: scale by |s| rounded up
+    const double sc = fabs(v.scale);
+    if (v.mode == VIEW_SAME) {
+#pragma unroll
+        for (int c = 0; c < DO; c++) o[c] = v.scaled ? __dmul_ru(sc, ind[c < D ? c : 0]) : ind[c < D ? c : 0];
+    }
+    else if (v.mode == VIEW_EXTRACT) o[0] = v.scaled ? __dmul_ru(sc, ind[v.row < D ? v.row : 0]) : ind[v.row < D ? v.row : 0];
+    else {
+#pragma unroll
+        for (int c = 0; c < DO; c++) o[c] = 0.0;
+        o[v.row < DO ? v.row : 0] = v.scaled ? __dmul_ru(sc, ind[0]) : ind[0];
+    }
+}
+// dst = A (+/-) B through views.  Centre and radii of a VIEW_PLACE / VIEW_EXTRACT source are mapped the same way.
 template <int NT, int DA, int DB, int DO>
-__device__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA>& A, const View<DB>& B, bool negb) {
-    __syncthreads();
+__device__ __noinline__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA> A, const View<DB> B, bool negb) {
     const int na = A.p->n, nb = B.p->n;
     int N = na + nb;
     if (N > S.ncap) { if (threadIdx.x == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
-    u64* key = S.skey[0];
-    u16* idx = S.sidx[0];
+    u64* key = S.skey(0);
+    u16* idx = S.sidx(0);
     int W = 1;
     if (N > 0) {
         const u64* ka = A.p->keys; const u64* kb = B.p->keys;
-        if (na >= nb) {
+        if (na >= nb) {   // the longer run first: runs must have uniform width except the last
             W = na > 0 ? na : 1;
             for (int i = threadIdx.x; i < na; i += NT) { key[i] = ka[i]; idx[i] = (u16)i; }
             for (int j = threadIdx.x; j < nb; j += NT) { key[na + j] = kb[j]; idx[na + j] = (u16)(na + j); }
@@ -570,39 +618,25 @@ __device__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA>& A, const View<
             for (int i = threadIdx.x; i < na; i += NT) { key[nb + i] = ka[i]; idx[nb + i] = (u16)i; }
         }
     }
-    __syncthreads();
-    const int buf = merge_sort_runs<NT>(S, N, W);
     MergeOp<DA, DB, DO> op{A, B, na, negb, S.thr};
     double cen[DO], rad[2][DO];
     {
         double ca[DO], cb[DO];
         view_vec<DA, DO>(A, A.p->center, ca);
         view_vec<DB, DO>(B, B.p->center, cb);
-        if (A.mode == VIEW_PLACE) { /* only used as B */ }
 #pragma unroll
         for (int c = 0; c < DO; c++) cen[c] = negb ? add_rn(ca[c], -cb[c]) : add_rn(ca[c], cb[c]);
         for (int v = 0; v < 2; v++) {
             double ia[DO], ib[DO];
-            View<DA> Aa = A; Aa.scale = fabs(A.scale);
-            View<DB> Bb = B; Bb.scale = fabs(B.scale);
-            // radii are non-negative: scaling by |s| rounded up
-            if (Aa.mode == VIEW_SAME) { for (int c = 0; c < DO; c++) ia[c] = Aa.scaled ? __dmul_ru(Aa.scale, A.p->ind[v][c < DA ? c : 0]) : A.p->ind[v][c < DA ? c : 0]; }
-            else if (Aa.mode == VIEW_EXTRACT) ia[0] = Aa.scaled ? __dmul_ru(Aa.scale, A.p->ind[v][Aa.row < DA ? Aa.row : 0]) : A.p->ind[v][Aa.row < DA ? Aa.row : 0];
-            else { for (int c = 0; c < DO; c++) ia[c] = 0.0; ia[Aa.row < DO ? Aa.row : 0] = Aa.scaled ? __dmul_ru(Aa.scale, A.p->ind[v][0]) : A.p->ind[v][0]; }
-            if (Bb.mode == VIEW_SAME) { for (int c = 0; c < DO; c++) ib[c] = Bb.scaled ? __dmul_ru(Bb.scale, B.p->ind[v][c < DB ? c : 0]) : B.p->ind[v][c < DB ? c : 0]; }
-            else if (Bb.mode == VIEW_EXTRACT) ib[0] = Bb.scaled ? __dmul_ru(Bb.scale, B.p->ind[v][Bb.row < DB ? Bb.row : 0]) : B.p->ind[v][Bb.row < DB ? Bb.row : 0];
-            else { for (int c = 0; c < DO; c++) ib[c] = 0.0; ib[Bb.row < DO ? Bb.row : 0] = Bb.scaled ? __dmul_ru(Bb.scale, B.p->ind[v][0]) : B.p->ind[v][0]; }
+            view_radius<DA, DO>(A, A.p->ind[v], ia);
+            view_radius<DB, DO>(B, B.p->ind[v], ib);
 #pragma unroll
             for (int c = 0; c < DO; c++) rad[v][c] = __dadd_ru(ia[c], ib[c]);
         }
     }
-    double drop[DO];
-    reduce_emit<NT, DO, MergeOp<DA, DB, DO>>(S, buf, N, op, dst, drop);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int c = 0; c < DO; c++) { dst.center[c] = cen[c]; dst.ind[0][c] = __dadd_ru(rad[0][c], drop[c]); dst.ind[1][c] = __dadd_ru(rad[1][c], drop[c]); }
-    }
     __syncthreads();
+    const int buf = merge_sort_runs<NT>(S, N, W);
+    reduce_emit<NT, DO, MergeOp<DA, DB, DO>>(S, buf, N, op, dst, cen, rad);
 }
 template <int NT> __device__ __forceinline__ void pz_add3(Scratch& S, PZ<3>& dst, const PZ<3>& a, const PZ<3>& b) { pz_merge<NT, 3, 3, 3>(S, dst, view(a), view(b), false); }
 // dst = a with the scalar PZ s added into row `row`   (addOneDimPZ)
@@ -620,9 +654,10 @@ struct CrossPPOp {
     const PZ<3>& A;
     const PZ<3>& B;
     int na, nb;
+    FastDiv fdb;
     double thr;
     double ca[3], cb[3];
-    __device__ CrossPPOp(const PZ<3>& a, const PZ<3>& b, double t) : A(a), B(b), na(a.n), nb(b.n), thr(t) {
+    __device__ CrossPPOp(const PZ<3>& a, const PZ<3>& b, double t) : A(a), B(b), na(a.n), nb(b.n), fdb(b.n), thr(t) {
         for (int c = 0; c < 3; c++) { ca[c] = a.center[c]; cb[c] = b.center[c]; }
     }
     __device__ __forceinline__ void term(unsigned idx, double* o) const {
@@ -631,7 +666,7 @@ struct CrossPPOp {
         else if ((int)idx < na + nb) { ldc<3>(B, idx - na, b); a[0] = ca[0]; a[1] = ca[1]; a[2] = ca[2]; }
         else {
             const int p = idx - na - nb;
-            const int i = p / nb, j = p - i * nb;
+            const int i = fdb.div(p), j = p - i * nb;
             ldc<3>(A, i, a); ldc<3>(B, j, b);
         }
         o[0] = mul_rn(a[1], b[2]); o[1] = mul_rn(a[2], b[1]);
@@ -676,15 +711,12 @@ struct CrossPPOp {
     }
 };
 template <int NT>
-__device__ void pz_cross_pp(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B) {
-    __syncthreads();
+__device__ __noinline__ void pz_cross_pp(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B) {
     const int na = A.n, nb = B.n;
     int N = na + nb + na * nb;
     if (N > S.ncap || N > 65535) { if (threadIdx.x == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
     int W = 1;
     if (N > 0) fill_product_keys<NT>(S, A.keys, na, B.keys, nb, W);
-    __syncthreads();
-    const int buf = merge_sort_runs<NT>(S, N, W);
     CrossPPOp op(A, B, S.thr);
     double cen[3], rad[2][3];
     // component c of the result is P - Q with P = a[c+1]*b[c+2], Q = a[c+2]*b[c+1]
@@ -698,12 +730,9 @@ __device__ void pz_cross_pp(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>&
             rad[v][c] = __dadd_ru(rp, rq);
         }
     }
-    double drop[3];
-    reduce_emit<NT, 3, CrossPPOp>(S, buf, N, op, dst, drop);
-    if (threadIdx.x == 0) {
-        for (int c = 0; c < 3; c++) { dst.center[c] = cen[c]; dst.ind[0][c] = __dadd_ru(rad[0][c], drop[c]); dst.ind[1][c] = __dadd_ru(rad[1][c], drop[c]); }
-    }
     __syncthreads();
+    const int buf = merge_sort_runs<NT>(S, N, W);
+    reduce_emit<NT, 3, CrossPPOp>(S, buf, N, op, dst, cen, rad);
 }
 
 // =============================================================================================
@@ -747,8 +776,7 @@ struct CrossConstOp {
     }
 };
 template <int NT>
-__device__ void pz_cross_const(Scratch& S, PZ<3>& dst, const PZ<3>& Z, const double* kvec, bool const_first) {
-    __syncthreads();
+__device__ __noinline__ void pz_cross_const(Scratch& S, PZ<3>& dst, const PZ<3>& Z, const double* kvec, bool const_first) {
     CrossConstOp op{Z, {kvec[0], kvec[1], kvec[2]}, const_first, S.thr};
     double cen[3], rad[2][3];
     op.comp(Z.center, cen);
@@ -762,12 +790,7 @@ __device__ void pz_cross_const(Scratch& S, PZ<3>& dst, const PZ<3>& Z, const dou
         }
     const int n = Z.n;
     const u64* keys = Z.keys;
-    double drop[3];
-    elementwise_emit<NT, 3, CrossConstOp>(S, n, keys, op, dst, drop);
-    if (threadIdx.x == 0) {
-        for (int c = 0; c < 3; c++) { dst.center[c] = cen[c]; dst.ind[0][c] = __dadd_ru(rad[0][c], drop[c]); dst.ind[1][c] = __dadd_ru(rad[1][c], drop[c]); }
-    }
-    __syncthreads();
+    elementwise_emit<NT, 3, CrossConstOp>(S, n, keys, op, dst, cen, rad);
 }
 
 // dst(3x1) = M * v with M a monomial-free 3x3 PZ (centre Mc, radii Mi[2]) — I_arr(i) * w
@@ -788,8 +811,7 @@ struct ConstLeftOp {
     }
 };
 template <int NT>
-__device__ void pz_const_left(Scratch& S, PZ<3>& dst, const double* Mc, const double* Mi0, const double* Mi1, bool scalar, const PZ<3>& V) {
-    __syncthreads();
+__device__ __noinline__ void pz_const_left(Scratch& S, PZ<3>& dst, const double* Mc, const double* Mi0, const double* Mi1, bool scalar, const PZ<3>& V) {
     ConstLeftOp op{V, {0}, scalar, S.thr};
     const int DM = scalar ? 1 : 9;
     for (int c = 0; c < DM; c++) op.M[c] = Mc[c];
@@ -804,12 +826,7 @@ __device__ void pz_const_left(Scratch& S, PZ<3>& dst, const double* Mc, const do
     }
     const int n = V.n;
     const u64* keys = V.keys;
-    double drop[3];
-    elementwise_emit<NT, 3, ConstLeftOp>(S, n, keys, op, dst, drop);
-    if (threadIdx.x == 0) {
-        for (int c = 0; c < 3; c++) { dst.center[c] = cen[c]; dst.ind[0][c] = __dadd_ru(rad[0][c], drop[c]); dst.ind[1][c] = __dadd_ru(rad[1][c], drop[c]); }
-    }
-    __syncthreads();
+    elementwise_emit<NT, 3, ConstLeftOp>(S, n, keys, op, dst, cen, rad);
 }
 
 // dst(3x1) = R * p with R a 3x3 PZ and p a constant vector — FK_R * P   (KPR/Dynamics.cu:76)
@@ -827,8 +844,7 @@ struct ConstRightOp {
     }
 };
 template <int NT>
-__device__ void pz_const_right(Scratch& S, PZ<3>& dst, const PZ<9>& R, const double* pvec) {
-    __syncthreads();
+__device__ __noinline__ void pz_const_right(Scratch& S, PZ<3>& dst, const PZ<9>& R, const double* pvec) {
     ConstRightOp op{R, {pvec[0], pvec[1], pvec[2]}, S.thr};
     double cen[3], rad[2][3];
     double zero3[3] = {0, 0, 0}, drop0[3] = {0, 0, 0};
@@ -836,12 +852,7 @@ __device__ void pz_const_right(Scratch& S, PZ<3>& dst, const PZ<9>& R, const dou
     for (int v = 0; v < 2; v++) product_radius<9, 3, 3>(R.center, R.abss, R.ind[v], pvec, zero3, zero3, drop0, rad[v]);
     const int n = R.n;
     const u64* keys = R.keys;
-    double drop[3];
-    elementwise_emit<NT, 3, ConstRightOp>(S, n, keys, op, dst, drop);
-    if (threadIdx.x == 0) {
-        for (int c = 0; c < 3; c++) { dst.center[c] = cen[c]; dst.ind[0][c] = __dadd_ru(rad[0][c], drop[c]); dst.ind[1][c] = __dadd_ru(rad[1][c], drop[c]); }
-    }
-    __syncthreads();
+    elementwise_emit<NT, 3, ConstRightOp>(S, n, keys, op, dst, cen, rad);
 }
 
 // reset to a monomial-free PZ with centre c (all threads call; thread 0 writes)
@@ -851,6 +862,7 @@ __device__ void pz_set_const(PZ<D>& z, const double* c) {
         z.n = 0;
         for (int i = 0; i < D; i++) { z.center[i] = c ? c[i] : 0.0; z.ind[0][i] = 0.0; z.ind[1][i] = 0.0; z.abss[i] = 0.0; }
     }
+    __syncthreads();
 }
 // dst = src (deep copy)
 template <int NT, int D>

@@ -147,8 +147,8 @@ __device__ void make_poly_zono_joint(const Tables& tb, int prob, int s, int i, P
     const double qc = (ki_lb + ki_ub) * 0.5;
     // The reference's bound of the k-independent part may use an interior stationary value computed with
     // libm pow (Trajectory.cu:812-814); the device evaluates the same polynomial with products, so the radius
-    // can differ in the last bit.  It only feeds the interval remainders below: widen it by 2^-51 (sound).
-    const double rq = __dmul_ru(kd_radius + ki_radius + rm.qe, 1.0 + 0x1p-51);
+    // can differ by a few ulp of |q|.  It only feeds the interval remainders below: widen it by 2^-50 max(|q|, 1) (sound).
+    const double rq = __dadd_ru(kd_radius + ki_radius + rm.qe, fmax(fmax(fabs(ki_lb), fabs(ki_ub)), 1.0) * 0x1p-50);
     const Itv q_rad = itv(-rq, rq);
     const Itv kspan = imul(kd_center, itv(-kr, kr));
     const double cqc = cos(qc), sqc = sin(qc);
@@ -258,10 +258,9 @@ __device__ void make_poly_zono_joint(const Tables& tb, int prob, int s, int i, P
 
 // reduce_link_PZ + export (KPR/PZsparse.cu:370-402, armour_main.cu:123-126)
 template <int NT>
-__device__ void export_link(Scratch& S, const Tables& tb, size_t rec, PZ<3>& L) {
-    __syncthreads();
+__device__ __noinline__ void export_link(Scratch& S, const Tables& tb, size_t rec, PZ<3>& L) {
     const int n = L.n;
-    u16* flag = S.sidx[0];
+    u16* flag = S.sidx(0);
     double red[3] = {0, 0, 0};
     double* gens = tb.gens + rec * 18;
     for (int i = threadIdx.x; i < 18; i += NT) gens[i] = 0.0;
@@ -287,7 +286,7 @@ __device__ void export_link(Scratch& S, const Tables& tb, size_t rec, PZ<3>& L) 
     int cnt = 0;
     for (int g = g0; g < g1; g++) cnt += flag[g];
     int total;
-    int off = block_excl_scan<NT>(S, cnt, total);
+    int off = block_scan_sum<NT, 3>(S, cnt, red, total);
     if (total > LCAP) { if (threadIdx.x == 0) set_err(S, ERR_TABLE_CAP); total = 0; }
     else {
         u64* ok = tb.l_keys + rec * LCAP;
@@ -295,27 +294,24 @@ __device__ void export_link(Scratch& S, const Tables& tb, size_t rec, PZ<3>& L) 
         for (int g = g0; g < g1; g++)
             if (flag[g]) { ok[off] = L.keys[g]; for (int c = 0; c < 3; c++) oc[c * LCAP + off] = L.coef[c * L.cap + g]; off++; }
     }
-    block_sum_ru<NT, 3>(S, red);
-    if (threadIdx.x == 0) {
-        tb.l_n[rec] = total;
-        for (int c = 0; c < 3; c++) {
-            // final radius: inflate by 2^-40 so that last-bit libm differences upstream cannot make it
-            // smaller than the host restatement's (see DESIGN.md "soundness of radii")
-            const double r = __dmul_ru(__dadd_ru(L.ind[0][c], inflate(red[c], n)), 1.0 + 0x1p-40);
-            tb.l_center[rec * 3 + c] = L.center[c];
-            tb.l_ind[rec * 3 + c] = r;
-            gens[(3 + c) * 3 + c] = r;
-        }
+    if (threadIdx.x < 3) {
+        const int c = threadIdx.x;
+        // final radius: inflate by 2^-40 so that last-bit libm differences upstream cannot make it
+        // smaller than the host restatement's (see DESIGN.md "soundness of radii")
+        const double r = __dmul_ru(__dadd_ru(L.ind[0][c], inflate(block_total<NT, 3>(S, c), n)), 1.0 + 0x1p-40);
+        tb.l_center[rec * 3 + c] = L.center[c];
+        tb.l_ind[rec * 3 + c] = r;
+        gens[(3 + c) * 3 + c] = r;
+        if (c == 0) tb.l_n[rec] = total;
     }
     __syncthreads();
 }
 
 // disturbance radius, reduce() and export of one torque PZ (KPR/armour_main.cu:135-142, PZsparse.cu:352-368)
 template <int NT>
-__device__ void export_torque(Scratch& S, const Tables& tb, size_t rec, PZ<1>& U) {
-    __syncthreads();
+__device__ __noinline__ void export_torque(Scratch& S, const Tables& tb, size_t rec, PZ<1>& U) {
     const int n = U.n;
-    u16* flag = S.sidx[0];
+    u16* flag = S.sidx(0);
     double red[1] = {0};
     for (int i = threadIdx.x; i < n; i += NT) {
         const u64 k = U.keys[i];
@@ -329,7 +325,7 @@ __device__ void export_torque(Scratch& S, const Tables& tb, size_t rec, PZ<1>& U
     int cnt = 0;
     for (int g = g0; g < g1; g++) cnt += flag[g];
     int total;
-    int off = block_excl_scan<NT>(S, cnt, total);
+    int off = block_scan_sum<NT, 1>(S, cnt, red, total);
     if (total > UCAP) { if (threadIdx.x == 0) set_err(S, ERR_TABLE_CAP); total = 0; }
     else {
         u64* ok = tb.u_keys + rec * UCAP;
@@ -337,12 +333,11 @@ __device__ void export_torque(Scratch& S, const Tables& tb, size_t rec, PZ<1>& U
         for (int g = g0; g < g1; g++)
             if (flag[g]) { ok[off] = U.keys[g]; oc[off] = U.coef[g]; off++; }
     }
-    block_sum_ru<NT, 1>(S, red);
     if (threadIdx.x == 0) {
         tb.u_n[rec] = total;
         tb.u_center[rec] = U.center[0];
         tb.dist_rad[rec] = __dmul_ru(__dadd_ru(U.ind[1][0], U.ind[0][0]), 1.0 + 0x1p-40);
-        tb.u_ind[rec] = __dmul_ru(__dadd_ru(U.ind[0][0], inflate(red[0], n)), 1.0 + 0x1p-40);
+        tb.u_ind[rec] = __dmul_ru(__dadd_ru(U.ind[0][0], inflate(block_total<NT, 1>(S, 0), n)), 1.0 + 0x1p-40);
     }
     __syncthreads();
 }
@@ -375,19 +370,15 @@ __device__ char* carve(PZ<D>& z, char* p, int cap) {
     return p;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) reach_build_kernel(Tables tb, char* arena, size_t arena_stride, int mcap, int ncap, int n_work) {
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) reach_build_kernel(Tables tb, char* arena, size_t arena_stride, int mcap, int ncap, int n_work) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Scratch S;
     __shared__ Slots Z;
     const RobotModel& rm = c_robot;
     if (threadIdx.x == 0) {
-        unsigned char* p = smem_raw;
-        S.skey[0] = (u64*)p; p += (size_t)ncap * 8;
-        S.skey[1] = (u64*)p; p += (size_t)ncap * 8;
-        S.sidx[0] = (u16*)p; p += (size_t)ncap * 2;
-        S.sidx[1] = (u16*)p; p += (size_t)ncap * 2;
-        S.ncap = ncap; S.thr = tb.thr; S.gerr = tb.err;
+        S.bind(smem_raw, ncap);
+        S.thr = tb.thr; S.gerr = tb.err;
         char* g = arena + (size_t)blockIdx.x * arena_stride;
         PZ<3>* big3[] = {&Z.W, &Z.WD, &Z.WA, &Z.LA, &Z.T1, &Z.T2, &Z.T3, &Z.T4, &Z.T5, &Z.Fv, &Z.Nv, &Z.FKT};
         for (PZ<3>* z : big3) g = carve<3>(*z, g, mcap);
@@ -574,26 +565,22 @@ __global__ void __launch_bounds__(NT) pz_binary_kernel(int op, FlatPZ a, FlatPZ 
     __shared__ PZ<3> a3, b3, r3;
     __shared__ PZ<9> a9, b9, r9;
     if (threadIdx.x == 0) {
-        unsigned char* p = smem_raw;
-        S.skey[0] = (u64*)p; p += (size_t)ncap * 8;
-        S.skey[1] = (u64*)p; p += (size_t)ncap * 8;
-        S.sidx[0] = (u16*)p; p += (size_t)ncap * 2;
-        S.sidx[1] = (u16*)p;
-        S.ncap = ncap; S.thr = thr; S.gerr = err; S.tmp = tmp;
+        S.bind(smem_raw, ncap);
+        S.thr = thr; S.gerr = err; S.tmp = tmp;
         r1.cap = r3.cap = r9.cap = r.cap; r1.keys = r3.keys = r9.keys = r.keys; r1.coef = r3.coef = r9.coef = r.coef;
     }
     __syncthreads();
     FlatOut o; o.n = -1; o.dim = 0;
     if (op == 0) {
-        if (a.dim == 9 && b.dim == 3) { load_flat<9>(a9, a); load_flat<3>(b3, b); pz_mul<NT, 9, 3, 3>(S, r3, a9, b3); o.n = r3.n; o.dim = 3; store_flat<3>(r, r3); }
-        else if (a.dim == 9 && b.dim == 9) { load_flat<9>(a9, a); load_flat<9>(b9, b); pz_mul<NT, 9, 9, 9>(S, r9, a9, b9); o.n = r9.n; o.dim = 9; store_flat<9>(r, r9); }
-        else if (a.dim == 1 && b.dim == 1) { load_flat<1>(a1, a); load_flat<1>(b1, b); pz_mul<NT, 1, 1, 1>(S, r1, a1, b1); o.n = r1.n; o.dim = 1; store_flat<1>(r, r1); }
+        if (a.dim == 9 && b.dim == 3) { load_flat<9>(a9, a); load_flat<3>(b3, b); __syncthreads(); pz_mul<NT, 9, 3, 3>(S, r3, a9, b3); o.n = r3.n; o.dim = 3; store_flat<3>(r, r3); }
+        else if (a.dim == 9 && b.dim == 9) { load_flat<9>(a9, a); load_flat<9>(b9, b); __syncthreads(); pz_mul<NT, 9, 9, 9>(S, r9, a9, b9); o.n = r9.n; o.dim = 9; store_flat<9>(r, r9); }
+        else if (a.dim == 1 && b.dim == 1) { load_flat<1>(a1, a); load_flat<1>(b1, b); __syncthreads(); pz_mul<NT, 1, 1, 1>(S, r1, a1, b1); o.n = r1.n; o.dim = 1; store_flat<1>(r, r1); }
     }
     else if (op == 1 || op == 2) {
-        if (a.dim == 3 && b.dim == 3) { load_flat<3>(a3, a); load_flat<3>(b3, b); pz_merge<NT, 3, 3, 3>(S, r3, view(a3), view(b3), op == 2); o.n = r3.n; o.dim = 3; store_flat<3>(r, r3); }
-        else if (a.dim == 1 && b.dim == 1) { load_flat<1>(a1, a); load_flat<1>(b1, b); pz_merge<NT, 1, 1, 1>(S, r1, view(a1), view(b1), op == 2); o.n = r1.n; o.dim = 1; store_flat<1>(r, r1); }
+        if (a.dim == 3 && b.dim == 3) { load_flat<3>(a3, a); load_flat<3>(b3, b); __syncthreads(); pz_merge<NT, 3, 3, 3>(S, r3, view(a3), view(b3), op == 2); o.n = r3.n; o.dim = 3; store_flat<3>(r, r3); }
+        else if (a.dim == 1 && b.dim == 1) { load_flat<1>(a1, a); load_flat<1>(b1, b); __syncthreads(); pz_merge<NT, 1, 1, 1>(S, r1, view(a1), view(b1), op == 2); o.n = r1.n; o.dim = 1; store_flat<1>(r, r1); }
     }
-    else if (op == 3 && a.dim == 3 && b.dim == 3) { load_flat<3>(a3, a); load_flat<3>(b3, b); pz_cross_pp<NT>(S, r3, a3, b3); o.n = r3.n; o.dim = 3; store_flat<3>(r, r3); }
+    else if (op == 3 && a.dim == 3 && b.dim == 3) { load_flat<3>(a3, a); load_flat<3>(b3, b); __syncthreads(); pz_cross_pp<NT>(S, r3, a3, b3); o.n = r3.n; o.dim = 3; store_flat<3>(r, r3); }
     __syncthreads();
     if (threadIdx.x == 0) { if (o.dim == 1) o.n = r1.n; else if (o.dim == 3) o.n = r3.n; else if (o.dim == 9) o.n = r9.n; *out = o; }
 }
@@ -603,17 +590,20 @@ cudaError_t upload_robot_model(const RobotModel& rm) { return cudaMemcpyToSymbol
 
 size_t reach_smem_bytes(int ncap) { return (size_t)ncap * 20; }
 
-cudaError_t launch_reach_build(const Tables& tb, char* arena, size_t arena_stride, int mcap, int ncap, int n_work, int grid, int nt, cudaStream_t stream) {
+// kernel variants: (threads per CTA, CTAs per SM the register allocation is bounded for)
+typedef void (*ReachKernel)(Tables, char*, size_t, int, int, int);
+static ReachKernel pick_reach_kernel(int nt, int minb) {
+    if (nt == 128) return minb >= 4 ? reach_build_kernel<128, 4> : reach_build_kernel<128, 2>;
+    if (nt == 512) return reach_build_kernel<512, 1>;
+    return minb >= 2 ? reach_build_kernel<256, 2> : reach_build_kernel<256, 1>;
+}
+cudaError_t launch_reach_build(const Tables& tb, char* arena, size_t arena_stride, int mcap, int ncap, int n_work, int grid, int nt, int minb, cudaStream_t stream) {
     const size_t smem = reach_smem_bytes(ncap);
-    cudaError_t e;
-#define ARMOUR_LAUNCH(NTV)                                                                                          \
-    e = cudaFuncSetAttribute(reach_build_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-    if (e != cudaSuccess) return e;                                                                                 \
-    reach_build_kernel<NTV><<<grid, NTV, smem, stream>>>(tb, arena, arena_stride, mcap, ncap, n_work);
-    if (nt == 128) { ARMOUR_LAUNCH(128) }
-    else if (nt == 512) { ARMOUR_LAUNCH(512) }
-    else { ARMOUR_LAUNCH(256) }
-#undef ARMOUR_LAUNCH
+    ReachKernel k = pick_reach_kernel(nt, minb);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int threads = nt == 128 ? 128 : nt == 512 ? 512 : 256;
+    k<<<grid, threads, smem, stream>>>(tb, arena, arena_stride, mcap, ncap, n_work);
     return cudaGetLastError();
 }
 
@@ -625,12 +615,13 @@ cudaError_t launch_pz_binary(int op, const FlatPZ& a, const FlatPZ& b, const Fla
     return cudaGetLastError();
 }
 
-int reach_max_ctas_per_sm(int nt, int ncap) {
+int reach_max_ctas_per_sm(int nt, int minb, int ncap) {
     int n = 0;
     const size_t smem = reach_smem_bytes(ncap);
-    if (nt == 128) { cudaFuncSetAttribute(reach_build_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reach_build_kernel<128>, 128, smem); }
-    else if (nt == 512) { cudaFuncSetAttribute(reach_build_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reach_build_kernel<512>, 512, smem); }
-    else { cudaFuncSetAttribute(reach_build_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reach_build_kernel<256>, 256, smem); }
+    ReachKernel k = pick_reach_kernel(nt, minb);
+    const int threads = nt == 128 ? 128 : nt == 512 ? 512 : 256;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem) != cudaSuccess) return 0;
     return n;
 }
 

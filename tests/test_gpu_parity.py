@@ -133,10 +133,11 @@ def test_wide_k_range_grows_capacities(gpu_lib):
     """k_range = pi/24 (KPR/debug_script.m:35) produces lists beyond the default capacities: the build must grow
     them and still match, not fail or truncate."""
     kr = [np.pi / 24] * 7
-    T = 16
+    T = 128
     o = _oracle.Oracle(T=T, k_range=kr)
     o.build(DEBUG_Q0, DEBUG_QD0, DEBUG_QDD0, [])
-    p = ab.Planner(T=T, k_range=kr, max_monomials=256, max_entries=1024)
+    assert o.op_stats()["max_simplify_in"] > 4096 and o.op_stats()["max_simplify_out"] > 1024
+    p = ab.Planner(T=T, k_range=kr, max_monomials=512, max_entries=2048)
     p.build(DEBUG_Q0, DEBUG_QD0, DEBUG_QDD0, [])
     compare_build(o, p, T)
     compare_eval(o, p, DEBUG_K)
