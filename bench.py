@@ -96,6 +96,24 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_summary.csv")
+    out = {}
+    try:
+        import csv
+        rows = list(csv.reader(open(path)))
+        hdr = rows[0]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        for r in rows[2:]:
+            name = "reach_build_kernel" if "reach_build" in r[0] else "constraint_eval_kernel" if "constraint_eval" in r[0] else None
+            if name:
+                out[name] = (float(r[ir]) + float(r[iw])) * 1e6   # reported in Mbyte
+    except Exception:
+        pass
+    return out
+
+
 def eval_algorithmic_bytes(m):
     """half-space table read once + sliceable tables + outputs, per eval_g+eval_jac_g pair."""
     table = 40 * 36 * T * 7 * N_OBS
@@ -287,6 +305,7 @@ def run_ours(args):
         reach_mean_ms = float(np.mean(reach_ms))
         achieved = flops_per_build / (reach_mean_ms * 1e-3) / 1e12
         eval_bytes = eval_algorithmic_bytes(m)
+        traffic = ncu_traffic()
         eval_mean_ms = float(np.mean(eval_ms))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
@@ -297,11 +316,11 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "reach_build_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": None, "algorithmic_flops_per_launch": flops_per_build, "kernel_ms": reach_mean_ms,
+                         "traffic": traffic.get("reach_build_kernel"), "traffic_source": "profiles/r1_ncu_full_summary.csv (ncu --set full, one launch)", "algorithmic_flops_per_launch": flops_per_build, "kernel_ms": reach_mean_ms,
                          "peak_source": "fp64 FMA micro-benchmark in this run (MEASURED_PEAKS.json has no fp64 entry)",
                          "note": "a single plan is 128 CTAs of dependent small sorts: latency-bound, far from the fp64 roofline (SURVEY.md §7)"},
             "roofline_eval": {"bound": "hbm", "kernel": "constraint_eval_kernel", "achieved": eval_bytes / (eval_mean_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                              "unit": "GB/s", "frac": eval_bytes / (eval_mean_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                              "unit": "GB/s", "frac": eval_bytes / (eval_mean_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get("constraint_eval_kernel"),
                               "algorithmic_bytes_per_launch": eval_bytes, "kernel_ms": eval_mean_ms, "peak_source": peak_src},
             "kernel_ms": {"reach_build": reach_mean_ms, "hyperplanes": float(np.mean(hyper_ms)), "constraint_eval": eval_mean_ms},
             "wall_s_value_region": wall_value_region,
