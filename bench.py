@@ -129,8 +129,8 @@ def run_reference(args):
     if rank != 0:
         return
     import _oracle
-    o = _oracle.Oracle(T=T)
-    cores = o.L.oracle_num_threads()
+    cores = len(os.sched_getaffinity(0))   # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+    o = _oracle.Oracle(T=T, num_threads=cores)
     times = []
     for step in range(args.warmup + args.steps):
         q0, qd0, qdd0, _, obs = problem_for(0, step)
@@ -287,8 +287,8 @@ def run_ours(args):
         # algorithmic flops per build: the oracle's op counter on the reference op sequence
         import _oracle
         flops, cpu_t = [], []
-        o = _oracle.Oracle(T=T)
-        cores = o.L.oracle_num_threads()
+        cores = len(os.sched_getaffinity(0))
+        o = _oracle.Oracle(T=T, num_threads=cores)
         n_sample = 0
         t_budget = time.perf_counter()
         for s in range(W, W + K):
