@@ -631,6 +631,11 @@ int armour_kernel_launches(armour_handle* h, uint64_t* launches) {
     *launches = h->launches;
     return ARMOUR_OK;
 }
+int armour_debug_phase_cycles(uint64_t* cycles8, uint64_t* calls8, int reset) {
+    if (!cycles8 || !calls8) return fail(ARMOUR_E_INVALID, "null argument");
+    read_phase_cycles((unsigned long long*)cycles8, (unsigned long long*)calls8, reset != 0);
+    return ARMOUR_OK;
+}
 int armour_measure_fp64_peak(int device, double* tflops) {
     if (!tflops) return fail(ARMOUR_E_INVALID, "null argument");
     int ndev = 0;

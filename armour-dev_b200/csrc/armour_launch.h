@@ -17,4 +17,5 @@ cudaError_t launch_pz_binary(int op, const FlatPZ& a, const FlatPZ& b, const Fla
 cudaError_t launch_hyperplanes(const Tables& tb, cudaStream_t stream);
 cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* xdev, double* g, double* jac, double* link_center, cudaStream_t stream);
 double measure_fp64_tflops(int sm_count);
+void read_phase_cycles(unsigned long long* cycles, unsigned long long* calls, bool reset);
 }  // namespace armour

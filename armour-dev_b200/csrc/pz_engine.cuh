@@ -55,6 +55,7 @@ struct PZ {
     double center[D];
     double ind[2][D];   // interval radius: [0] nominal inertial parameters, [1] uncertain ones
     double abss[D];     // sum_i |coef_i| rounded up
+    u64 divM;           // FastDiv magic for division by n (kept with the descriptor: one division per op, off the critical path)
 };
 
 // per-CTA scratch (shared memory) ------------------------------------------------------------
@@ -82,12 +83,33 @@ struct Scratch {
 
 // exact n / d for n, d < 2^16 with one multiply: q = (n * M) >> 32, M = floor((2^32 - 1) / d) + 1
 struct FastDiv {
-    u64 M; int d;
-    __device__ __forceinline__ explicit FastDiv(int d_) : M((u64)(0xFFFFFFFFu / (unsigned)(d_ > 0 ? d_ : 1)) + 1), d(d_ > 0 ? d_ : 1) {}
+    u64 M;
+    __device__ __forceinline__ static u64 magic(int d) { return (u64)(0xFFFFFFFFu / (unsigned)(d > 0 ? d : 1)) + 1; }
+    __device__ __forceinline__ explicit FastDiv(u64 M_) : M(M_) {}
     __device__ __forceinline__ int div(int n) const { return (int)(((u64)(unsigned)n * M) >> 32); }
 };
 
 __device__ __forceinline__ void set_err(Scratch& S, int e) { atomicOr(S.gerr, e); }
+
+// Optional per-phase cycle accounting (profiling builds only: -DARMOUR_PHASE_TIMING).  Thread 0 of every CTA
+// charges the cycles since the previous mark to a phase; armour_phase_cycles[] is summed over CTAs.
+enum { PH_FILL = 0, PH_SORT = 1, PH_SEGMENT = 2, PH_COMPACT = 3, PH_ELEMENTWISE = 4, PH_STAGE_A = 5, PH_EXPORT = 6, PH_OTHER = 7, PH_COUNT = 8 };
+#ifdef ARMOUR_PHASE_TIMING
+__device__ unsigned long long armour_phase_cycles[PH_COUNT];
+__device__ unsigned long long armour_phase_calls[PH_COUNT];
+struct PhaseClock { long long last; };
+__shared__ PhaseClock g_phase_clock;
+__device__ __forceinline__ void phase_mark(int ph) {
+    if (threadIdx.x == 0) {
+        const long long t = clock64();
+        atomicAdd(&armour_phase_cycles[ph], (unsigned long long)(t - g_phase_clock.last));
+        atomicAdd(&armour_phase_calls[ph], 1ull);
+        g_phase_clock.last = t;
+    }
+}
+#else
+__device__ __forceinline__ void phase_mark(int) {}
+#endif
 
 // ---- small fp helpers (round-to-nearest, no contraction; -fmad=false is also set) -----------
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
@@ -202,15 +224,17 @@ __device__ __forceinline__ double block_total(const Scratch& S, int k) {
 // Returns the buffer that holds the fully sorted sequence.  All (key, idx) pairs are distinct, so
 // ordering by (key, idx) equals a stable sort by key of the list in origin order.
 template <int NT>
-__device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W) {
+__device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 magicW) {
     int cur = 0;
-    const FastDiv fd(W);
+    const FastDiv fd(magicW);
     int level = 0;
     for (int w = W; w < N; w <<= 1, level++) {
         const u64* ki = S.skey(cur);
         const u16* ii = S.sidx(cur);
         u64* ko = S.skey(cur ^ 1);
         u16* io = S.sidx(cur ^ 1);
+        // rank of each element among its sibling run (binary search; key and index are fetched together so the
+        // tie-break does not add a dependent shared-memory round trip)
         for (int g = threadIdx.x; g < N; g += NT) {
             const int r = fd.div(g) >> level;      // g / (W << level)
             const int base = r * w;
@@ -223,7 +247,8 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W) {
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
                     const u64 km = ki[mid];
-                    const bool less = (km < k) || (km == k && ii[mid] < id);
+                    const unsigned im = ii[mid];
+                    const bool less = (km < k) || (km == k && im < id);
                     if (less) lo = mid + 1; else hi = mid;
                 }
                 pos = min(base, sb) + (g - base) + (lo - sb);
@@ -232,6 +257,7 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W) {
             io[pos] = (u16)id;
         }
         __syncthreads();
+        phase_mark(PH_SORT);
         cur ^= 1;
     }
     return cur;
@@ -243,11 +269,38 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W) {
 //   void first(unsigned idx, double* acc);              acc  = contribution of the segment's first entry
 //   void next (unsigned idx, double* acc);              acc += contribution (round-to-nearest, in order)
 //   bool finish(const double* acc, double* out, double* drop);   threshold logic; out[DOUT]; drop[DOUT] = |dropped|
-// cen / rad: centre and the two radii of the result before the dropped monomials are added (computed by the
-// caller from the operands before anything is written, because dst may alias an operand).
+// Epi interface (scalar epilogue, run by thread c < DOUT only, off the other threads' critical path):
+//   void operator()(int c, double& cen, double& r0, double& r1)   centre and the two radii of component c before the
+//                                                                  dropped monomials are added, read from the operands
+// dst may alias an operand: the epilogue lanes read the operands at entry (before any barrier) and write the
+// descriptor only after the scan barrier, when every thread is done with the operands' descriptors.
+// The epilogue is owned by lanes 0..DOUT-1 of the LAST warp (the warp most likely to be idle in the segment pass):
+// begin() reads the operands before any barrier, finish() adds the block totals and writes the descriptor.
+template <int NT, int DOUT>
+struct ScalarEpilogue {
+    double cen, r0, r1;
+    int c;
+    template <class Epi>
+    __device__ __forceinline__ void begin(const Epi& epi) {
+        c = (int)threadIdx.x - (NT - 32);
+        cen = 0; r0 = 0; r1 = 0;
+        if (c >= 0 && c < DOUT) epi(c, cen, r0, r1);
+    }
+    __device__ __forceinline__ void finish(const Scratch& S, PZ<DOUT>& dst, int n_in, int total) const {
+        if (c >= 0 && c < DOUT) {
+            const double drop = inflate(block_total<NT, 2 * DOUT>(S, c), n_in);
+            dst.abss[c] = inflate(block_total<NT, 2 * DOUT>(S, DOUT + c), total);
+            dst.center[c] = cen;
+            dst.ind[0][c] = __dadd_ru(r0, drop);
+            dst.ind[1][c] = __dadd_ru(r1, drop);
+            if (c == 0) { dst.n = total; dst.divM = FastDiv::magic(total); }
+        }
+    }
+};
+
 // Barriers: one after the segment pass, one inside block_scan_sum, one at the end.
-template <int NT, int DOUT, class Op>
-__device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, PZ<DOUT>& dst, const double* cen, const double (*rad)[DOUT]) {
+template <int NT, int DOUT, class Op, class Epi>
+__device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, PZ<DOUT>& dst, const Epi& epi) {
     const u64* key = S.skey(buf);
     const u16* idx = S.sidx(buf);
     u16* flag = S.sidx(buf ^ 1);
@@ -256,6 +309,8 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
     double red[2 * DOUT];
 #pragma unroll
     for (int c = 0; c < 2 * DOUT; c++) red[c] = 0.0;
+    ScalarEpilogue<NT, DOUT> se;
+    se.begin(epi);
     // pass 1: one thread per segment head
     for (int g = threadIdx.x; g < N; g += NT) {
         const u64 k = key[g];
@@ -279,6 +334,7 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
         flag[g] = f;
     }
     __syncthreads();
+    phase_mark(PH_SEGMENT);
     // compaction of the kept keys (blocked ranges keep the order)
     const int ipt = (N + NT - 1) / NT;
     const int g0 = min(threadIdx.x * ipt, N), g1 = min(g0 + ipt, N);
@@ -300,22 +356,15 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
             }
         }
     }
-    if (threadIdx.x < DOUT) {   // scalar epilogue, one component per thread
-        const int c = threadIdx.x;
-        const double drop = inflate(block_total<NT, 2 * DOUT>(S, c), N);
-        dst.abss[c] = inflate(block_total<NT, 2 * DOUT>(S, DOUT + c), total);
-        dst.center[c] = cen[c];
-        dst.ind[0][c] = __dadd_ru(rad[0][c], drop);
-        dst.ind[1][c] = __dadd_ru(rad[1][c], drop);
-        if (c == 0) dst.n = total;
-    }
+    se.finish(S, dst, N, total);
     __syncthreads();
+    phase_mark(PH_COMPACT);
 }
 
 // elementwise variant: no sort, keys are those of `src` in order; op computes out from index i.
 //   bool Op::finish(int i, double* out, double* drop)
-template <int NT, int DOUT, class Op>
-__device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* src_keys, Op& op, PZ<DOUT>& dst, const double* cen, const double (*rad)[DOUT]) {
+template <int NT, int DOUT, class Op, class Epi>
+__device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* src_keys, Op& op, PZ<DOUT>& dst, const Epi& epi) {
     u16* flag = S.sidx(0);
     u64* kcopy = S.skey(0);
     double* tmp = S.tmp;
@@ -324,6 +373,8 @@ __device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* s
 #pragma unroll
     for (int c = 0; c < 2 * DOUT; c++) red[c] = 0.0;
     if (n > ncap) { if (threadIdx.x == 0) set_err(S, ERR_ENTRY_CAP); n = 0; }
+    ScalarEpilogue<NT, DOUT> se;
+    se.begin(epi);
     for (int i = threadIdx.x; i < n; i += NT) {
         double out[DOUT], dr[DOUT];
 #pragma unroll
@@ -339,6 +390,7 @@ __device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* s
         kcopy[i] = src_keys[i];   // dst may alias src
     }
     __syncthreads();
+    phase_mark(PH_ELEMENTWISE);
     const int ipt = (n + NT - 1) / NT;
     const int g0 = min(threadIdx.x * ipt, n), g1 = min(g0 + ipt, n);
     int cnt = 0;
@@ -359,16 +411,9 @@ __device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* s
             }
         }
     }
-    if (threadIdx.x < DOUT) {
-        const int c = threadIdx.x;
-        const double drop = inflate(block_total<NT, 2 * DOUT>(S, c), n);
-        dst.abss[c] = inflate(block_total<NT, 2 * DOUT>(S, DOUT + c), total);
-        dst.center[c] = cen[c];
-        dst.ind[0][c] = __dadd_ru(rad[0][c], drop);
-        dst.ind[1][c] = __dadd_ru(rad[1][c], drop);
-        if (c == 0) dst.n = total;
-    }
+    se.finish(S, dst, n, total);
     __syncthreads();
+    phase_mark(PH_COMPACT);
 }
 
 // load coefficient vector i of a PZ
@@ -397,7 +442,7 @@ struct MulOp {
     FastDiv fdb;
     double thr;
     double ca[DA], cb[DB];
-    __device__ MulOp(const PZ<DA>& a, const PZ<DB>& b, double t) : A(a), B(b), na(a.n), nb(b.n), fdb(b.n), thr(t) {
+    __device__ MulOp(const PZ<DA>& a, const PZ<DB>& b, double t) : A(a), B(b), na(a.n), nb(b.n), fdb(b.divM), thr(t) {
 #pragma unroll
         for (int c = 0; c < DA; c++) ca[c] = a.center[c];
 #pragma unroll
@@ -435,18 +480,19 @@ struct MulOp {
 
 // fill the sort buffer for a product: rows over the smaller operand, width W = max(na, nb)
 template <int NT>
-__device__ int fill_product_keys(Scratch& S, const u64* ka, int na, const u64* kb, int nb, int& W) {
+__device__ __forceinline__ int fill_product_keys(Scratch& S, const u64* ka, int na, u64 magic_a, const u64* kb, int nb, u64 magic_b, int& W, u64& magicW) {
     const int N = na + nb + na * nb;
     u64* key = S.skey(0);
     u16* idx = S.sidx(0);
     if (na == 0 || nb == 0) {   // single sorted run
         W = N > 0 ? N : 1;
+        magicW = na ? magic_a : magic_b;
         for (int g = threadIdx.x; g < N; g += NT) { key[g] = na ? ka[g] : kb[g]; idx[g] = (u16)g; }
         return N;
     }
     if (nb >= na) {   // runs: i = 0..na-1 (width nb), then B's own list (nb), then A's own list (na <= nb, last)
-        W = nb;
-        const FastDiv fd(nb);
+        W = nb; magicW = magic_b;
+        const FastDiv fd(magic_b);
         for (int g = threadIdx.x; g < na * nb; g += NT) {
             const int i = fd.div(g), j = g - i * nb;
             key[g] = ka[i] + kb[j];   // degrees add; no carry by construction (KPR/PZsparse.cu:938-940)
@@ -458,8 +504,8 @@ __device__ int fill_product_keys(Scratch& S, const u64* ka, int na, const u64* k
         for (int i = threadIdx.x; i < na; i += NT) { key[o0 + i] = ka[i]; idx[o0 + i] = (u16)i; }
     }
     else {            // runs: j = 0..nb-1 (width na), then A's own list (na), then B's own list (nb < na, last)
-        W = na;
-        const FastDiv fd(na);
+        W = na; magicW = magic_a;
+        const FastDiv fd(magic_a);
         for (int g = threadIdx.x; g < na * nb; g += NT) {
             const int j = fd.div(g), i = g - j * na;
             key[g] = ka[i] + kb[j];
@@ -473,26 +519,42 @@ __device__ int fill_product_keys(Scratch& S, const u64* ka, int na, const u64* k
     return N;
 }
 
-// radius of a product, rounded up (KPR/PZsparse.cu:944-989), for radius variant v
+// radius of component c of a product, rounded up (KPR/PZsparse.cu:944-989):
+//   ind_a * ind_b + ((|c_a| + sum|a_i|) * ind_b + ind_a * (|c_b| + sum|b_j|))
+// with matrix products for matrix shapes.  Element (r, col) of a 3x3 result is index r + 3*col.
 template <int DA, int DB, int DO>
-__device__ void product_radius(const double* ca, const double* abssa, const double* inda, const double* cb, const double* abssb, const double* indb,
-                               const double* drop, double* out) {
-    double ma[DA], mb[DB];
-#pragma unroll
-    for (int c = 0; c < DA; c++) ma[c] = __dadd_ru(fabs(ca[c]), abssa[c]);
-#pragma unroll
-    for (int c = 0; c < DB; c++) mb[c] = __dadd_ru(fabs(cb[c]), abssb[c]);
-    double r2[DO], r3[DO], r1[DO];
-    if (DA == 9 && DB == 3) { matvec_ru(ma, indb, r2); matvec_ru(inda, mb, r3); matvec_ru(inda, indb, r1); }
-    else if (DA == 9 && DB == 9) { matmat_ru(ma, indb, r2); matmat_ru(inda, mb, r3); matmat_ru(inda, indb, r1); }
-    else if (DA == 1 && DB == 1) { r2[0] = __dmul_ru(ma[0], indb[0]); r3[0] = __dmul_ru(inda[0], mb[0]); r1[0] = __dmul_ru(inda[0], indb[0]); }
-    else {   // DA == 1: scalar times vector
-#pragma unroll
-        for (int c = 0; c < DO; c++) { r2[c] = __dmul_ru(ma[0], indb[c]); r3[c] = __dmul_ru(inda[0], mb[c]); r1[c] = __dmul_ru(inda[0], indb[c]); }
+__device__ __forceinline__ double product_radius_c(int c, const double* ca, const double* abssa, const double* inda, const double* cb, const double* abssb, const double* indb) {
+    if (DA == 1) {   // scalar times scalar / vector
+        const double ma = __dadd_ru(fabs(ca[0]), abssa[0]), mb = __dadd_ru(fabs(cb[c]), abssb[c]);
+        return __dadd_ru(__dmul_ru(inda[0], indb[c]), __dadd_ru(__dmul_ru(ma, indb[c]), __dmul_ru(inda[0], mb)));
     }
+    const int r = (DB == 9) ? c % 3 : c, col = (DB == 9) ? c / 3 : 0;
+    double r1 = 0, r2 = 0, r3 = 0;
 #pragma unroll
-    for (int c = 0; c < DO; c++) out[c] = __dadd_ru(__dadd_ru(r1[c], __dadd_ru(r2[c], r3[c])), drop[c]);
+    for (int k = 0; k < 3; k++) {
+        const int ia = r + 3 * k, ib = k + 3 * col;
+        const double ma = __dadd_ru(fabs(ca[ia]), abssa[ia]), mb = __dadd_ru(fabs(cb[ib]), abssb[ib]);
+        const double t1 = __dmul_ru(inda[ia], indb[ib]), t2 = __dmul_ru(ma, indb[ib]), t3 = __dmul_ru(inda[ia], mb);
+        r1 = k ? __dadd_ru(r1, t1) : t1; r2 = k ? __dadd_ru(r2, t2) : t2; r3 = k ? __dadd_ru(r3, t3) : t3;
+    }
+    return __dadd_ru(r1, __dadd_ru(r2, r3));
 }
+template <int DA, int DB, int DO>
+__device__ __forceinline__ double product_center_c(int c, const double* ca, const double* cb) {
+    if (DA == 1) return mul_rn(ca[0], cb[c]);
+    const int r = (DB == 9) ? c % 3 : c, col = (DB == 9) ? c / 3 : 0;
+    return add_rn(add_rn(mul_rn(ca[r], cb[3 * col]), mul_rn(ca[r + 3], cb[3 * col + 1])), mul_rn(ca[r + 6], cb[3 * col + 2]));
+}
+template <int DA, int DB, int DO>
+struct MulEpi {
+    const PZ<DA>& A;
+    const PZ<DB>& B;
+    __device__ __forceinline__ void operator()(int c, double& cen, double& r0, double& r1) const {
+        cen = product_center_c<DA, DB, DO>(c, A.center, B.center);
+        r0 = product_radius_c<DA, DB, DO>(c, A.center, A.abss, A.ind[0], B.center, B.abss, B.ind[0]);
+        r1 = product_radius_c<DA, DB, DO>(c, A.center, A.abss, A.ind[1], B.center, B.abss, B.ind[1]);
+    }
+};
 
 template <int NT, int DA, int DB, int DO>
 __device__ __noinline__ void pz_mul(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, const PZ<DB>& B) {
@@ -500,18 +562,13 @@ __device__ __noinline__ void pz_mul(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, co
     int N = na + nb + na * nb;
     if (N > S.ncap || N > 65535) { if (threadIdx.x == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
     int W = 1;
-    if (N > 0) fill_product_keys<NT>(S, A.keys, na, B.keys, nb, W);
-    // everything the scalar epilogue needs from A and B is read before dst (which may alias) is written
+    u64 magicW = 0;
+    if (N > 0) fill_product_keys<NT>(S, A.keys, na, A.divM, B.keys, nb, B.divM, W, magicW);
     MulOp<DA, DB, DO> op(A, B, S.thr);
-    double cen[DO], rad[2][DO];
-    double drop0[DO];
-#pragma unroll
-    for (int c = 0; c < DO; c++) drop0[c] = 0.0;
-    coef_mul<DA, DB, DO>(op.ca, op.cb, cen);
-    for (int v = 0; v < 2; v++) product_radius<DA, DB, DO>(A.center, A.abss, A.ind[v], B.center, B.abss, B.ind[v], drop0, rad[v]);
     __syncthreads();
-    const int buf = merge_sort_runs<NT>(S, N, W);
-    reduce_emit<NT, DO, MulOp<DA, DB, DO>>(S, buf, N, op, dst, cen, rad);
+    phase_mark(PH_FILL);
+    const int buf = merge_sort_runs<NT>(S, N, W, magicW);
+    reduce_emit<NT, DO, MulOp<DA, DB, DO>, MulEpi<DA, DB, DO>>(S, buf, N, op, dst, MulEpi<DA, DB, DO>{A, B});
 }
 
 // =============================================================================================
@@ -544,6 +601,17 @@ __device__ __forceinline__ void view_vec(const View<D>& v, const double* src, do
         for (int c = 0; c < DO; c++) o[c] = 0.0;
         o[v.row < DO ? v.row : 0] = v.scaled ? mul_rn(v.scale, src[0]) : src[0];
     }
+}
+// component c of a view's centre (round-to-nearest scaling) / radius (|scale|, rounded up)
+template <int D>
+__device__ __forceinline__ double view_comp(const View<D>& v, const double* src, int c, bool radius) {
+    int i;
+    if (v.mode == VIEW_SAME) i = c;
+    else if (v.mode == VIEW_EXTRACT) i = v.row;
+    else { if (c != v.row) return 0.0; i = 0; }
+    i = i < D ? i : 0;
+    if (!v.scaled) return src[i];
+    return radius ? __dmul_ru(fabs(v.scale), src[i]) : mul_rn(v.scale, src[i]);
 }
 template <int DA, int DB, int DO>
 struct MergeOp {
@@ -581,21 +649,18 @@ struct MergeOp {
         return true;
     }
 };
-// dst = A (+/-) B through views.  The centre of the VIEW_PLACE / VIEW_EXTRACT source is mapped the same way.
-template <int D, int DO>
-__device__ __forceinline__ void view_radius(const View<D>& v, const double* ind, double* o) {   // radii are non-negative: scale by |s| rounded up
-    const double sc = fabs(v.scale);
-    if (v.mode == VIEW_SAME) {
-#pragma unroll
-        for (int c = 0; c < DO; c++) o[c] = v.scaled ? __dmul_ru(sc, ind[c < D ? c : 0]) : ind[c < D ? c : 0];
+template <int DA, int DB>
+struct MergeEpi {
+    View<DA> A;
+    View<DB> B;
+    bool negb;
+    __device__ __forceinline__ void operator()(int c, double& cen, double& r0, double& r1) const {
+        const double ca = view_comp<DA>(A, A.p->center, c, false), cb = view_comp<DB>(B, B.p->center, c, false);
+        cen = negb ? add_rn(ca, -cb) : add_rn(ca, cb);
+        r0 = __dadd_ru(view_comp<DA>(A, A.p->ind[0], c, true), view_comp<DB>(B, B.p->ind[0], c, true));
+        r1 = __dadd_ru(view_comp<DA>(A, A.p->ind[1], c, true), view_comp<DB>(B, B.p->ind[1], c, true));
     }
-    else if (v.mode == VIEW_EXTRACT) o[0] = v.scaled ? __dmul_ru(sc, ind[v.row < D ? v.row : 0]) : ind[v.row < D ? v.row : 0];
-    else {
-#pragma unroll
-        for (int c = 0; c < DO; c++) o[c] = 0.0;
-        o[v.row < DO ? v.row : 0] = v.scaled ? __dmul_ru(sc, ind[0]) : ind[0];
-    }
-}
+};
 // dst = A (+/-) B through views.  Centre and radii of a VIEW_PLACE / VIEW_EXTRACT source are mapped the same way.
 template <int NT, int DA, int DB, int DO>
 __device__ __noinline__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA> A, const View<DB> B, bool negb) {
@@ -605,38 +670,25 @@ __device__ __noinline__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA> A,
     u64* key = S.skey(0);
     u16* idx = S.sidx(0);
     int W = 1;
+    u64 magicW = 0;
     if (N > 0) {
         const u64* ka = A.p->keys; const u64* kb = B.p->keys;
         if (na >= nb) {   // the longer run first: runs must have uniform width except the last
-            W = na > 0 ? na : 1;
+            W = na > 0 ? na : 1; magicW = A.p->divM;
             for (int i = threadIdx.x; i < na; i += NT) { key[i] = ka[i]; idx[i] = (u16)i; }
             for (int j = threadIdx.x; j < nb; j += NT) { key[na + j] = kb[j]; idx[na + j] = (u16)(na + j); }
         }
         else {
-            W = nb;
+            W = nb; magicW = B.p->divM;
             for (int j = threadIdx.x; j < nb; j += NT) { key[j] = kb[j]; idx[j] = (u16)(na + j); }
             for (int i = threadIdx.x; i < na; i += NT) { key[nb + i] = ka[i]; idx[nb + i] = (u16)i; }
         }
     }
     MergeOp<DA, DB, DO> op{A, B, na, negb, S.thr};
-    double cen[DO], rad[2][DO];
-    {
-        double ca[DO], cb[DO];
-        view_vec<DA, DO>(A, A.p->center, ca);
-        view_vec<DB, DO>(B, B.p->center, cb);
-#pragma unroll
-        for (int c = 0; c < DO; c++) cen[c] = negb ? add_rn(ca[c], -cb[c]) : add_rn(ca[c], cb[c]);
-        for (int v = 0; v < 2; v++) {
-            double ia[DO], ib[DO];
-            view_radius<DA, DO>(A, A.p->ind[v], ia);
-            view_radius<DB, DO>(B, B.p->ind[v], ib);
-#pragma unroll
-            for (int c = 0; c < DO; c++) rad[v][c] = __dadd_ru(ia[c], ib[c]);
-        }
-    }
     __syncthreads();
-    const int buf = merge_sort_runs<NT>(S, N, W);
-    reduce_emit<NT, DO, MergeOp<DA, DB, DO>>(S, buf, N, op, dst, cen, rad);
+    phase_mark(PH_FILL);
+    const int buf = merge_sort_runs<NT>(S, N, W, magicW);
+    reduce_emit<NT, DO, MergeOp<DA, DB, DO>, MergeEpi<DA, DB>>(S, buf, N, op, dst, MergeEpi<DA, DB>{A, B, negb});
 }
 template <int NT> __device__ __forceinline__ void pz_add3(Scratch& S, PZ<3>& dst, const PZ<3>& a, const PZ<3>& b) { pz_merge<NT, 3, 3, 3>(S, dst, view(a), view(b), false); }
 // dst = a with the scalar PZ s added into row `row`   (addOneDimPZ)
@@ -657,7 +709,7 @@ struct CrossPPOp {
     FastDiv fdb;
     double thr;
     double ca[3], cb[3];
-    __device__ CrossPPOp(const PZ<3>& a, const PZ<3>& b, double t) : A(a), B(b), na(a.n), nb(b.n), fdb(b.n), thr(t) {
+    __device__ CrossPPOp(const PZ<3>& a, const PZ<3>& b, double t) : A(a), B(b), na(a.n), nb(b.n), fdb(b.divM), thr(t) {
         for (int c = 0; c < 3; c++) { ca[c] = a.center[c]; cb[c] = b.center[c]; }
     }
     __device__ __forceinline__ void term(unsigned idx, double* o) const {
@@ -710,56 +762,63 @@ struct CrossPPOp {
         return true;
     }
 };
+struct CrossPPEpi {
+    const PZ<3>& A;
+    const PZ<3>& B;
+    // component c of the result is P - Q with P = a[c+1]*b[c+2], Q = a[c+2]*b[c+1]
+    __device__ __forceinline__ void operator()(int c, double& cen, double& r0, double& r1) const {
+        const int i1 = (c + 1) % 3, i2 = (c + 2) % 3;
+        cen = add_rn(mul_rn(A.center[i1], B.center[i2]), -mul_rn(A.center[i2], B.center[i1]));
+        double r[2];
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            const double rp = product_radius_c<1, 1, 1>(0, &A.center[i1], &A.abss[i1], &A.ind[v][i1], &B.center[i2], &B.abss[i2], &B.ind[v][i2]);
+            const double rq = product_radius_c<1, 1, 1>(0, &A.center[i2], &A.abss[i2], &A.ind[v][i2], &B.center[i1], &B.abss[i1], &B.ind[v][i1]);
+            r[v] = __dadd_ru(rp, rq);
+        }
+        r0 = r[0]; r1 = r[1];
+    }
+};
 template <int NT>
 __device__ __noinline__ void pz_cross_pp(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B) {
     const int na = A.n, nb = B.n;
     int N = na + nb + na * nb;
     if (N > S.ncap || N > 65535) { if (threadIdx.x == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
     int W = 1;
-    if (N > 0) fill_product_keys<NT>(S, A.keys, na, B.keys, nb, W);
+    u64 magicW = 0;
+    if (N > 0) fill_product_keys<NT>(S, A.keys, na, A.divM, B.keys, nb, B.divM, W, magicW);
     CrossPPOp op(A, B, S.thr);
-    double cen[3], rad[2][3];
-    // component c of the result is P - Q with P = a[c+1]*b[c+2], Q = a[c+2]*b[c+1]
-    for (int c = 0; c < 3; c++) {
-        const int i1 = (c + 1) % 3, i2 = (c + 2) % 3;
-        cen[c] = add_rn(mul_rn(op.ca[i1], op.cb[i2]), -mul_rn(op.ca[i2], op.cb[i1]));
-        for (int v = 0; v < 2; v++) {
-            double z = 0.0, rp, rq;
-            product_radius<1, 1, 1>(&A.center[i1], &A.abss[i1], &A.ind[v][i1], &B.center[i2], &B.abss[i2], &B.ind[v][i2], &z, &rp);
-            product_radius<1, 1, 1>(&A.center[i2], &A.abss[i2], &A.ind[v][i2], &B.center[i1], &B.abss[i1], &B.ind[v][i1], &z, &rq);
-            rad[v][c] = __dadd_ru(rp, rq);
-        }
-    }
     __syncthreads();
-    const int buf = merge_sort_runs<NT>(S, N, W);
-    reduce_emit<NT, 3, CrossPPOp>(S, buf, N, op, dst, cen, rad);
+    phase_mark(PH_FILL);
+    const int buf = merge_sort_runs<NT>(S, N, W, magicW);
+    reduce_emit<NT, 3, CrossPPOp, CrossPPEpi>(S, buf, N, op, dst, CrossPPEpi{A, B});
 }
 
 // =============================================================================================
 // Elementwise operations (operand lists with identical keys: no sort needed)
 // =============================================================================================
 // cross(PZ a, const b) and cross(const a, PZ b)   (KPR/PZsparse.cu:1118-1132, 1153-1167)
+__device__ __forceinline__ void cross_const_comp(const double* k, bool const_first, const double* z, double* r) {
+    if (const_first) {   // r_c = k[c+1]*z[c+2] - k[c+2]*z[c+1]
+        r[0] = add_rn(mul_rn(k[1], z[2]), -mul_rn(k[2], z[1]));
+        r[1] = add_rn(mul_rn(k[2], z[0]), -mul_rn(k[0], z[2]));
+        r[2] = add_rn(mul_rn(k[0], z[1]), -mul_rn(k[1], z[0]));
+    }
+    else {               // r_c = z[c+1]*k[c+2] - z[c+2]*k[c+1]
+        r[0] = add_rn(mul_rn(k[2], z[1]), -mul_rn(k[1], z[2]));
+        r[1] = add_rn(mul_rn(k[0], z[2]), -mul_rn(k[2], z[0]));
+        r[2] = add_rn(mul_rn(k[1], z[0]), -mul_rn(k[0], z[1]));
+    }
+}
 struct CrossConstOp {
     const PZ<3>& Z;
     double k[3];
     bool const_first;   // true: cross(k, Z); false: cross(Z, k)
     double thr;
-    __device__ __forceinline__ void comp(const double* z, double* r) const {
-        if (const_first) {   // r_c = k[c+1]*z[c+2] - k[c+2]*z[c+1]
-            r[0] = add_rn(mul_rn(k[1], z[2]), -mul_rn(k[2], z[1]));
-            r[1] = add_rn(mul_rn(k[2], z[0]), -mul_rn(k[0], z[2]));
-            r[2] = add_rn(mul_rn(k[0], z[1]), -mul_rn(k[1], z[0]));
-        }
-        else {               // r_c = z[c+1]*k[c+2] - z[c+2]*k[c+1]
-            r[0] = add_rn(mul_rn(k[2], z[1]), -mul_rn(k[1], z[2]));
-            r[1] = add_rn(mul_rn(k[0], z[2]), -mul_rn(k[2], z[0]));
-            r[2] = add_rn(mul_rn(k[1], z[0]), -mul_rn(k[0], z[1]));
-        }
-    }
     __device__ __forceinline__ bool finish(int i, double* out, double* drop) const {
         double z[3], r[3];
         ldc<3>(Z, i, z);
-        comp(z, r);
+        cross_const_comp(k, const_first, z, r);
         bool any = false;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
@@ -775,22 +834,24 @@ struct CrossConstOp {
         return true;
     }
 };
+struct CrossConstEpi {
+    const PZ<3>& Z;
+    double k[3];
+    bool const_first;
+    __device__ __forceinline__ void operator()(int c, double& cen, double& r0, double& r1) const {
+        double r[3];
+        cross_const_comp(k, const_first, Z.center, r);
+        cen = r[c];
+        const int i1 = (c + 1) % 3, i2 = (c + 2) % 3;
+        // operator*(double) scales the radius by |k|, operator- adds the two radii
+        r0 = __dadd_ru(__dmul_ru(Z.ind[0][i1], fabs(k[i2])), __dmul_ru(Z.ind[0][i2], fabs(k[i1])));
+        r1 = __dadd_ru(__dmul_ru(Z.ind[1][i1], fabs(k[i2])), __dmul_ru(Z.ind[1][i2], fabs(k[i1])));
+    }
+};
 template <int NT>
 __device__ __noinline__ void pz_cross_const(Scratch& S, PZ<3>& dst, const PZ<3>& Z, const double* kvec, bool const_first) {
     CrossConstOp op{Z, {kvec[0], kvec[1], kvec[2]}, const_first, S.thr};
-    double cen[3], rad[2][3];
-    op.comp(Z.center, cen);
-    for (int v = 0; v < 2; v++)
-        for (int c = 0; c < 3; c++) {
-            const int i1 = (c + 1) % 3, i2 = (c + 2) % 3;
-            // operator*(double) scales the radius by |k|, operator- adds the two radii.
-            // cross(Z, k): r_c = z[i1]*k[i2] - z[i2]*k[i1];  cross(k, Z): r_c = k[i1]*z[i2] - k[i2]*z[i1]
-            rad[v][c] = const_first ? __dadd_ru(__dmul_ru(Z.ind[v][i2], fabs(kvec[i1])), __dmul_ru(Z.ind[v][i1], fabs(kvec[i2])))
-                                    : __dadd_ru(__dmul_ru(Z.ind[v][i1], fabs(kvec[i2])), __dmul_ru(Z.ind[v][i2], fabs(kvec[i1])));
-        }
-    const int n = Z.n;
-    const u64* keys = Z.keys;
-    elementwise_emit<NT, 3, CrossConstOp>(S, n, keys, op, dst, cen, rad);
+    elementwise_emit<NT, 3, CrossConstOp, CrossConstEpi>(S, Z.n, Z.keys, op, dst, CrossConstEpi{Z, {kvec[0], kvec[1], kvec[2]}, const_first});
 }
 
 // dst(3x1) = M * v with M a monomial-free 3x3 PZ (centre Mc, radii Mi[2]) — I_arr(i) * w
@@ -810,23 +871,32 @@ struct ConstLeftOp {
         return true;
     }
 };
+struct ConstLeftEpi {
+    const PZ<3>& V;
+    const double* Mc;
+    const double* Mi0;
+    const double* Mi1;
+    bool scalar;
+    __device__ __forceinline__ void operator()(int c, double& cen, double& r0, double& r1) const {
+        const double zero9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (scalar) {
+            cen = mul_rn(Mc[0], V.center[c]);
+            r0 = product_radius_c<1, 3, 3>(c, Mc, zero9, Mi0, V.center, V.abss, V.ind[0]);
+            r1 = product_radius_c<1, 3, 3>(c, Mc, zero9, Mi1, V.center, V.abss, V.ind[1]);
+        }
+        else {
+            cen = product_center_c<9, 3, 3>(c, Mc, V.center);
+            r0 = product_radius_c<9, 3, 3>(c, Mc, zero9, Mi0, V.center, V.abss, V.ind[0]);
+            r1 = product_radius_c<9, 3, 3>(c, Mc, zero9, Mi1, V.center, V.abss, V.ind[1]);
+        }
+    }
+};
 template <int NT>
 __device__ __noinline__ void pz_const_left(Scratch& S, PZ<3>& dst, const double* Mc, const double* Mi0, const double* Mi1, bool scalar, const PZ<3>& V) {
     ConstLeftOp op{V, {0}, scalar, S.thr};
     const int DM = scalar ? 1 : 9;
     for (int c = 0; c < DM; c++) op.M[c] = Mc[c];
-    double cen[3], rad[2][3];
-    double zero9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, drop0[3] = {0, 0, 0};
-    if (scalar) { for (int c = 0; c < 3; c++) cen[c] = mul_rn(Mc[0], V.center[c]); }
-    else matvec_rn(Mc, V.center, cen);
-    for (int v = 0; v < 2; v++) {
-        const double* Mi = v ? Mi1 : Mi0;
-        if (scalar) product_radius<1, 3, 3>(Mc, zero9, Mi, V.center, V.abss, V.ind[v], drop0, rad[v]);
-        else product_radius<9, 3, 3>(Mc, zero9, Mi, V.center, V.abss, V.ind[v], drop0, rad[v]);
-    }
-    const int n = V.n;
-    const u64* keys = V.keys;
-    elementwise_emit<NT, 3, ConstLeftOp>(S, n, keys, op, dst, cen, rad);
+    elementwise_emit<NT, 3, ConstLeftOp, ConstLeftEpi>(S, V.n, V.keys, op, dst, ConstLeftEpi{V, Mc, Mi0, Mi1, scalar});
 }
 
 // dst(3x1) = R * p with R a 3x3 PZ and p a constant vector — FK_R * P   (KPR/Dynamics.cu:76)
@@ -843,39 +913,28 @@ struct ConstRightOp {
         return true;
     }
 };
+struct ConstRightEpi {
+    const PZ<9>& R;
+    double p[3];
+    __device__ __forceinline__ void operator()(int c, double& cen, double& r0, double& r1) const {
+        const double zero3[3] = {0, 0, 0};
+        cen = product_center_c<9, 3, 3>(c, R.center, p);
+        r0 = product_radius_c<9, 3, 3>(c, R.center, R.abss, R.ind[0], p, zero3, zero3);
+        r1 = product_radius_c<9, 3, 3>(c, R.center, R.abss, R.ind[1], p, zero3, zero3);
+    }
+};
 template <int NT>
 __device__ __noinline__ void pz_const_right(Scratch& S, PZ<3>& dst, const PZ<9>& R, const double* pvec) {
     ConstRightOp op{R, {pvec[0], pvec[1], pvec[2]}, S.thr};
-    double cen[3], rad[2][3];
-    double zero3[3] = {0, 0, 0}, drop0[3] = {0, 0, 0};
-    matvec_rn(R.center, pvec, cen);
-    for (int v = 0; v < 2; v++) product_radius<9, 3, 3>(R.center, R.abss, R.ind[v], pvec, zero3, zero3, drop0, rad[v]);
-    const int n = R.n;
-    const u64* keys = R.keys;
-    elementwise_emit<NT, 3, ConstRightOp>(S, n, keys, op, dst, cen, rad);
+    elementwise_emit<NT, 3, ConstRightOp, ConstRightEpi>(S, R.n, R.keys, op, dst, ConstRightEpi{R, {pvec[0], pvec[1], pvec[2]}});
 }
 
 // reset to a monomial-free PZ with centre c (all threads call; thread 0 writes)
 template <int D>
 __device__ void pz_set_const(PZ<D>& z, const double* c) {
     if (threadIdx.x == 0) {
-        z.n = 0;
+        z.n = 0; z.divM = FastDiv::magic(0);
         for (int i = 0; i < D; i++) { z.center[i] = c ? c[i] : 0.0; z.ind[0][i] = 0.0; z.ind[1][i] = 0.0; z.abss[i] = 0.0; }
-    }
-    __syncthreads();
-}
-// dst = src (deep copy)
-template <int NT, int D>
-__device__ void pz_copy(PZ<D>& dst, const PZ<D>& src) {
-    __syncthreads();
-    const int n = src.n;
-    for (int i = threadIdx.x; i < n; i += NT) {
-        dst.keys[i] = src.keys[i];
-        for (int c = 0; c < D; c++) dst.coef[c * dst.cap + i] = src.coef[c * src.cap + i];
-    }
-    if (threadIdx.x == 0) {
-        dst.n = n;
-        for (int c = 0; c < D; c++) { dst.center[c] = src.center[c]; dst.ind[0][c] = src.ind[0][c]; dst.ind[1][c] = src.ind[1][c]; dst.abss[c] = src.abss[c]; }
     }
     __syncthreads();
 }

@@ -103,7 +103,7 @@ __device__ void small_scalar(PZ<1>& z, double center, u64 k0, double c0, u64 k1,
     if (norm1(&c0) > thr) { z.keys[n] = k0; z.coef[n] = c0; abss = __dadd_ru(abss, fabs(c0)); n++; } else ind = __dadd_ru(ind, fabs(c0));
     if (norm1(&c1) > thr) { z.keys[n] = k1; z.coef[n] = c1; abss = __dadd_ru(abss, fabs(c1)); n++; } else ind = __dadd_ru(ind, fabs(c1));
     ind = __dmul_ru(ind, 1.0 + 0x1p-40);   // a dropped coefficient built from device libm values may be an ulp below the host's
-    z.n = n; z.center[0] = center; z.ind[0][0] = ind; z.ind[1][0] = ind; z.abss[0] = abss;
+    z.n = n; z.divM = FastDiv::magic(n); z.center[0] = center; z.ind[0][0] = ind; z.ind[1][0] = ind; z.abss[0] = abss;
 }
 template <int D>
 __device__ void export_small(SmallRec& r, const PZ<D>& z) {
@@ -211,10 +211,10 @@ __device__ void make_poly_zono_joint(const Tables& tb, int prob, int s, int i, P
                 nr++;
             }
         }
-        R.n = nr;
+        R.n = nr; R.divM = FastDiv::magic(nr);
         for (int c = 0; c < 9; c++) { R.center[c] = cen[c]; R.ind[0][c] = ind[c]; R.ind[1][c] = ind[c]; R.abss[c] = abss[c]; }
         // R_t = R.transpose()
-        Rt.n = nr;
+        Rt.n = nr; Rt.divM = FastDiv::magic(nr);
         for (int r = 0; r < 3; r++)
             for (int c = 0; c < 3; c++) {
                 const int src = r + 3 * c, dstp = c + 3 * r;
@@ -305,6 +305,7 @@ __device__ __noinline__ void export_link(Scratch& S, const Tables& tb, size_t re
         if (c == 0) tb.l_n[rec] = total;
     }
     __syncthreads();
+    phase_mark(PH_EXPORT);
 }
 
 // disturbance radius, reduce() and export of one torque PZ (KPR/armour_main.cu:135-142, PZsparse.cu:352-368)
@@ -340,6 +341,7 @@ __device__ __noinline__ void export_torque(Scratch& S, const Tables& tb, size_t 
         tb.u_ind[rec] = __dmul_ru(__dadd_ru(U.ind[0][0], inflate(block_total<NT, 1>(S, 0), n)), 1.0 + 0x1p-40);
     }
     __syncthreads();
+    phase_mark(PH_EXPORT);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -363,7 +365,7 @@ size_t arena_bytes(int mcap, int ncap) {
 
 template <int D>
 __device__ char* carve(PZ<D>& z, char* p, int cap) {
-    z.cap = cap; z.n = 0;
+    z.cap = cap; z.n = 0; z.divM = FastDiv::magic(0);
     z.keys = (u64*)p; p += (size_t)cap * 8;
     z.coef = (double*)p; p += (size_t)cap * 8 * D;
     for (int c = 0; c < D; c++) { z.center[c] = 0; z.ind[0][c] = 0; z.ind[1][c] = 0; z.abss[c] = 0; }
@@ -396,6 +398,9 @@ __global__ void __launch_bounds__(NT, MINB) reach_build_kernel(Tables tb, char* 
     __syncthreads();
     const double zero3[3] = {0, 0, 0};
 
+#ifdef ARMOUR_PHASE_TIMING
+    if (threadIdx.x == 0) g_phase_clock.last = clock64();
+#endif
     for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
         const int prob = work / tb.T, s = work - prob * tb.T;
         __syncthreads();
@@ -425,15 +430,16 @@ __global__ void __launch_bounds__(NT, MINB) reach_build_kernel(Tables tb, char* 
                 }
                 else ind[j] = fabs(g);
             }
-            L0.n = n;
+            L0.n = n; L0.divM = FastDiv::magic(n);
             for (int c = 0; c < 3; c++) { L0.center[c] = rm.link_c[i][c]; L0.ind[0][c] = ind[c]; L0.ind[1][c] = ind[c]; L0.abss[c] = abss[c]; }
         }
         if (threadIdx.x == NJ) {   // R(NUM_JOINTS) = identity
             PZ<9>& R = Z.R[NJ];
-            R.n = 0;
+            R.n = 0; R.divM = FastDiv::magic(0);
             for (int c = 0; c < 9; c++) { R.center[c] = rm.R0[NJ][c]; R.ind[0][c] = 0; R.ind[1][c] = 0; R.abss[c] = 0; }
         }
         __syncthreads();
+        phase_mark(PH_STAGE_A);
 
         // ---- stage B: forward kinematics (KPR/Dynamics.cu:69-81) ------------------------------------
         pz_set_const<9>(Z.FKR, rm.R0[NJ]);
@@ -544,7 +550,7 @@ __global__ void __launch_bounds__(NT, MINB) reach_build_kernel(Tables tb, char* 
 template <int D>
 __device__ void load_flat(PZ<D>& z, const FlatPZ& f) {
     if (threadIdx.x == 0) {
-        z.n = f.n; z.cap = f.cap; z.keys = f.keys; z.coef = f.coef;
+        z.n = f.n; z.divM = FastDiv::magic(f.n); z.cap = f.cap; z.keys = f.keys; z.coef = f.coef;
         for (int c = 0; c < D; c++) {
             z.center[c] = f.center[c]; z.ind[0][c] = f.ind[c]; z.ind[1][c] = f.ind[c];
             double s = 0.0;
@@ -613,6 +619,22 @@ cudaError_t launch_pz_binary(int op, const FlatPZ& a, const FlatPZ& b, const Fla
     if (e != cudaSuccess) return e;
     pz_binary_kernel<256><<<1, 256, smem, stream>>>(op, a, b, r, out, tmp, ncap, thr, err);
     return cudaGetLastError();
+}
+
+// profiling builds only: cycles and call counts per phase, summed over CTAs (zeros otherwise)
+void read_phase_cycles(unsigned long long* cycles, unsigned long long* calls, bool reset) {
+#ifdef ARMOUR_PHASE_TIMING
+    cudaMemcpyFromSymbol(cycles, armour_phase_cycles, sizeof(unsigned long long) * PH_COUNT);
+    cudaMemcpyFromSymbol(calls, armour_phase_calls, sizeof(unsigned long long) * PH_COUNT);
+    if (reset) {
+        unsigned long long z[PH_COUNT] = {0};
+        cudaMemcpyToSymbol(armour_phase_cycles, z, sizeof(z));
+        cudaMemcpyToSymbol(armour_phase_calls, z, sizeof(z));
+    }
+#else
+    for (int i = 0; i < PH_COUNT; i++) { cycles[i] = 0; calls[i] = 0; }
+    (void)reset;
+#endif
 }
 
 int reach_max_ctas_per_sm(int nt, int minb, int ncap) {

@@ -137,6 +137,9 @@ int armour_upload_problems(armour_handle* h, int count, const double* q0, const 
 int armour_build_resident(armour_handle* h);
 int armour_eval_resident(armour_handle* h, const double* x); /* x == NULL: reuse the x uploaded by armour_upload_x */
 int armour_upload_x(armour_handle* h, const double* x);
+/* profiling builds (-DARMOUR_PHASE_TIMING) only: cycles / calls per engine phase summed over CTAs; zeros otherwise.
+ * phases: 0 fill, 1 sort level, 2 segment walk, 3 scan+compact, 4 element-wise, 5 stage A, 6 export, 7 other */
+int armour_debug_phase_cycles(uint64_t* cycles8, uint64_t* calls8, int reset);
 /* fp64 FMA micro-benchmark (TFLOP/s) used as the fp64 roofline denominator */
 int armour_measure_fp64_peak(int device, double* tflops);
 
