@@ -65,19 +65,29 @@ struct Scratch {
     // LDS/STS instead of generic loads (a pointer loaded from a struct has no known address space).
     unsigned skey_a[2];   // u64[ncap]
     unsigned sidx_a[2];   // u16[ncap]
-    double* tmp;      // global [9][ncap]: per-key results before compaction
+    double* tmp;      // global [9][ncap]: per-key results before compaction (operations with more than TCAP candidates)
+    unsigned stmp_a;  // shared [3][TCAP]: the same for small operations (most of them): no L2 round trip
     int ncap;
-    double thr;
+    double thr;   // squared-domain threshold (Scratch::thr_sq)
+    double thr_sq;    // largest x with RN(sqrt(x)) <= thr: "norm <= thr" is tested as "squared norm <= thr_sq", exactly
     int* gerr;        // global error word
     double red[32 * 32];
     int iscan[34];
     __device__ __forceinline__ u64* skey(int b) const { return (u64*)__cvta_shared_to_generic((size_t)skey_a[b]); }
     __device__ __forceinline__ u16* sidx(int b) const { return (u16*)__cvta_shared_to_generic((size_t)sidx_a[b]); }
+    static constexpr int TCAP = 1024;
+    __device__ __forceinline__ double* stmp() const { return (double*)__cvta_shared_to_generic((size_t)stmp_a); }
     __device__ void bind(unsigned char* smem, int ncap_) {
         const unsigned base = (unsigned)__cvta_generic_to_shared(smem);
         skey_a[0] = base; skey_a[1] = base + (unsigned)ncap_ * 8;
         sidx_a[0] = base + (unsigned)ncap_ * 16; sidx_a[1] = base + (unsigned)ncap_ * 18;
+        stmp_a = base + (unsigned)ncap_ * 20;
         ncap = ncap_;
+    }
+    // per-key staging buffer and its plane stride for an operation with n candidates and D output components
+    __device__ __forceinline__ double* staging(int n, int D, int& stride) const {
+        if (D <= 3 && n <= TCAP) { stride = TCAP; return stmp(); }
+        stride = ncap; return tmp;
     }
 };
 
@@ -90,6 +100,18 @@ struct FastDiv {
 };
 
 __device__ __forceinline__ void set_err(Scratch& S, int e) { atomicOr(S.gerr, e); }
+
+// sqrt is monotone, so {x : RN(sqrt(x)) <= thr} is a down-set {x <= X}.  Find X once per kernel; the hot loops then
+// compare squared norms and never take a square root, with bit-identical keep/drop decisions.
+__device__ inline double squared_threshold(double thr) {
+    double x = __dmul_rn(thr, thr);
+    for (int i = 0; i < 8 && __dsqrt_rn(x) > thr; i++) x = __longlong_as_double(__double_as_longlong(x) - 1);
+    for (int i = 0; i < 8; i++) {
+        const double up = __longlong_as_double(__double_as_longlong(x) + 1);
+        if (__dsqrt_rn(up) <= thr) x = up; else break;
+    }
+    return x;
+}
 
 // Optional per-phase cycle accounting (profiling builds only: -DARMOUR_PHASE_TIMING).  Thread 0 of every CTA
 // charges the cycles since the previous mark to a phase; armour_phase_cycles[] is summed over CTAs.
@@ -114,10 +136,11 @@ __device__ __forceinline__ void phase_mark(int) {}
 // ---- small fp helpers (round-to-nearest, no contraction; -fmad=false is also set) -----------
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-// Frobenius norms in Eigen 3.3's reduction order (see oracle/oracle_pz.hpp Mat::squaredNorm)
-__device__ __forceinline__ double norm1(const double* v) { return __dsqrt_rn(mul_rn(v[0], v[0])); }
+// squared Frobenius norms in Eigen 3.3's reduction order (see oracle/oracle_pz.hpp Mat::squaredNorm)
+// squared norms; compare against Scratch::thr_sq
+__device__ __forceinline__ double norm1(const double* v) { return mul_rn(v[0], v[0]); }
 __device__ __forceinline__ double norm3(const double* v) {
-    return __dsqrt_rn(add_rn(add_rn(mul_rn(v[0], v[0]), mul_rn(v[1], v[1])), mul_rn(v[2], v[2])));
+    return add_rn(add_rn(mul_rn(v[0], v[0]), mul_rn(v[1], v[1])), mul_rn(v[2], v[2]));
 }
 __device__ __forceinline__ double norm9(const double* v) {
     double p0a = add_rn(mul_rn(v[0], v[0]), mul_rn(v[4], v[4]));
@@ -125,7 +148,7 @@ __device__ __forceinline__ double norm9(const double* v) {
     double p1a = add_rn(mul_rn(v[2], v[2]), mul_rn(v[6], v[6]));
     double p1b = add_rn(mul_rn(v[3], v[3]), mul_rn(v[7], v[7]));
     double s = add_rn(add_rn(p0a, p1a), add_rn(p0b, p1b));
-    return __dsqrt_rn(add_rn(s, mul_rn(v[8], v[8])));
+    return add_rn(s, mul_rn(v[8], v[8]));
 }
 template <int D>
 __device__ __forceinline__ double normD(const double* v) {
@@ -304,8 +327,8 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
     const u64* key = S.skey(buf);
     const u16* idx = S.sidx(buf);
     u16* flag = S.sidx(buf ^ 1);
-    double* tmp = S.tmp;
-    const int ncap = S.ncap;
+    int ncap;
+    double* tmp = S.staging(N, DOUT, ncap);
     double red[2 * DOUT];
 #pragma unroll
     for (int c = 0; c < 2 * DOUT; c++) red[c] = 0.0;
@@ -367,12 +390,12 @@ template <int NT, int DOUT, class Op, class Epi>
 __device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* src_keys, Op& op, PZ<DOUT>& dst, const Epi& epi) {
     u16* flag = S.sidx(0);
     u64* kcopy = S.skey(0);
-    double* tmp = S.tmp;
-    const int ncap = S.ncap;
     double red[2 * DOUT];
 #pragma unroll
     for (int c = 0; c < 2 * DOUT; c++) red[c] = 0.0;
-    if (n > ncap) { if (threadIdx.x == 0) set_err(S, ERR_ENTRY_CAP); n = 0; }
+    if (n > S.ncap) { if (threadIdx.x == 0) set_err(S, ERR_ENTRY_CAP); n = 0; }
+    int ncap;
+    double* tmp = S.staging(n, DOUT, ncap);
     ScalarEpilogue<NT, DOUT> se;
     se.begin(epi);
     for (int i = threadIdx.x; i < n; i += NT) {
@@ -440,7 +463,7 @@ struct MulOp {
     const PZ<DB>& B;
     int na, nb;
     FastDiv fdb;
-    double thr;
+    double thr;   // squared-domain threshold (Scratch::thr_sq)
     double ca[DA], cb[DB];
     __device__ MulOp(const PZ<DA>& a, const PZ<DB>& b, double t) : A(a), B(b), na(a.n), nb(b.n), fdb(b.divM), thr(t) {
 #pragma unroll
@@ -564,7 +587,7 @@ __device__ __noinline__ void pz_mul(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, co
     int W = 1;
     u64 magicW = 0;
     if (N > 0) fill_product_keys<NT>(S, A.keys, na, A.divM, B.keys, nb, B.divM, W, magicW);
-    MulOp<DA, DB, DO> op(A, B, S.thr);
+    MulOp<DA, DB, DO> op(A, B, S.thr_sq);
     __syncthreads();
     phase_mark(PH_FILL);
     const int buf = merge_sort_runs<NT>(S, N, W, magicW);
@@ -620,7 +643,7 @@ struct MergeOp {
     View<DB> B;
     int na;
     bool negb;
-    double thr;
+    double thr;   // squared-domain threshold (Scratch::thr_sq)
     __device__ __forceinline__ void term(unsigned idx, double* o) const {
         if ((int)idx < na) { double a[DA]; ldc<DA>(*A.p, idx, a); view_vec<DA, DO>(A, a, o); }
         else {
@@ -684,7 +707,7 @@ __device__ __noinline__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA> A,
             for (int i = threadIdx.x; i < na; i += NT) { key[nb + i] = ka[i]; idx[nb + i] = (u16)i; }
         }
     }
-    MergeOp<DA, DB, DO> op{A, B, na, negb, S.thr};
+    MergeOp<DA, DB, DO> op{A, B, na, negb, S.thr_sq};
     __syncthreads();
     phase_mark(PH_FILL);
     const int buf = merge_sort_runs<NT>(S, N, W, magicW);
@@ -707,7 +730,7 @@ struct CrossPPOp {
     const PZ<3>& B;
     int na, nb;
     FastDiv fdb;
-    double thr;
+    double thr;   // squared-domain threshold (Scratch::thr_sq)
     double ca[3], cb[3];
     __device__ CrossPPOp(const PZ<3>& a, const PZ<3>& b, double t) : A(a), B(b), na(a.n), nb(b.n), fdb(b.divM), thr(t) {
         for (int c = 0; c < 3; c++) { ca[c] = a.center[c]; cb[c] = b.center[c]; }
@@ -787,7 +810,7 @@ __device__ __noinline__ void pz_cross_pp(Scratch& S, PZ<3>& dst, const PZ<3>& A,
     int W = 1;
     u64 magicW = 0;
     if (N > 0) fill_product_keys<NT>(S, A.keys, na, A.divM, B.keys, nb, B.divM, W, magicW);
-    CrossPPOp op(A, B, S.thr);
+    CrossPPOp op(A, B, S.thr_sq);
     __syncthreads();
     phase_mark(PH_FILL);
     const int buf = merge_sort_runs<NT>(S, N, W, magicW);
@@ -814,7 +837,7 @@ struct CrossConstOp {
     const PZ<3>& Z;
     double k[3];
     bool const_first;   // true: cross(k, Z); false: cross(Z, k)
-    double thr;
+    double thr;   // squared-domain threshold (Scratch::thr_sq)
     __device__ __forceinline__ bool finish(int i, double* out, double* drop) const {
         double z[3], r[3];
         ldc<3>(Z, i, z);
@@ -850,7 +873,7 @@ struct CrossConstEpi {
 };
 template <int NT>
 __device__ __noinline__ void pz_cross_const(Scratch& S, PZ<3>& dst, const PZ<3>& Z, const double* kvec, bool const_first) {
-    CrossConstOp op{Z, {kvec[0], kvec[1], kvec[2]}, const_first, S.thr};
+    CrossConstOp op{Z, {kvec[0], kvec[1], kvec[2]}, const_first, S.thr_sq};
     elementwise_emit<NT, 3, CrossConstOp, CrossConstEpi>(S, Z.n, Z.keys, op, dst, CrossConstEpi{Z, {kvec[0], kvec[1], kvec[2]}, const_first});
 }
 
@@ -860,7 +883,7 @@ struct ConstLeftOp {
     const PZ<3>& V;
     double M[9];
     bool scalar;
-    double thr;
+    double thr;   // squared-domain threshold (Scratch::thr_sq)
     __device__ __forceinline__ bool finish(int i, double* out, double* drop) const {
         double z[3], r[3];
         ldc<3>(V, i, z);
@@ -893,7 +916,7 @@ struct ConstLeftEpi {
 };
 template <int NT>
 __device__ __noinline__ void pz_const_left(Scratch& S, PZ<3>& dst, const double* Mc, const double* Mi0, const double* Mi1, bool scalar, const PZ<3>& V) {
-    ConstLeftOp op{V, {0}, scalar, S.thr};
+    ConstLeftOp op{V, {0}, scalar, S.thr_sq};
     const int DM = scalar ? 1 : 9;
     for (int c = 0; c < DM; c++) op.M[c] = Mc[c];
     elementwise_emit<NT, 3, ConstLeftOp, ConstLeftEpi>(S, V.n, V.keys, op, dst, ConstLeftEpi{V, Mc, Mi0, Mi1, scalar});
@@ -903,7 +926,7 @@ __device__ __noinline__ void pz_const_left(Scratch& S, PZ<3>& dst, const double*
 struct ConstRightOp {
     const PZ<9>& R;
     double p[3];
-    double thr;
+    double thr;   // squared-domain threshold (Scratch::thr_sq)
     __device__ __forceinline__ bool finish(int i, double* out, double* drop) const {
         double m[9], r[3];
         ldc<9>(R, i, m);
@@ -925,7 +948,7 @@ struct ConstRightEpi {
 };
 template <int NT>
 __device__ __noinline__ void pz_const_right(Scratch& S, PZ<3>& dst, const PZ<9>& R, const double* pvec) {
-    ConstRightOp op{R, {pvec[0], pvec[1], pvec[2]}, S.thr};
+    ConstRightOp op{R, {pvec[0], pvec[1], pvec[2]}, S.thr_sq};
     elementwise_emit<NT, 3, ConstRightOp, ConstRightEpi>(S, R.n, R.keys, op, dst, ConstRightEpi{R, {pvec[0], pvec[1], pvec[2]}});
 }
 

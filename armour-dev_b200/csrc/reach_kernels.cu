@@ -97,11 +97,11 @@ __device__ __forceinline__ void bound_k_indep(double lbv, double ubv, double s_l
 }
 
 // scalar PZ from (centre, {k_i: c0, key1: c1}) with simplify()  (KPR/PZsparse.cu:120-136)
-__device__ void small_scalar(PZ<1>& z, double center, u64 k0, double c0, u64 k1, double c1, double thr) {
+__device__ void small_scalar(PZ<1>& z, double center, u64 k0, double c0, u64 k1, double c1, double thr_sq) {
     int n = 0;
     double ind = 0.0, abss = 0.0;
-    if (norm1(&c0) > thr) { z.keys[n] = k0; z.coef[n] = c0; abss = __dadd_ru(abss, fabs(c0)); n++; } else ind = __dadd_ru(ind, fabs(c0));
-    if (norm1(&c1) > thr) { z.keys[n] = k1; z.coef[n] = c1; abss = __dadd_ru(abss, fabs(c1)); n++; } else ind = __dadd_ru(ind, fabs(c1));
+    if (norm1(&c0) > thr_sq) { z.keys[n] = k0; z.coef[n] = c0; abss = __dadd_ru(abss, fabs(c0)); n++; } else ind = __dadd_ru(ind, fabs(c0));
+    if (norm1(&c1) > thr_sq) { z.keys[n] = k1; z.coef[n] = c1; abss = __dadd_ru(abss, fabs(c1)); n++; } else ind = __dadd_ru(ind, fabs(c1));
     ind = __dmul_ru(ind, 1.0 + 0x1p-40);   // a dropped coefficient built from device libm values may be an ulp below the host's
     z.n = n; z.divM = FastDiv::magic(n); z.center[0] = center; z.ind[0][0] = ind; z.ind[1][0] = ind; z.abss[0] = abss;
 }
@@ -114,7 +114,7 @@ __device__ void export_small(SmallRec& r, const PZ<D>& z) {
 
 // joint i, interval s: everything makePolyZono produces for that joint (KPR/Trajectory.cu:63-254)
 __device__ void make_poly_zono_joint(const Tables& tb, int prob, int s, int i, PZ<9>& R, PZ<9>& Rt, PZ<1>& qd, PZ<1>& qda, PZ<1>& qdda,
-                                     PZ<1>& cosq, PZ<1>& sinq, double thr) {
+                                     PZ<1>& cosq, PZ<1>& sinq, double thr) {   // thr: squared-domain threshold (Scratch::thr_sq)
     const RobotModel& rm = c_robot;
     const double* st = tb.state + (size_t)prob * 21;
     const double q0 = st[i], a = st[7 + i] * 1.0, b = st[14 + i] * 1.0 * 1.0;   // Tqd0, TTqdd0 with DURATION = 1
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(NT, MINB) reach_build_kernel(Tables tb, char* 
     const RobotModel& rm = c_robot;
     if (threadIdx.x == 0) {
         S.bind(smem_raw, ncap);
-        S.thr = tb.thr; S.gerr = tb.err;
+        S.thr = tb.thr; S.thr_sq = squared_threshold(tb.thr); S.gerr = tb.err;
         char* g = arena + (size_t)blockIdx.x * arena_stride;
         PZ<3>* big3[] = {&Z.W, &Z.WD, &Z.WA, &Z.LA, &Z.T1, &Z.T2, &Z.T3, &Z.T4, &Z.T5, &Z.Fv, &Z.Nv, &Z.FKT};
         for (PZ<3>* z : big3) g = carve<3>(*z, g, mcap);
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(NT, MINB) reach_build_kernel(Tables tb, char* 
         // ---- stage A: joint reach sets (one thread per joint; tiny scalar work) -------------------
         if (threadIdx.x < NJ) {
             const int i = threadIdx.x;
-            make_poly_zono_joint(tb, prob, s, i, Z.R[i], Z.Rt[i], Z.qd[i], Z.qda[i], Z.qdda[i], Z.cosq[i], Z.sinq[i], S.thr);
+            make_poly_zono_joint(tb, prob, s, i, Z.R[i], Z.Rt[i], Z.qd[i], Z.qda[i], Z.qdda[i], Z.cosq[i], Z.sinq[i], S.thr_sq);
             if (tb.traj) {
                 SmallRec* rec = tb.traj + (((size_t)prob * tb.T + s) * TRAJ_TABLES) * NJ;
                 export_small<1>(rec[TRAJ_COS * NJ + i], Z.cosq[i]); export_small<1>(rec[TRAJ_SIN * NJ + i], Z.sinq[i]);
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(NT, MINB) reach_build_kernel(Tables tb, char* 
             const u64 gk[3] = {key_qde(0), key_qdae(0), key_qddae(0)};
             for (int j = 0; j < 3; j++) {
                 const double g = rm.link_g[i][j];
-                if (norm1(&g) > S.thr) {   // both the scalar ctor's simplify and stack()'s see |g|
+                if (norm1(&g) > S.thr_sq) {   // both the scalar ctor's simplify and stack()'s see |g|
                     L0.keys[n] = gk[j];
                     for (int c = 0; c < 3; c++) L0.coef[c * L0.cap + n] = (c == j) ? g : 0.0;
                     abss[j] = fabs(g);
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(NT) pz_binary_kernel(int op, FlatPZ a, FlatPZ 
     __shared__ PZ<9> a9, b9, r9;
     if (threadIdx.x == 0) {
         S.bind(smem_raw, ncap);
-        S.thr = thr; S.gerr = err; S.tmp = tmp;
+        S.thr = thr; S.thr_sq = squared_threshold(thr); S.gerr = err; S.tmp = tmp;
         r1.cap = r3.cap = r9.cap = r.cap; r1.keys = r3.keys = r9.keys = r.keys; r1.coef = r3.coef = r9.coef = r.coef;
     }
     __syncthreads();
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(NT) pz_binary_kernel(int op, FlatPZ a, FlatPZ 
 // ---- host-side launch helpers -----------------------------------------------------------------
 cudaError_t upload_robot_model(const RobotModel& rm) { return cudaMemcpyToSymbol(c_robot, &rm, sizeof(RobotModel)); }
 
-size_t reach_smem_bytes(int ncap) { return (size_t)ncap * 20; }
+size_t reach_smem_bytes(int ncap) { return (size_t)ncap * 20 + (size_t)3 * 1024 * 8; }   // sort ping-pong + per-key staging (Scratch::TCAP)
 
 // kernel variants: (threads per CTA, CTAs per SM the register allocation is bounded for)
 typedef void (*ReachKernel)(Tables, char*, size_t, int, int, int);
