@@ -26,7 +26,7 @@ EXPORTS = [
     "armour_eval_grad_f", "armour_eval_g", "armour_eval_jac_g", "armour_eval_g_jac", "armour_jac_structure", "armour_check_feasible",
     "armour_get_torque_radius", "armour_get_link_generators", "armour_get_link_sliced_center", "armour_get_hyperplanes",
     "armour_get_taylor_remainders", "armour_get_pz", "armour_pz_binary", "armour_last_build_ms", "armour_last_eval_ms",
-    "armour_kernel_launches", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_upload_x", "armour_debug_phase_cycles", "armour_measure_fp64_peak",
+    "armour_kernel_launches", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_upload_x", "armour_standin_solve", "armour_debug_phase_cycles", "armour_measure_fp64_peak",
 ]
 
 
@@ -270,6 +270,13 @@ class Planner:
         f = C.c_int()
         self._ck(self.L.armour_check_feasible(self.h, _dp(_vec(g, self.m)), C.byref(f)))
         return bool(f.value)
+
+    def standin_solve(self, q_des, t_plan=0.5):
+        """Stand-in for the Ipopt solve (Ipopt is not installed): returns k, feasible, iterations, evaluations."""
+        k = np.zeros(7)
+        f, it, ev = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.armour_standin_solve(self.h, _dp(_vec(q_des, 7)), C.c_double(t_plan), _dp(k), C.byref(f), C.byref(it), C.byref(ev)))
+        return k, bool(f.value), it.value, ev.value
 
     # ---- tables ----
     def get_pz(self, which, idx, s):

@@ -4,6 +4,7 @@
 // reach_kernels.cu / constraint_kernels.cu.  There is no CPU fallback anywhere in this file.
 #include "../../include/armour_b200.h"
 #include "armour_launch.h"
+#include "../host/standin_solver.hpp"
 
 #include <cmath>
 #include <cstdio>
@@ -612,6 +613,19 @@ int armour_pz_binary(armour_handle* h, int op,
     memcpy(center, rcen, 8 * d);
     memcpy(independent, rcen + 9, 8 * d);
     return o.n;
+}
+
+int armour_standin_solve(armour_handle* h, const double* q_des, double t_plan, double* k_opt, int* feasible, int* iterations, int* evaluations) {
+    if (!h || !q_des || !k_opt) return fail(ARMOUR_E_INVALID, "null argument");
+    if (!h->built) return fail(ARMOUR_E_STATE, "solve before build");
+    armtd_NLP nlp;
+    nlp.set_time_steps(h->T);
+    if (!nlp.set_parameters(q_des, t_plan, h)) return fail(ARMOUR_E_STATE, "set_parameters failed");
+    StandinResult r = standin_solve(nlp, k_opt);
+    if (feasible) *feasible = nlp.feasible ? 1 : 0;
+    if (iterations) *iterations = r.iterations;
+    if (evaluations) *evaluations = r.evaluations;
+    return ARMOUR_OK;
 }
 
 int armour_last_build_ms(armour_handle* h, float* total_ms, float* reach_kernel_ms, float* hyperplane_kernel_ms) {

@@ -60,6 +60,7 @@ int main(int argc, char** argv) {
 
     auto start2 = std::chrono::high_resolution_clock::now();
     armtd_NLP nlp;
+    nlp.verbose = true;
     nlp.set_time_steps(NUM_TIME_STEPS);
     if (!nlp.set_parameters(q_des, t_plan, h)) { printf("        CUDA & C++: Error initializing the NLP!\n"); out1 << -1 << '\n'; out1.close(); armour_destroy(h); return 1; }
     double k_opt[7] = {0};

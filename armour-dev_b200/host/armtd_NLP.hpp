@@ -106,7 +106,7 @@ public:
     virtual void finalize_solution(Ipopt::SolverReturn, Index n, const Number* x, const Number*, const Number*, Index m, const Number* g,
                                    const Number*, Number obj_value, const Ipopt::IpoptData*, Ipopt::IpoptCalculatedQuantities*) {
         for (Index i = 0; i < n; i++) solution[i] = (double)x[i];
-        printf("        CUDA & C++: Ipopt: final cost function value: %g\n", obj_value / 10.0);
+        if (verbose) printf("        CUDA & C++: Ipopt: final cost function value: %g\n", obj_value / 10.0);
         memcpy(g_copy.data(), g, (size_t)m * sizeof(Number));
         int f = 0;
         feasible = (armour_check_feasible(handle, g_copy.data(), &f) == ARMOUR_OK) && f != 0;
@@ -123,6 +123,7 @@ public:
     void set_time_steps(int T) { time_steps = T; }
 
     double t_plan = 1.0;
+    bool verbose = false;   // the reference prints the final cost from finalize_solution (KPR/NLPclass.cu:443)
     double solution[ARMOUR_NUM_FACTORS] = {0};
     Index constraint_number = 0;
     std::vector<Number> g_copy;

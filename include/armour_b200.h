@@ -125,6 +125,11 @@ int armour_pz_binary(armour_handle* h, int op,
                      int b_rows, int b_cols, int b_n, const uint64_t* b_keys, const double* b_coeffs, const double* b_center, const double* b_independent,
                      int cap, int* dims, uint64_t* keys, double* coeffs, double* center, double* independent);
 
+/* Stand-in NLP solve for hosts without Ipopt (this image): quadratic-penalty Gauss-Newton over the same callbacks
+ * Ipopt would call (armour-dev_b200/host/standin_solver.hpp).  NOT the reference's solver — results are labelled
+ * "stand-in" wherever reported.  k_opt[7]; *feasible as armour_check_feasible at the returned point. */
+int armour_standin_solve(armour_handle* h, const double* q_des, double t_plan, double* k_opt, int* feasible, int* iterations, int* evaluations);
+
 /* ---- timing / accounting ------------------------------------------------------------------------------ */
 /* device time of the last build / eval in milliseconds (CUDA events on the handle's stream) */
 int armour_last_build_ms(armour_handle* h, float* total_ms, float* reach_kernel_ms, float* hyperplane_kernel_ms);
