@@ -23,7 +23,7 @@ PZ_OPS = {"mul": 0, "add": 1, "sub": 2, "cross": 3}
 EXPORTS = [
     "armour_default_config", "armour_create", "armour_destroy", "armour_last_error", "armour_build", "armour_build_batch",
     "armour_select_problem", "armour_get_nlp_info", "armour_get_bounds_info", "armour_get_starting_point", "armour_eval_f",
-    "armour_eval_grad_f", "armour_eval_g", "armour_eval_jac_g", "armour_eval_g_jac", "armour_jac_structure", "armour_check_feasible",
+    "armour_eval_grad_f", "armour_eval_g", "armour_eval_jac_g", "armour_eval_g_jac", "armour_jac_structure", "armour_release_host_buffers", "armour_check_feasible",
     "armour_get_torque_radius", "armour_get_link_generators", "armour_get_link_sliced_center", "armour_get_hyperplanes",
     "armour_get_taylor_remainders", "armour_get_pz", "armour_pz_binary", "armour_last_build_ms", "armour_last_eval_ms",
     "armour_kernel_launches", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_upload_x", "armour_standin_solve", "armour_debug_phase_cycles", "armour_measure_fp64_peak",
@@ -43,6 +43,7 @@ class ArmourConfig(C.Structure):
         ("threads_per_cta", C.c_int),
         ("device", C.c_int),
         ("batch", C.c_int),
+        ("pin_user_buffers", C.c_int),
     ]
 
 
@@ -115,7 +116,7 @@ class Planner:
     planning problem (or a batch of independent ones)."""
 
     def __init__(self, T=128, k_range=None, mass_uncertainty=0.03, inertia_uncertainty=0.03, threshold=5e-4, max_obstacles=40,
-                 max_monomials=0, max_entries=0, threads_per_cta=0, device=-1, batch=1):
+                 max_monomials=0, max_entries=0, threads_per_cta=0, device=-1, batch=1, pin_user_buffers=False):
         self.L = lib()
         cfg = default_config()
         cfg.num_time_steps = T
@@ -131,6 +132,7 @@ class Planner:
         cfg.threads_per_cta = threads_per_cta
         cfg.device = device
         cfg.batch = batch
+        cfg.pin_user_buffers = 1 if pin_user_buffers else 0
         self.T = T
         self.batch = batch
         self.k_range = np.array([cfg.k_range[i] for i in range(7)])

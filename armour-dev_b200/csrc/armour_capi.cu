@@ -133,6 +133,9 @@ struct armour_handle {
     std::vector<int> m_un, m_ln;
     std::vector<unsigned long long> m_ukeys, m_lkeys;
     std::vector<double> m_ucoef, m_ucenter, m_uind, m_dist, m_lcoef, m_lcenter, m_lind;
+    // caller arrays page-locked under cfg.pin_user_buffers: host pointer, bytes, device alias
+    struct Pinned { const void* host; size_t bytes; void* dev; };
+    std::vector<Pinned> pinned;
     // pz_binary scratch
     char* bin_buf = nullptr;
     size_t bin_bytes = 0;
@@ -187,27 +190,33 @@ int run_build(armour_handle* h) {   // kernels only; inputs already on the devic
     return fail(ARMOUR_E_CAPACITY, "monomial capacities exceeded after retries");
 }
 
-int run_eval(armour_handle* h, const double* x, bool copy_back) {
+// One launch per call.  to_host: the kernel writes g and the Jacobian straight into the handle's pinned host
+// buffers (zero-copy over PCIe, overlapped with the computation); otherwise into device buffers (device-resident timing).
+int run_eval(armour_handle* h, const double* x, bool to_host) {
     if (!h->built) return fail(ARMOUR_E_STATE, "eval before build");
-    const int m = m_of(h);
-    if (x) {
-        memcpy(h->h_x, x, sizeof(double) * NF);
-        CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * NF, cudaMemcpyHostToDevice, h->stream));
-    }
+    if (x) memcpy(h->h_x, x, sizeof(double) * NF);
     Tables tb = h->tb;
     tb.P = h->count; tb.n_obs = h->n_obs;
     CU(cudaEventRecord(h->ev[3], h->stream));
-    CU(launch_constraint_eval(tb, h->sel, h->d_x, h->d_g, h->d_jac, h->d_link_center, h->stream));
+    CU(launch_constraint_eval(tb, h->sel, h->h_x, to_host ? h->h_g : h->d_g, to_host ? h->h_jac : h->d_jac, h->d_link_center, h->stream));
     CU(cudaEventRecord(h->ev[4], h->stream));
     h->launches += 1;
-    if (copy_back) {
-        CU(cudaMemcpyAsync(h->h_g, h->d_g, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaMemcpyAsync(h->h_jac, h->d_jac, sizeof(double) * (size_t)m * NF, cudaMemcpyDeviceToHost, h->stream));
-    }
     CU(cudaStreamSynchronize(h->stream));
     cudaEventElapsedTime(&h->eval_ms, h->ev[3], h->ev[4]);
-    if (x && copy_back) { memcpy(h->last_x, x, sizeof(double) * NF); h->have_eval = true; }
+    if (x && to_host) { memcpy(h->last_x, x, sizeof(double) * NF); h->have_eval = true; }
     return ARMOUR_OK;
+}
+
+void* pinned_alias(armour_handle* h, void* host, size_t bytes) {   // device alias of a caller array, registering it on first sight
+    for (auto& p : h->pinned) if (p.host == host && p.bytes >= bytes) return p.dev;
+    for (size_t i = 0; i < h->pinned.size(); i++)
+        if (h->pinned[i].host == host) { cudaHostUnregister(host); h->pinned.erase(h->pinned.begin() + i); break; }
+    if (h->pinned.size() >= 8) { cudaHostUnregister((void*)h->pinned[0].host); h->pinned.erase(h->pinned.begin()); }
+    if (cudaHostRegister(host, bytes, cudaHostRegisterMapped) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    void* dev = nullptr;
+    if (cudaHostGetDevicePointer(&dev, host, 0) != cudaSuccess) { cudaGetLastError(); cudaHostUnregister(host); return nullptr; }
+    h->pinned.push_back({host, bytes, dev});
+    return dev;
 }
 
 int ensure_mirror(armour_handle* h) {
@@ -316,6 +325,8 @@ void armour_destroy(armour_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto& p : h->pinned) cudaHostUnregister((void*)p.host);
+    cudaGetLastError();
     Tables& tb = h->tb;
     void* dev[] = {h->d_state, h->d_obs, tb.traj, tb.cos_rem, tb.sin_rem, tb.u_n, tb.u_keys, tb.u_coef, tb.u_center, tb.u_ind, tb.dist_rad, tb.torque_radius,
                    tb.l_n, tb.l_keys, tb.l_coef, tb.l_center, tb.l_ind, tb.gens, tb.A, tb.d, tb.delta, h->d_err, h->d_x, h->d_g, h->d_jac, h->d_link_center, h->arena, h->bin_buf};
@@ -411,9 +422,35 @@ int armour_eval_grad_f(armour_handle* h, const double* q_des, double t_plan, con
     }
     return ARMOUR_OK;
 }
+int armour_release_host_buffers(armour_handle* h) {
+    if (!h) return fail(ARMOUR_E_INVALID, "null argument");
+    cudaSetDevice(h->device);
+    for (auto& p : h->pinned) cudaHostUnregister((void*)p.host);
+    h->pinned.clear();
+    cudaGetLastError();
+    return ARMOUR_OK;
+}
 int armour_eval_g_jac(armour_handle* h, const double* x, double* g, double* values) {
     if (!h || !x) return fail(ARMOUR_E_INVALID, "null argument");
     CU(cudaSetDevice(h->device));
+    if (h->cfg.pin_user_buffers && g && values && h->built) {   // zero staging: the kernel writes the caller's arrays
+        const int m = m_of(h);
+        double* dg = (double*)pinned_alias(h, g, sizeof(double) * m);
+        double* dj = dg ? (double*)pinned_alias(h, values, sizeof(double) * (size_t)m * NF) : nullptr;
+        if (dg && dj) {
+            memcpy(h->h_x, x, sizeof(double) * NF);
+            Tables tb = h->tb;
+            tb.P = h->count; tb.n_obs = h->n_obs;
+            CU(cudaEventRecord(h->ev[3], h->stream));
+            CU(launch_constraint_eval(tb, h->sel, h->h_x, dg, dj, h->d_link_center, h->stream));
+            CU(cudaEventRecord(h->ev[4], h->stream));
+            h->launches += 1;
+            CU(cudaStreamSynchronize(h->stream));
+            cudaEventElapsedTime(&h->eval_ms, h->ev[3], h->ev[4]);
+            h->have_eval = false;
+            return ARMOUR_OK;
+        }
+    }
     if (!(h->have_eval && memcmp(h->last_x, x, sizeof(double) * NF) == 0)) {
         int rc = run_eval(h, x, true);
         if (rc != ARMOUR_OK) return rc;
@@ -433,9 +470,7 @@ int armour_eval_resident(armour_handle* h, const double* x) {
 int armour_upload_x(armour_handle* h, const double* x) {
     if (!h || !x) return fail(ARMOUR_E_INVALID, "null argument");
     CU(cudaSetDevice(h->device));
-    memcpy(h->h_x, x, sizeof(double) * NF);
-    CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * NF, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    memcpy(h->h_x, x, sizeof(double) * NF);   // k travels as a kernel argument
     h->have_eval = false;
     return ARMOUR_OK;
 }

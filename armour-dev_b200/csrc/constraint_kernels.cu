@@ -156,17 +156,23 @@ __device__ __forceinline__ double slice_term(double coef, u64 key, const double*
 }
 
 constexpr int EVAL_NT = 256;
+constexpr int EVAL_MAX_OBS = 64;
+struct XArg { double x[NF]; };   // k passed by value: no host-to-device copy on the per-iteration path
 // grid: P_sel * (T * NJ + 1) blocks for the selected problem: block (t, j) handles torque row (t, j), link j
 // at interval t against every obstacle; the extra block handles the 28 limit rows.
-__global__ void __launch_bounds__(EVAL_NT) constraint_eval_kernel(Tables tb, int prob, const double* __restrict__ xdev, double* __restrict__ g, double* __restrict__ jac,
+// g / jac may point to device memory or to pinned host memory (UVA): results of one block are staged in shared
+// memory and written out in contiguous runs, so that over PCIe they leave as full-width posted writes while the
+// rest of the grid is still computing (no separate device-to-host copy after the kernel).
+__global__ void __launch_bounds__(EVAL_NT) constraint_eval_kernel(Tables tb, int prob, XArg xarg, double* __restrict__ g, double* __restrict__ jac,
                                                                   double* __restrict__ link_center_out) {
     __shared__ double x[NF];
+    __shared__ double sg[EVAL_MAX_OBS], sjac[EVAL_MAX_OBS * NF];
     __shared__ double terms[24][LCAP];      // link: 3 values + 21 gradients per monomial; torque rows reuse [0..7][UCAP/...]
     __shared__ double uterms[8][UCAP];
     __shared__ double lc[3], ldk[NF][3];
     const int T = tb.T, n_obs = tb.n_obs;
     const int tid = threadIdx.x;
-    if (tid < NF) x[tid] = xdev[tid];
+    if (tid < NF) x[tid] = xarg.x[tid];
     __syncthreads();
     const int blk = blockIdx.x;
     const size_t off_obs = (size_t)NF * T, off_lim = off_obs + (size_t)NJ * T * n_obs;
@@ -250,16 +256,20 @@ __global__ void __launch_bounds__(EVAL_NT) constraint_eval_kernel(Tables tb, int
             if (ob > best || (ob == best && oe < best_e)) { best = ob; best_e = oe; }
         }
         if (best_e == 0x7fffffff) best_e = 0;
-        const size_t row = off_obs + ((size_t)j * T + t) * n_obs + o;
-        if (lane == 0) g[row] = -best;
+        if (lane == 0) sg[o] = -best;
         if (lane < NF) {
             const int p = best_e >> 1;
             const bool neg = best_e & 1;
             const double a0 = tb.A[(base + p) * 3], a1 = tb.A[(base + p) * 3 + 1], a2 = tb.A[(base + p) * 3 + 2];
             const double dot = dadd(dadd(dmul(a0, ldk[lane][0]), dmul(a1, ldk[lane][1])), dmul(a2, ldk[lane][2]));
-            jac[row * NF + lane] = neg ? dot : -dot;
+            sjac[o * NF + lane] = neg ? dot : -dot;
         }
     }
+    __syncthreads();
+    // rows (j*T + t)*n_obs + [0, n_obs) are contiguous in g and in jac: coalesced write-out
+    const size_t row0 = off_obs + ((size_t)j * T + t) * n_obs;
+    for (int e = tid; e < n_obs; e += EVAL_NT) g[row0 + e] = sg[e];
+    for (int e = tid; e < n_obs * NF; e += EVAL_NT) jac[row0 * NF + e] = sjac[e];
 }
 
 cudaError_t launch_hyperplanes(const Tables& tb, cudaStream_t stream) {
@@ -270,8 +280,11 @@ cudaError_t launch_hyperplanes(const Tables& tb, cudaStream_t stream) {
     hyperplane_kernel<<<grid, nt, 0, stream>>>(tb);
     return cudaGetLastError();
 }
-cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* xdev, double* g, double* jac, double* link_center, cudaStream_t stream) {
-    constraint_eval_kernel<<<tb.T * NJ + 1, EVAL_NT, 0, stream>>>(tb, prob, xdev, g, jac, link_center);
+cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* x_host, double* g, double* jac, double* link_center, cudaStream_t stream) {
+    if (tb.n_obs > EVAL_MAX_OBS) return cudaErrorInvalidValue;
+    XArg xa;
+    for (int i = 0; i < NF; i++) xa.x[i] = x_host[i];
+    constraint_eval_kernel<<<tb.T * NJ + 1, EVAL_NT, 0, stream>>>(tb, prob, xa, g, jac, link_center);
     return cudaGetLastError();
 }
 

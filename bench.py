@@ -175,7 +175,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     K, W = args.steps, args.warmup
-    p = ab.Planner(T=T, max_obstacles=N_OBS, device=local_rank, threads_per_cta=args.threads)
+    p = ab.Planner(T=T, max_obstacles=N_OBS, device=local_rank, threads_per_cta=args.threads, pin_user_buffers=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def flush_l2():

@@ -58,6 +58,9 @@ typedef struct armour_config {
     int threads_per_cta;        /* 128, 256 or 512; default 256 (0 = default)            */
     int device;                 /* CUDA device ordinal; -1 = current device              */
     int batch;                  /* problems one handle builds per armour_build_batch call; default 1 */
+    int pin_user_buffers;       /* 1: armour_eval_g_jac page-locks the caller's g / values arrays (cudaHostRegister) and the
+                                 * kernel writes into them directly, no staging copy.  The arrays must stay allocated until
+                                 * armour_release_host_buffers / armour_destroy.  Default 0 (staging through pinned buffers). */
 } armour_config;
 
 void armour_default_config(armour_config* cfg);
@@ -94,6 +97,8 @@ int armour_eval_g(armour_handle* h, const double* x, double* g);
 int armour_eval_jac_g(armour_handle* h, const double* x, double* values);
 int armour_eval_g_jac(armour_handle* h, const double* x, double* g, double* values);
 int armour_jac_structure(armour_handle* h, int* iRow, int* jCol);
+/* undo the page-locking done under cfg.pin_user_buffers (call before freeing those arrays) */
+int armour_release_host_buffers(armour_handle* h);
 /* armtd_NLP::finalize_solution's feasibility re-check (:446-537): *feasible = 1 or 0 */
 int armour_check_feasible(armour_handle* h, const double* g, int* feasible);
 

@@ -248,3 +248,20 @@ def test_pz_self_subtraction_cancels(gpu_lib):
     r = p.pz_binary("sub", a, a)
     assert len(r["keys"]) == 0 and np.all(r["center"] == 0)
     assert np.all(r["independent"] >= 2 * a["independent"])
+
+
+def test_pinned_user_buffers_give_identical_results(gpu_lib):
+    """cfg.pin_user_buffers: the kernel writes the caller's arrays directly; same numbers as the staged path."""
+    q0, qd0, qdd0, _, obs = make_problem(41, 12)
+    a = ab.Planner(T=32)
+    b = ab.Planner(T=32, pin_user_buffers=True)
+    a.build(q0, qd0, qdd0, obs)
+    b.build(q0, qd0, qdd0, obs)
+    g, J = np.zeros(a.m), np.zeros(a.m * 7)
+    for x in (DEBUG_K, np.zeros(7), -DEBUG_K):
+        ga, Ja = a.eval_g_jac(x)
+        b.eval_g_jac(x, g, J)
+        assert np.array_equal(ga, g) and np.array_equal(Ja.ravel(), J)
+    assert b.L.armour_release_host_buffers(b.h) == 0
+    b.eval_g_jac(DEBUG_K, g, J)   # re-registers transparently
+    assert np.array_equal(a.eval_g(DEBUG_K), g)
