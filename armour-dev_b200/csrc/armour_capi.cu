@@ -111,7 +111,7 @@ struct armour_handle {
     RobotModel model;
     Tables tb;
     int P = 1, T = 128, max_obs = 40;
-    int mcap = 1024, ncap = 4096, nt = 256, minb = 1;
+    int mcap = 1024, ncap = 3072, nt = 256, minb = 1, groups = 2, groups_cfg = 2;
     char* arena = nullptr;
     size_t arena_stride = 0;
     int grid = 0;
@@ -149,7 +149,10 @@ void free_arena(armour_handle* h) { if (h->arena) cudaFree(h->arena); h->arena =
 int alloc_arena(armour_handle* h) {
     free_arena(h);
     h->arena_stride = arena_bytes(h->mcap, h->ncap);
-    int per_sm = reach_max_ctas_per_sm(h->nt, h->minb, h->ncap);
+    // two thread groups per CTA (joint chain || forces + FK) when their sort buffers fit in shared memory
+    h->groups = h->groups_cfg;
+    int per_sm = h->groups == 2 ? reach_max_ctas_per_sm(h->nt, h->minb, 2, h->ncap) : 0;
+    if (per_sm < 1) { h->groups = 1; per_sm = reach_max_ctas_per_sm(h->nt, h->minb, 1, h->ncap); }
     if (per_sm < 1) return fail(ARMOUR_E_CUDA, "reach_build_kernel does not fit on an SM with these capacities");
     const int n_work = h->P * h->T;
     h->grid = std::min(n_work, per_sm * h->sm_count);
@@ -164,7 +167,7 @@ int run_build(armour_handle* h) {   // kernels only; inputs already on the devic
     for (int attempt = 0; attempt < 4; attempt++) {
         CU(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
         CU(cudaEventRecord(h->ev[0], h->stream));
-        CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, n_work, std::min(h->grid, n_work), h->nt, h->minb, h->stream));
+        CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, n_work, std::min(h->grid, n_work), h->nt, h->minb, h->groups, h->stream));
         CU(cudaEventRecord(h->ev[1], h->stream));
         CU(launch_hyperplanes(tb, h->stream));
         CU(cudaEventRecord(h->ev[2], h->stream));
@@ -260,7 +263,7 @@ void armour_default_config(armour_config* cfg) {
     cfg->simplify_threshold = 5e-4;
     cfg->max_obstacles = 40;
     cfg->max_monomials = 1024;
-    cfg->max_entries = 4096;
+    cfg->max_entries = 3072;
     cfg->threads_per_cta = 256;
     cfg->device = -1;
     cfg->batch = 1;
@@ -272,7 +275,7 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     if (cfg.num_time_steps <= 0 || (cfg.num_time_steps & 1)) return fail(ARMOUR_E_INVALID, "num_time_steps must be a positive even number");
     if (cfg.max_obstacles < 0) return fail(ARMOUR_E_INVALID, "max_obstacles < 0");
     if (cfg.max_monomials <= 0) cfg.max_monomials = 1024;
-    if (cfg.max_entries <= 0) cfg.max_entries = 4096;
+    if (cfg.max_entries <= 0) cfg.max_entries = 3072;
     if (cfg.threads_per_cta != 128 && cfg.threads_per_cta != 512) cfg.threads_per_cta = 256;
     if (cfg.batch <= 0) cfg.batch = 1;
     int ndev = 0;
@@ -289,6 +292,9 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     // register budget: one plan is latency-bound (1 CTA/SM, all registers); a batch wants more resident CTAs
     h->minb = cfg.batch > 1 ? 2 : 1;
     if (const char* e = getenv("ARMOUR_TUNE_MINB")) h->minb = atoi(e);
+    // one plan (latency): two thread groups per CTA; a batch (throughput): one group and two resident CTAs per SM
+    h->groups_cfg = (cfg.batch > 1 || cfg.threads_per_cta == 128 || cfg.threads_per_cta == 512) ? 1 : 2;
+    if (const char* e = getenv("ARMOUR_TUNE_GROUPS")) h->groups_cfg = atoi(e) == 2 ? 2 : 1;
     kinova_model(h->model);
     *out = h;   // so that armour_destroy can clean up after a partial failure
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));

@@ -101,6 +101,13 @@ struct FastDiv {
 
 __device__ __forceinline__ void set_err(Scratch& S, int e) { atomicOr(S.gerr, e); }
 
+// A CTA may hold several independent groups of NT threads (reach_kernels.cu runs the RNEA joint chain and the
+// force/FK computations of one interval side by side).  Every cooperative routine below works within one group:
+// gtid<NT>() is the thread's index in its group, gsync<NT>() a named barrier (id 1 + group) over the group's NT
+// threads.  With a single group this is __syncthreads() under another name.
+template <int NT> __device__ __forceinline__ int gtid() { return (int)(threadIdx.x & (NT - 1)); }
+template <int NT> __device__ __forceinline__ void gsync() { asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x / NT)), "n"(NT) : "memory"); }
+
 // sqrt is monotone, so {x : RN(sqrt(x)) <= thr} is a down-set {x <= X}.  Find X once per kernel; the hot loops then
 // compare squared norms and never take a square root, with bit-identical keep/drop decisions.
 __device__ inline double squared_threshold(double thr) {
@@ -122,7 +129,7 @@ __device__ unsigned long long armour_phase_calls[PH_COUNT];
 struct PhaseClock { long long last; };
 __shared__ PhaseClock g_phase_clock;
 __device__ __forceinline__ void phase_mark(int ph) {
-    if (threadIdx.x == 0) {
+    if ((threadIdx.x & 255) == 0 && threadIdx.x < 256) {
         const long long t = clock64();
         atomicAdd(&armour_phase_cycles[ph], (unsigned long long)(t - g_phase_clock.last));
         atomicAdd(&armour_phase_calls[ph], 1ull);
@@ -216,7 +223,7 @@ template <int NT, int V>
 __device__ __forceinline__ int block_scan_sum(Scratch& S, int cnt, const double (&red)[V], int& total) {
     constexpr int VP = Pow2Ceil<V>::value;
     constexpr int NW = NT / 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = gtid<NT>() >> 5;
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
@@ -226,7 +233,7 @@ __device__ __forceinline__ int block_scan_sum(Scratch& S, int cnt, const double 
     warp_multi_sum_ru<VP>(v);
     if (lane == 31) S.iscan[warp] = incl;
     if ((lane & ((32 >> Log2<VP>::value) - 1)) == 0) S.red[warp * VP + (lane >> (5 - Log2<VP>::value))] = v[0];
-    __syncthreads();
+    gsync<NT>();
     int before = 0, all = 0;
 #pragma unroll
     for (int w = 0; w < NW; w++) { const int t = S.iscan[w]; all += t; if (w < warp) before += t; }
@@ -258,7 +265,7 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 mag
         u16* io = S.sidx(cur ^ 1);
         // rank of each element among its sibling run (binary search; key and index are fetched together so the
         // tie-break does not add a dependent shared-memory round trip)
-        for (int g = threadIdx.x; g < N; g += NT) {
+        for (int g = gtid<NT>(); g < N; g += NT) {
             const int r = fd.div(g) >> level;      // g / (W << level)
             const int base = r * w;
             const int sb = (r ^ 1) * w;
@@ -279,7 +286,7 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 mag
             ko[pos] = k;
             io[pos] = (u16)id;
         }
-        __syncthreads();
+        gsync<NT>();
         phase_mark(PH_SORT);
         cur ^= 1;
     }
@@ -305,7 +312,7 @@ struct ScalarEpilogue {
     int c;
     template <class Epi>
     __device__ __forceinline__ void begin(const Epi& epi) {
-        c = (int)threadIdx.x - (NT - 32);
+        c = gtid<NT>() - (NT - 32);
         cen = 0; r0 = 0; r1 = 0;
         if (c >= 0 && c < DOUT) epi(c, cen, r0, r1);
     }
@@ -335,7 +342,7 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
     ScalarEpilogue<NT, DOUT> se;
     se.begin(epi);
     // pass 1: one thread per segment head
-    for (int g = threadIdx.x; g < N; g += NT) {
+    for (int g = gtid<NT>(); g < N; g += NT) {
         const u64 k = key[g];
         u16 f = 0;
         if (g == 0 || key[g - 1] != k) {
@@ -356,17 +363,17 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
         }
         flag[g] = f;
     }
-    __syncthreads();
+    gsync<NT>();
     phase_mark(PH_SEGMENT);
     // compaction of the kept keys (blocked ranges keep the order)
     const int ipt = (N + NT - 1) / NT;
-    const int g0 = min(threadIdx.x * ipt, N), g1 = min(g0 + ipt, N);
+    const int g0 = min(gtid<NT>() * ipt, N), g1 = min(g0 + ipt, N);
     int cnt = 0;
     for (int g = g0; g < g1; g++) cnt += flag[g];
     int total;
     int off = block_scan_sum<NT, 2 * DOUT>(S, cnt, red, total);
     const int dcap = dst.cap;
-    if (total > dcap) { if (threadIdx.x == 0) set_err(S, ERR_MONO_CAP); total = 0; }
+    if (total > dcap) { if (gtid<NT>() == 0) set_err(S, ERR_MONO_CAP); total = 0; }
     else {
         u64* dk = dst.keys;
         double* dc = dst.coef;
@@ -380,7 +387,7 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
         }
     }
     se.finish(S, dst, N, total);
-    __syncthreads();
+    gsync<NT>();
     phase_mark(PH_COMPACT);
 }
 
@@ -393,12 +400,12 @@ __device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* s
     double red[2 * DOUT];
 #pragma unroll
     for (int c = 0; c < 2 * DOUT; c++) red[c] = 0.0;
-    if (n > S.ncap) { if (threadIdx.x == 0) set_err(S, ERR_ENTRY_CAP); n = 0; }
+    if (n > S.ncap) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); n = 0; }
     int ncap;
     double* tmp = S.staging(n, DOUT, ncap);
     ScalarEpilogue<NT, DOUT> se;
     se.begin(epi);
-    for (int i = threadIdx.x; i < n; i += NT) {
+    for (int i = gtid<NT>(); i < n; i += NT) {
         double out[DOUT], dr[DOUT];
 #pragma unroll
         for (int c = 0; c < DOUT; c++) dr[c] = 0.0;
@@ -412,16 +419,16 @@ __device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* s
         flag[i] = keep ? 1 : 0;
         kcopy[i] = src_keys[i];   // dst may alias src
     }
-    __syncthreads();
+    gsync<NT>();
     phase_mark(PH_ELEMENTWISE);
     const int ipt = (n + NT - 1) / NT;
-    const int g0 = min(threadIdx.x * ipt, n), g1 = min(g0 + ipt, n);
+    const int g0 = min(gtid<NT>() * ipt, n), g1 = min(g0 + ipt, n);
     int cnt = 0;
     for (int g = g0; g < g1; g++) cnt += flag[g];
     int total;
     int off = block_scan_sum<NT, 2 * DOUT>(S, cnt, red, total);
     const int dcap = dst.cap;
-    if (total > dcap) { if (threadIdx.x == 0) set_err(S, ERR_MONO_CAP); total = 0; }
+    if (total > dcap) { if (gtid<NT>() == 0) set_err(S, ERR_MONO_CAP); total = 0; }
     else {
         u64* dk = dst.keys;
         double* dc = dst.coef;
@@ -435,7 +442,7 @@ __device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* s
         }
     }
     se.finish(S, dst, n, total);
-    __syncthreads();
+    gsync<NT>();
     phase_mark(PH_COMPACT);
 }
 
@@ -510,34 +517,34 @@ __device__ __forceinline__ int fill_product_keys(Scratch& S, const u64* ka, int 
     if (na == 0 || nb == 0) {   // single sorted run
         W = N > 0 ? N : 1;
         magicW = na ? magic_a : magic_b;
-        for (int g = threadIdx.x; g < N; g += NT) { key[g] = na ? ka[g] : kb[g]; idx[g] = (u16)g; }
+        for (int g = gtid<NT>(); g < N; g += NT) { key[g] = na ? ka[g] : kb[g]; idx[g] = (u16)g; }
         return N;
     }
     if (nb >= na) {   // runs: i = 0..na-1 (width nb), then B's own list (nb), then A's own list (na <= nb, last)
         W = nb; magicW = magic_b;
         const FastDiv fd(magic_b);
-        for (int g = threadIdx.x; g < na * nb; g += NT) {
+        for (int g = gtid<NT>(); g < na * nb; g += NT) {
             const int i = fd.div(g), j = g - i * nb;
             key[g] = ka[i] + kb[j];   // degrees add; no carry by construction (KPR/PZsparse.cu:938-940)
             idx[g] = (u16)(na + nb + g);
         }
         const int o1 = na * nb;
-        for (int j = threadIdx.x; j < nb; j += NT) { key[o1 + j] = kb[j]; idx[o1 + j] = (u16)(na + j); }
+        for (int j = gtid<NT>(); j < nb; j += NT) { key[o1 + j] = kb[j]; idx[o1 + j] = (u16)(na + j); }
         const int o0 = o1 + nb;
-        for (int i = threadIdx.x; i < na; i += NT) { key[o0 + i] = ka[i]; idx[o0 + i] = (u16)i; }
+        for (int i = gtid<NT>(); i < na; i += NT) { key[o0 + i] = ka[i]; idx[o0 + i] = (u16)i; }
     }
     else {            // runs: j = 0..nb-1 (width na), then A's own list (na), then B's own list (nb < na, last)
         W = na; magicW = magic_a;
         const FastDiv fd(magic_a);
-        for (int g = threadIdx.x; g < na * nb; g += NT) {
+        for (int g = gtid<NT>(); g < na * nb; g += NT) {
             const int j = fd.div(g), i = g - j * na;
             key[g] = ka[i] + kb[j];
             idx[g] = (u16)(na + nb + i * nb + j);
         }
         const int o0 = na * nb;
-        for (int i = threadIdx.x; i < na; i += NT) { key[o0 + i] = ka[i]; idx[o0 + i] = (u16)i; }
+        for (int i = gtid<NT>(); i < na; i += NT) { key[o0 + i] = ka[i]; idx[o0 + i] = (u16)i; }
         const int o1 = o0 + na;
-        for (int j = threadIdx.x; j < nb; j += NT) { key[o1 + j] = kb[j]; idx[o1 + j] = (u16)(na + j); }
+        for (int j = gtid<NT>(); j < nb; j += NT) { key[o1 + j] = kb[j]; idx[o1 + j] = (u16)(na + j); }
     }
     return N;
 }
@@ -583,12 +590,12 @@ template <int NT, int DA, int DB, int DO>
 __device__ __noinline__ void pz_mul(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, const PZ<DB>& B) {
     const int na = A.n, nb = B.n;
     int N = na + nb + na * nb;
-    if (N > S.ncap || N > 65535) { if (threadIdx.x == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
+    if (N > S.ncap || N > 65535) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
     int W = 1;
     u64 magicW = 0;
     if (N > 0) fill_product_keys<NT>(S, A.keys, na, A.divM, B.keys, nb, B.divM, W, magicW);
     MulOp<DA, DB, DO> op(A, B, S.thr_sq);
-    __syncthreads();
+    gsync<NT>();
     phase_mark(PH_FILL);
     const int buf = merge_sort_runs<NT>(S, N, W, magicW);
     reduce_emit<NT, DO, MulOp<DA, DB, DO>, MulEpi<DA, DB, DO>>(S, buf, N, op, dst, MulEpi<DA, DB, DO>{A, B});
@@ -689,7 +696,7 @@ template <int NT, int DA, int DB, int DO>
 __device__ __noinline__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA> A, const View<DB> B, bool negb) {
     const int na = A.p->n, nb = B.p->n;
     int N = na + nb;
-    if (N > S.ncap) { if (threadIdx.x == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
+    if (N > S.ncap) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
     u64* key = S.skey(0);
     u16* idx = S.sidx(0);
     int W = 1;
@@ -698,17 +705,17 @@ __device__ __noinline__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA> A,
         const u64* ka = A.p->keys; const u64* kb = B.p->keys;
         if (na >= nb) {   // the longer run first: runs must have uniform width except the last
             W = na > 0 ? na : 1; magicW = A.p->divM;
-            for (int i = threadIdx.x; i < na; i += NT) { key[i] = ka[i]; idx[i] = (u16)i; }
-            for (int j = threadIdx.x; j < nb; j += NT) { key[na + j] = kb[j]; idx[na + j] = (u16)(na + j); }
+            for (int i = gtid<NT>(); i < na; i += NT) { key[i] = ka[i]; idx[i] = (u16)i; }
+            for (int j = gtid<NT>(); j < nb; j += NT) { key[na + j] = kb[j]; idx[na + j] = (u16)(na + j); }
         }
         else {
             W = nb; magicW = B.p->divM;
-            for (int j = threadIdx.x; j < nb; j += NT) { key[j] = kb[j]; idx[j] = (u16)(na + j); }
-            for (int i = threadIdx.x; i < na; i += NT) { key[nb + i] = ka[i]; idx[nb + i] = (u16)i; }
+            for (int j = gtid<NT>(); j < nb; j += NT) { key[j] = kb[j]; idx[j] = (u16)(na + j); }
+            for (int i = gtid<NT>(); i < na; i += NT) { key[nb + i] = ka[i]; idx[nb + i] = (u16)i; }
         }
     }
     MergeOp<DA, DB, DO> op{A, B, na, negb, S.thr_sq};
-    __syncthreads();
+    gsync<NT>();
     phase_mark(PH_FILL);
     const int buf = merge_sort_runs<NT>(S, N, W, magicW);
     reduce_emit<NT, DO, MergeOp<DA, DB, DO>, MergeEpi<DA, DB>>(S, buf, N, op, dst, MergeEpi<DA, DB>{A, B, negb});
@@ -806,12 +813,12 @@ template <int NT>
 __device__ __noinline__ void pz_cross_pp(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B) {
     const int na = A.n, nb = B.n;
     int N = na + nb + na * nb;
-    if (N > S.ncap || N > 65535) { if (threadIdx.x == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
+    if (N > S.ncap || N > 65535) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
     int W = 1;
     u64 magicW = 0;
     if (N > 0) fill_product_keys<NT>(S, A.keys, na, A.divM, B.keys, nb, B.divM, W, magicW);
     CrossPPOp op(A, B, S.thr_sq);
-    __syncthreads();
+    gsync<NT>();
     phase_mark(PH_FILL);
     const int buf = merge_sort_runs<NT>(S, N, W, magicW);
     reduce_emit<NT, 3, CrossPPOp, CrossPPEpi>(S, buf, N, op, dst, CrossPPEpi{A, B});
@@ -953,13 +960,13 @@ __device__ __noinline__ void pz_const_right(Scratch& S, PZ<3>& dst, const PZ<9>&
 }
 
 // reset to a monomial-free PZ with centre c (all threads call; thread 0 writes)
-template <int D>
+template <int NT, int D>
 __device__ void pz_set_const(PZ<D>& z, const double* c) {
-    if (threadIdx.x == 0) {
+    if (gtid<NT>() == 0) {
         z.n = 0; z.divM = FastDiv::magic(0);
         for (int i = 0; i < D; i++) { z.center[i] = c ? c[i] : 0.0; z.ind[0][i] = 0.0; z.ind[1][i] = 0.0; z.abss[i] = 0.0; }
     }
-    __syncthreads();
+    gsync<NT>();
 }
 
 }  // namespace armour

@@ -10,12 +10,16 @@
 //      radius (KPR/PZsparse.cu:93-98, 944-989) — so one pass carries two radii.
 //   M  disturbance radius, reduce(), torque radius                             KPR/armour_main.cu:135-205
 // The half-space tables (stage D) are built by hyperplane_kernel in constraint_kernels.cu.
+#include <cstdio>
 #include "armour_launch.h"
 #include "pz_engine.cuh"
 
 namespace armour {
 
 __constant__ RobotModel c_robot;
+
+// dynamic shared memory of one thread group: sort ping-pong (u64 + u16, twice) + per-key staging (Scratch::TCAP)
+__host__ __device__ inline size_t reach_smem_bytes_dev(int ncap) { return (size_t)ncap * 20 + (size_t)3 * 1024 * 8; }
 
 // ---------------------------------------------------------------------------------------------
 // Directed-rounding interval arithmetic (replaces boost::numeric::interval with
@@ -263,9 +267,9 @@ __device__ __noinline__ void export_link(Scratch& S, const Tables& tb, size_t re
     u16* flag = S.sidx(0);
     double red[3] = {0, 0, 0};
     double* gens = tb.gens + rec * 18;
-    for (int i = threadIdx.x; i < 18; i += NT) gens[i] = 0.0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += NT) {
+    for (int i = gtid<NT>(); i < 18; i += NT) gens[i] = 0.0;
+    gsync<NT>();
+    for (int i = gtid<NT>(); i < n; i += NT) {
         const u64 k = L.keys[i];
         u16 f = 0;
         if (k < KEY_K_ONLY) f = 1;
@@ -278,24 +282,24 @@ __device__ __noinline__ void export_link(Scratch& S, const Tables& tb, size_t re
         else for (int c = 0; c < 3; c++) red[c] = __dadd_ru(red[c], fabs(L.coef[c * L.cap + i]));
         flag[i] = f;
     }
-    __syncthreads();
+    gsync<NT>();
     // the link-generator columns must be packed in order of appearance (j++ in the reference): with the
     // three fixed keys all present (checked on the host model) appearance order equals column order.
     const int ipt = (n + NT - 1) / NT;
-    const int g0 = min(threadIdx.x * ipt, n), g1 = min(g0 + ipt, n);
+    const int g0 = min(gtid<NT>() * ipt, n), g1 = min(g0 + ipt, n);
     int cnt = 0;
     for (int g = g0; g < g1; g++) cnt += flag[g];
     int total;
     int off = block_scan_sum<NT, 3>(S, cnt, red, total);
-    if (total > LCAP) { if (threadIdx.x == 0) set_err(S, ERR_TABLE_CAP); total = 0; }
+    if (total > LCAP) { if (gtid<NT>() == 0) set_err(S, ERR_TABLE_CAP); total = 0; }
     else {
         u64* ok = tb.l_keys + rec * LCAP;
         double* oc = tb.l_coef + rec * 3 * LCAP;
         for (int g = g0; g < g1; g++)
             if (flag[g]) { ok[off] = L.keys[g]; for (int c = 0; c < 3; c++) oc[c * LCAP + off] = L.coef[c * L.cap + g]; off++; }
     }
-    if (threadIdx.x < 3) {
-        const int c = threadIdx.x;
+    if (gtid<NT>() < 3) {
+        const int c = gtid<NT>();
         // final radius: inflate by 2^-40 so that last-bit libm differences upstream cannot make it
         // smaller than the host restatement's (see DESIGN.md "soundness of radii")
         const double r = __dmul_ru(__dadd_ru(L.ind[0][c], inflate(block_total<NT, 3>(S, c), n)), 1.0 + 0x1p-40);
@@ -304,7 +308,7 @@ __device__ __noinline__ void export_link(Scratch& S, const Tables& tb, size_t re
         gens[(3 + c) * 3 + c] = r;
         if (c == 0) tb.l_n[rec] = total;
     }
-    __syncthreads();
+    gsync<NT>();
     phase_mark(PH_EXPORT);
 }
 
@@ -314,52 +318,57 @@ __device__ __noinline__ void export_torque(Scratch& S, const Tables& tb, size_t 
     const int n = U.n;
     u16* flag = S.sidx(0);
     double red[1] = {0};
-    for (int i = threadIdx.x; i < n; i += NT) {
+    for (int i = gtid<NT>(); i < n; i += NT) {
         const u64 k = U.keys[i];
         const u16 f = (k < KEY_K_ONLY) ? 1 : 0;
         if (!f) red[0] = __dadd_ru(red[0], fabs(U.coef[i]));
         flag[i] = f;
     }
-    __syncthreads();
+    gsync<NT>();
     const int ipt = (n + NT - 1) / NT;
-    const int g0 = min(threadIdx.x * ipt, n), g1 = min(g0 + ipt, n);
+    const int g0 = min(gtid<NT>() * ipt, n), g1 = min(g0 + ipt, n);
     int cnt = 0;
     for (int g = g0; g < g1; g++) cnt += flag[g];
     int total;
     int off = block_scan_sum<NT, 1>(S, cnt, red, total);
-    if (total > UCAP) { if (threadIdx.x == 0) set_err(S, ERR_TABLE_CAP); total = 0; }
+    if (total > UCAP) { if (gtid<NT>() == 0) set_err(S, ERR_TABLE_CAP); total = 0; }
     else {
         u64* ok = tb.u_keys + rec * UCAP;
         double* oc = tb.u_coef + rec * UCAP;
         for (int g = g0; g < g1; g++)
             if (flag[g]) { ok[off] = U.keys[g]; oc[off] = U.coef[g]; off++; }
     }
-    if (threadIdx.x == 0) {
+    if (gtid<NT>() == 0) {
         tb.u_n[rec] = total;
         tb.u_center[rec] = U.center[0];
         tb.dist_rad[rec] = __dmul_ru(__dadd_ru(U.ind[1][0], U.ind[0][0]), 1.0 + 0x1p-40);
         tb.u_ind[rec] = __dmul_ru(__dadd_ru(U.ind[0][0], inflate(block_total<NT, 1>(S, 0), n)), 1.0 + 0x1p-40);
     }
-    __syncthreads();
+    gsync<NT>();
     phase_mark(PH_EXPORT);
 }
 
 // ---------------------------------------------------------------------------------------------
+// Working set of one interval.  The RNEA joint state (w, wdot, w_aux, linear_acc) is double-buffered by joint
+// parity so that the force/moment computation of joint i can run beside the chain update of joint i + 1.
 struct Slots {
-    PZ<3> W, WD, WA, LA, T1, T2, T3, T4, T5, F[NJ], N[NJ], Fv, Nv, FKT, LINK[NJ], link0[NJ];
+    PZ<3> W[2], WD[2], WA[2], LA[2];
+    PZ<3> T[2][5];                       // temporaries, one set per thread group
+    PZ<3> F[NJ], N[NJ], Fv, Nv, FKT, LINK[NJ], link0[NJ];
     PZ<9> FKR, R[NJ + 1], Rt[NJ];
     PZ<1> qd[NJ], qda[NJ], qdda[NJ], u[NJ], cosq[NJ], sinq[NJ];
 };
+constexpr int N_BIG3 = 8 + 10 + 3 + 3 * NJ;
 
 size_t arena_bytes(int mcap, int ncap) {
     size_t b = 0;
-    b += (size_t)(9 + 2 * NJ + 2 + 1 + NJ) * mcap * (8 + 3 * 8);   // big 3-vectors
+    b += (size_t)N_BIG3 * mcap * (8 + 3 * 8);                    // big 3-vectors
     b += (size_t)NJ * SMALL_CAP * (8 + 3 * 8);                    // link0
     b += (size_t)mcap * (8 + 9 * 8);                              // FK_R
     b += (size_t)(2 * NJ + 1) * SMALL_CAP * (8 + 9 * 8);          // R, R_t
     b += (size_t)5 * NJ * SMALL_CAP * 16;                         // qd, qda, qdda, cos, sin
     b += (size_t)NJ * mcap * 16;                                  // u
-    b += (size_t)9 * ncap * 8;                                    // tmp
+    b += (size_t)2 * 9 * ncap * 8;                                // per-group staging for large operations
     return (b + 255) & ~(size_t)255;
 }
 
@@ -372,18 +381,139 @@ __device__ char* carve(PZ<D>& z, char* p, int cap) {
     return p;
 }
 
-template <int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) reach_build_kernel(Tables tb, char* arena, size_t arena_stride, int mcap, int ncap, int n_work) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ Scratch S;
-    __shared__ Slots Z;
+// ---- hand-off between the two thread groups of a CTA --------------------------------------------------------
+// Monotonic counters in shared memory.  The producing group signals after an operation (whose closing group
+// barrier has made every thread's writes visible to its thread 0); the consuming group's thread 0 polls, then the
+// group barrier releases the rest.  The poll is bounded: a lost signal becomes an error word, never a hang.
+enum { ERR_SYNC = 32 };
+template <int NT>
+__device__ __forceinline__ void group_signal(volatile int* flag, int value) {
+    if (gtid<NT>() == 0) { __threadfence_block(); *flag = value; }
+}
+template <int NT>
+__device__ __forceinline__ void group_wait(Scratch& S, volatile int* flag, int needed) {
+    if (gtid<NT>() == 0) {
+        const long long t0 = clock64();
+        while (*flag < needed) {
+            if (clock64() - t0 > (1ll << 32)) { set_err(S, ERR_SYNC); break; }
+        }
+        __threadfence_block();
+    }
+    gsync<NT>();
+}
+
+// ---- the per-interval program, in four pieces --------------------------------------------------------------
+// RNEA forward recursion, joint chain (KPR/Dynamics.cu:102-137): state `p` (after joint i-1) -> state `c`
+template <int NT>
+__device__ void chain_joint(Scratch& S, Slots& Z, PZ<3>* T, int i, int p, int c) {
     const RobotModel& rm = c_robot;
+    const double zero3[3] = {0, 0, 0};
+    const int axis = rm.axes[i];
+    const int row = (axis < 0 ? -axis : axis) - 1;
+    // linear_acc = R_t * (linear_acc + cross(wdot, trans) + cross(w, cross(w_aux, trans)))   (line 16)
+    pz_cross_const<NT>(S, T[0], Z.WD[p], rm.trans[i], false);
+    pz_cross_const<NT>(S, T[1], Z.WA[p], rm.trans[i], false);
+    pz_cross_pp<NT>(S, T[2], Z.W[p], T[1]);
+    pz_add3<NT>(S, T[3], Z.LA[p], T[0]);
+    pz_add3<NT>(S, T[3], T[3], T[2]);
+    pz_mul<NT, 9, 3, 3>(S, Z.LA[c], Z.Rt[i], T[3]);
+    // w = R_t * w (+ qd_des on the joint axis)                                               (line 13)
+    pz_mul<NT, 9, 3, 3>(S, Z.W[c], Z.Rt[i], Z.W[p]);
+    if (axis != 0) pz_add_one_dim<NT>(S, Z.W[c], Z.W[c], Z.qd[i], row);
+    // w_aux = R_t * w_aux                                                                     (line 14)
+    pz_mul<NT, 9, 3, 3>(S, Z.WA[c], Z.Rt[i], Z.WA[p]);
+    // wdot = R_t * wdot (+ cross(w_aux, qd_des * z) + qdda_des on the axis)                   (line 15)
+    pz_mul<NT, 9, 3, 3>(S, Z.WD[c], Z.Rt[i], Z.WD[p]);
+    if (axis != 0) {
+        pz_set_const<NT, 3>(T[0], zero3);
+        pz_add_one_dim<NT>(S, T[0], T[0], Z.qd[i], row);
+        pz_cross_pp<NT>(S, T[1], Z.WA[c], T[0]);
+        pz_add3<NT>(S, Z.WD[c], Z.WD[c], T[1]);
+        pz_add_one_dim<NT>(S, Z.WD[c], Z.WD[c], Z.qdda[i], row);
+        pz_add_one_dim<NT>(S, Z.WA[c], Z.WA[c], Z.qda[i], row);
+    }
+}
+// F = m * (linear_acc + cross(wdot, com) + cross(w, cross(w_aux, com))), N = I * wdot + cross(w_aux, I * w)
+// from the state after joint i (KPR/Dynamics.cu:146-154)
+template <int NT>
+__device__ void force_joint(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, int i, int c) {
+    const RobotModel& rm = c_robot;
+    pz_cross_const<NT>(S, T[0], Z.WD[c], rm.com[i], false);
+    pz_cross_const<NT>(S, T[1], Z.WA[c], rm.com[i], false);
+    pz_cross_pp<NT>(S, T[2], Z.W[c], T[1]);
+    pz_add3<NT>(S, T[3], Z.LA[c], T[0]);
+    pz_add3<NT>(S, T[3], T[3], T[2]);
+    {
+        const double m0 = 0.0, m1 = __dmul_ru(tb.mass_unc, fabs(rm.mass[i]));
+        pz_const_left<NT>(S, Z.F[i], &rm.mass[i], &m0, &m1, true, T[3]);
+    }
+    {
+        double I0[9], I1[9];
+        for (int k = 0; k < 9; k++) { I0[k] = 0.0; I1[k] = __dmul_ru(tb.inertia_unc, fabs(rm.inertia[i][k])); }
+        pz_const_left<NT>(S, T[0], rm.inertia[i], I0, I1, false, Z.WD[c]);
+        pz_const_left<NT>(S, T[1], rm.inertia[i], I0, I1, false, Z.W[c]);
+    }
+    pz_cross_pp<NT>(S, T[2], Z.WA[c], T[1]);
+    pz_add3<NT>(S, Z.N[i], T[0], T[2]);
+}
+// forward kinematics + reduce_link_PZ (KPR/Dynamics.cu:69-81, armour_main.cu:123-126)
+template <int NT>
+__device__ void forward_kinematics(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0) {
+    const RobotModel& rm = c_robot;
+    const double zero3[3] = {0, 0, 0};
+    pz_set_const<NT, 9>(Z.FKR, rm.R0[NJ]);
+    pz_set_const<NT, 3>(Z.FKT, zero3);
+    for (int i = 0; i < NJ; i++) {
+        pz_const_right<NT>(S, T[0], Z.FKR, rm.trans[i]);          // FK_R * P
+        pz_add3<NT>(S, Z.FKT, Z.FKT, T[0]);                       // FK_T = FK_T + FK_R * P
+        pz_mul<NT, 9, 9, 9>(S, Z.FKR, Z.FKR, Z.R[i]);             // FK_R = FK_R * R_i
+        pz_mul<NT, 9, 3, 3>(S, T[1], Z.FKR, Z.link0[i]);          // FK_R * link_i
+        pz_add3<NT>(S, Z.LINK[i], T[1], Z.FKT);                   //          + FK_T
+        export_link<NT>(S, tb, rec0 + i, Z.LINK[i]);
+    }
+}
+// RNEA reverse recursion for joint i (KPR/Dynamics.cu:161-180)
+template <int NT>
+__device__ void backward_joint(Scratch& S, Slots& Z, PZ<3>* T, int i) {
+    const RobotModel& rm = c_robot;
+    const int axis = rm.axes[i];
+    const int row = (axis < 0 ? -axis : axis) - 1;
+    // n = N + R * n + cross(com, F) + cross(trans_{i+1}, R * f)                              (line 29)
+    pz_mul<NT, 9, 3, 3>(S, T[0], Z.R[i + 1], Z.Nv);
+    pz_add3<NT>(S, T[1], Z.N[i], T[0]);
+    pz_cross_const<NT>(S, T[2], Z.F[i], rm.com[i], true);
+    pz_add3<NT>(S, T[1], T[1], T[2]);
+    pz_mul<NT, 9, 3, 3>(S, T[3], Z.R[i + 1], Z.Fv);             // R * f (the reference evaluates it twice)
+    pz_cross_const<NT>(S, T[2], T[3], rm.trans[i + 1], true);
+    pz_add3<NT>(S, Z.Nv, T[1], T[2]);
+    // f = R * f + F                                                                           (line 28)
+    pz_add3<NT>(S, Z.Fv, T[3], Z.F[i]);
+    if (axis != 0) {
+        // u = n(axis) + armature * qdda_des + damping * qd_des
+        pz_merge<NT, 3, 1, 1>(S, Z.u[i], view_extract(Z.Nv, row), view_scaled(Z.qdda[i], rm.armature[i]), false);
+        pz_merge<NT, 1, 1, 1>(S, Z.u[i], view(Z.u[i]), view_scaled(Z.qd[i], rm.damping[i]), false);
+    }
+}
+
+// GROUPS == 1: one group of NT threads runs the whole program in the reference's order.
+// GROUPS == 2: group 0 runs the joint chain and then the reverse recursion; group 1 computes each joint's F / N as
+// soon as the chain publishes that joint's state, then the forward kinematics while group 0 recurses backwards.
+// Critical path: 98 + 11 + 70 operations instead of 280.
+template <int NT, int MINB, int GROUPS>
+__global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables tb, char* arena, size_t arena_stride, int mcap, int ncap, int n_work) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ Scratch SS[GROUPS];
+    __shared__ Slots Z;
+    __shared__ volatile int sig_state, sig_force;
+    const RobotModel& rm = c_robot;
+    const int group = threadIdx.x / NT;
+    Scratch& S = SS[group];
+    PZ<3>* T = Z.T[group];
     if (threadIdx.x == 0) {
-        S.bind(smem_raw, ncap);
-        S.thr = tb.thr; S.thr_sq = squared_threshold(tb.thr); S.gerr = tb.err;
         char* g = arena + (size_t)blockIdx.x * arena_stride;
-        PZ<3>* big3[] = {&Z.W, &Z.WD, &Z.WA, &Z.LA, &Z.T1, &Z.T2, &Z.T3, &Z.T4, &Z.T5, &Z.Fv, &Z.Nv, &Z.FKT};
-        for (PZ<3>* z : big3) g = carve<3>(*z, g, mcap);
+        for (int k = 0; k < 2; k++) { g = carve<3>(Z.W[k], g, mcap); g = carve<3>(Z.WD[k], g, mcap); g = carve<3>(Z.WA[k], g, mcap); g = carve<3>(Z.LA[k], g, mcap); }
+        for (int k = 0; k < 2; k++) for (int t = 0; t < 5; t++) g = carve<3>(Z.T[k][t], g, mcap);
+        g = carve<3>(Z.Fv, g, mcap); g = carve<3>(Z.Nv, g, mcap); g = carve<3>(Z.FKT, g, mcap);
         for (int i = 0; i < NJ; i++) { g = carve<3>(Z.F[i], g, mcap); g = carve<3>(Z.N[i], g, mcap); g = carve<3>(Z.LINK[i], g, mcap); g = carve<3>(Z.link0[i], g, SMALL_CAP); }
         g = carve<9>(Z.FKR, g, mcap);
         for (int i = 0; i <= NJ; i++) g = carve<9>(Z.R[i], g, SMALL_CAP);
@@ -393,16 +523,22 @@ __global__ void __launch_bounds__(NT, MINB) reach_build_kernel(Tables tb, char* 
             g = carve<1>(Z.cosq[i], g, SMALL_CAP); g = carve<1>(Z.sinq[i], g, SMALL_CAP);
             g = carve<1>(Z.u[i], g, mcap);
         }
-        S.tmp = (double*)g;
+        const double thr_sq = squared_threshold(tb.thr);
+        for (int k = 0; k < GROUPS; k++) {
+            SS[k].bind(smem_raw + (size_t)k * reach_smem_bytes_dev(ncap), ncap);
+            SS[k].thr = tb.thr; SS[k].thr_sq = thr_sq; SS[k].gerr = tb.err;
+            SS[k].tmp = (double*)g + (size_t)k * 9 * ncap;
+        }
     }
     __syncthreads();
     const double zero3[3] = {0, 0, 0};
-
 #ifdef ARMOUR_PHASE_TIMING
     if (threadIdx.x == 0) g_phase_clock.last = clock64();
 #endif
     for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
         const int prob = work / tb.T, s = work - prob * tb.T;
+        const size_t rec0 = ((size_t)prob * tb.T + s) * NJ;
+        if (threadIdx.x == 0) { sig_state = 0; sig_force = 0; }
         __syncthreads();
         // ---- stage A: joint reach sets (one thread per joint; tiny scalar work) -------------------
         if (threadIdx.x < NJ) {
@@ -433,116 +569,87 @@ __global__ void __launch_bounds__(NT, MINB) reach_build_kernel(Tables tb, char* 
             L0.n = n; L0.divM = FastDiv::magic(n);
             for (int c = 0; c < 3; c++) { L0.center[c] = rm.link_c[i][c]; L0.ind[0][c] = ind[c]; L0.ind[1][c] = ind[c]; L0.abss[c] = abss[c]; }
         }
-        if (threadIdx.x == NJ) {   // R(NUM_JOINTS) = identity
+        if (threadIdx.x == NJ) {   // R(NUM_JOINTS) = identity; initial RNEA state (KPR/Dynamics.cu:87-99) in set 1 (= "before joint 0")
             PZ<9>& R = Z.R[NJ];
             R.n = 0; R.divM = FastDiv::magic(0);
             for (int c = 0; c < 9; c++) { R.center[c] = rm.R0[NJ][c]; R.ind[0][c] = 0; R.ind[1][c] = 0; R.abss[c] = 0; }
+            PZ<3>* init[6] = {&Z.W[1], &Z.WD[1], &Z.WA[1], &Z.LA[1], &Z.Fv, &Z.Nv};
+            for (PZ<3>* z : init) { z->n = 0; z->divM = FastDiv::magic(0); for (int c = 0; c < 3; c++) { z->center[c] = 0; z->ind[0][c] = 0; z->ind[1][c] = 0; z->abss[c] = 0; } }
+            Z.LA[1].center[2] = rm.gravity;
         }
         __syncthreads();
         phase_mark(PH_STAGE_A);
 
-        // ---- stage B: forward kinematics (KPR/Dynamics.cu:69-81) ------------------------------------
-        pz_set_const<9>(Z.FKR, rm.R0[NJ]);
-        pz_set_const<3>(Z.FKT, zero3);
-        for (int i = 0; i < NJ; i++) {
-            pz_const_right<NT>(S, Z.T1, Z.FKR, rm.trans[i]);          // FK_R * P
-            pz_add3<NT>(S, Z.FKT, Z.FKT, Z.T1);                       // FK_T = FK_T + FK_R * P
-            pz_mul<NT, 9, 9, 9>(S, Z.FKR, Z.FKR, Z.R[i]);             // FK_R = FK_R * R_i
-            pz_mul<NT, 9, 3, 3>(S, Z.T2, Z.FKR, Z.link0[i]);          // FK_R * link_i
-            pz_add3<NT>(S, Z.LINK[i], Z.T2, Z.FKT);                   //          + FK_T
-            export_link<NT>(S, tb, ((size_t)prob * tb.T + s) * NJ + i, Z.LINK[i]);
+#ifdef ARMOUR_PHASE_TIMING
+#define PIECE_T0() long long pt0__ = clock64()
+#define PIECE(acc) do { const long long t__ = clock64(); acc += t__ - pt0__; pt0__ = t__; } while (0)
+        long long pc_chain = 0, pc_force = 0, pc_fk = 0, pc_back = 0, pc_wait = 0;
+#else
+#define PIECE_T0()
+#define PIECE(acc)
+#endif
+        PIECE_T0();
+        if (GROUPS == 1) {
+            forward_kinematics<NT>(S, Z, T, tb, rec0);                                    // stage B
+            for (int i = 0; i < NJ; i++) {                                                 // stage C forward
+                chain_joint<NT>(S, Z, T, i, (i + 1) & 1, i & 1);
+                force_joint<NT>(S, Z, T, tb, i, i & 1);
+            }
+            for (int i = NJ - 1; i >= 0; i--) backward_joint<NT>(S, Z, T, i);             // stage C backward
         }
-
-        // ---- stage C: RNEA forward recursion (KPR/Dynamics.cu:83-155) -------------------------------
-        pz_set_const<3>(Z.W, zero3); pz_set_const<3>(Z.WD, zero3); pz_set_const<3>(Z.WA, zero3);
-        { const double g3[3] = {0, 0, rm.gravity}; pz_set_const<3>(Z.LA, g3); }
-        for (int i = 0; i < NJ; i++) {
-            const int axis = rm.axes[i];
-            const int row = (axis < 0 ? -axis : axis) - 1;
-            // linear_acc = R_t * (linear_acc + cross(wdot, trans) + cross(w, cross(w_aux, trans)))   (line 16)
-            pz_cross_const<NT>(S, Z.T1, Z.WD, rm.trans[i], false);
-            pz_cross_const<NT>(S, Z.T2, Z.WA, rm.trans[i], false);
-            pz_cross_pp<NT>(S, Z.T3, Z.W, Z.T2);
-            pz_add3<NT>(S, Z.T4, Z.LA, Z.T1);
-            pz_add3<NT>(S, Z.T4, Z.T4, Z.T3);
-            pz_mul<NT, 9, 3, 3>(S, Z.LA, Z.Rt[i], Z.T4);
-            // w = R_t * w (+ qd_des on the joint axis)                                               (line 13)
-            pz_mul<NT, 9, 3, 3>(S, Z.W, Z.Rt[i], Z.W);
-            if (axis != 0) pz_add_one_dim<NT>(S, Z.W, Z.W, Z.qd[i], row);
-            // w_aux = R_t * w_aux                                                                     (line 14)
-            pz_mul<NT, 9, 3, 3>(S, Z.WA, Z.Rt[i], Z.WA);
-            // wdot = R_t * wdot (+ cross(w_aux, qd_des * z) + qdda_des on the axis)                   (line 15)
-            pz_mul<NT, 9, 3, 3>(S, Z.WD, Z.Rt[i], Z.WD);
-            if (axis != 0) {
-                pz_set_const<3>(Z.T1, zero3);
-                pz_add_one_dim<NT>(S, Z.T1, Z.T1, Z.qd[i], row);
-                pz_cross_pp<NT>(S, Z.T2, Z.WA, Z.T1);
-                pz_add3<NT>(S, Z.WD, Z.WD, Z.T2);
-                pz_add_one_dim<NT>(S, Z.WD, Z.WD, Z.qdda[i], row);
-                pz_add_one_dim<NT>(S, Z.WA, Z.WA, Z.qda[i], row);
+        else if (group == 0) {
+            for (int i = 0; i < NJ; i++) {
+                if (i >= 2) group_wait<NT>(S, &sig_force, i - 1);    // set i&1 was read by the force step of joint i-2
+                PIECE(pc_wait);
+                chain_joint<NT>(S, Z, T, i, (i + 1) & 1, i & 1);
+                group_signal<NT>(&sig_state, i + 1);
+                PIECE(pc_chain);
             }
-            // F = m * (linear_acc + cross(wdot, com) + cross(w, cross(w_aux, com)))                  (lines 23 & 27)
-            pz_cross_const<NT>(S, Z.T1, Z.WD, rm.com[i], false);
-            pz_cross_const<NT>(S, Z.T2, Z.WA, rm.com[i], false);
-            pz_cross_pp<NT>(S, Z.T3, Z.W, Z.T2);
-            pz_add3<NT>(S, Z.T4, Z.LA, Z.T1);
-            pz_add3<NT>(S, Z.T4, Z.T4, Z.T3);
-            {
-                const double m0 = 0.0, m1 = __dmul_ru(tb.mass_unc, fabs(rm.mass[i]));
-                pz_const_left<NT>(S, Z.F[i], &rm.mass[i], &m0, &m1, true, Z.T4);
-            }
-            // N = I * wdot + cross(w_aux, I * w)                                                      (line 29)
-            {
-                double I0[9], I1[9];
-                for (int c = 0; c < 9; c++) { I0[c] = 0.0; I1[c] = __dmul_ru(tb.inertia_unc, fabs(rm.inertia[i][c])); }
-                pz_const_left<NT>(S, Z.T1, rm.inertia[i], I0, I1, false, Z.WD);
-                pz_const_left<NT>(S, Z.T2, rm.inertia[i], I0, I1, false, Z.W);
-            }
-            pz_cross_pp<NT>(S, Z.T3, Z.WA, Z.T2);
-            pz_add3<NT>(S, Z.N[i], Z.T1, Z.T3);
-        }
-
-        // ---- RNEA reverse recursion (KPR/Dynamics.cu:157-180) ---------------------------------------
-        pz_set_const<3>(Z.Fv, zero3); pz_set_const<3>(Z.Nv, zero3);
-        for (int i = NJ - 1; i >= 0; i--) {
-            const int axis = rm.axes[i];
-            const int row = (axis < 0 ? -axis : axis) - 1;
-            // n = N + R * n + cross(com, F) + cross(trans_{i+1}, R * f)                              (line 29)
-            pz_mul<NT, 9, 3, 3>(S, Z.T1, Z.R[i + 1], Z.Nv);
-            pz_add3<NT>(S, Z.T2, Z.N[i], Z.T1);
-            pz_cross_const<NT>(S, Z.T3, Z.F[i], rm.com[i], true);
-            pz_add3<NT>(S, Z.T2, Z.T2, Z.T3);
-            pz_mul<NT, 9, 3, 3>(S, Z.T4, Z.R[i + 1], Z.Fv);             // R * f (the reference evaluates it twice)
-            pz_cross_const<NT>(S, Z.T3, Z.T4, rm.trans[i + 1], true);
-            pz_add3<NT>(S, Z.Nv, Z.T2, Z.T3);
-            // f = R * f + F                                                                           (line 28)
-            pz_add3<NT>(S, Z.Fv, Z.T4, Z.F[i]);
-            if (axis != 0) {
-                // u = n(axis) + armature * qdda_des + damping * qd_des
-                pz_merge<NT, 3, 1, 1>(S, Z.u[i], view_extract(Z.Nv, row), view_scaled(Z.qdda[i], rm.armature[i]), false);
-                pz_merge<NT, 1, 1, 1>(S, Z.u[i], view(Z.u[i]), view_scaled(Z.qd[i], rm.damping[i]), false);
+            for (int i = NJ - 1; i >= 0; i--) {
+                group_wait<NT>(S, &sig_force, i + 1);
+                PIECE(pc_wait);
+                backward_joint<NT>(S, Z, T, i);
+                PIECE(pc_back);
             }
         }
+        else {
+            for (int i = 0; i < NJ; i++) {
+                group_wait<NT>(S, &sig_state, i + 1);
+                PIECE(pc_wait);
+                force_joint<NT>(S, Z, T, tb, i, i & 1);
+                group_signal<NT>(&sig_force, i + 1);
+                PIECE(pc_force);
+            }
+            forward_kinematics<NT>(S, Z, T, tb, rec0);
+            PIECE(pc_fk);
+        }
+#ifdef ARMOUR_PHASE_TIMING
+        if (blockIdx.x == 64 && gtid<NT>() == 0)
+            printf("PIECES group %d: chain %lld force %lld fk %lld backward %lld wait %lld (cycles)\n", group, pc_chain, pc_force, pc_fk, pc_back, pc_wait);
+#endif
 
         // ---- stage M: disturbance, reduce(), torque radius (KPR/armour_main.cu:135-205) -------------
-        for (int i = 0; i < NF; i++) export_torque<NT>(S, tb, ((size_t)prob * tb.T + s) * NF + i, Z.u[i]);
-        if (threadIdx.x == 0) {
-            const size_t base = ((size_t)prob * tb.T + s) * NF;
-            // rho = sqrt(sum_i [-r_i, r_i]^2): only the upper end is used; everything rounded up
-            double rho = 0.0;
-            for (int i = 0; i < NF; i++) { const double r = tb.dist_rad[base + i]; rho = __dadd_ru(rho, __dmul_ru(r, r)); }
-            rho = __dsqrt_ru(rho);
-            const double c0 = __dmul_ru(__dmul_ru(rm.alpha, __dadd_ru(rm.M_max, -rm.M_min)), rm.eps);
-            for (int i = 0; i < NF; i++) {
-                double tr = __dadd_ru(c0, __dmul_ru(0.5, tb.dist_rad[base + i]));
-                tr = __dadd_ru(tr, __dmul_ru(0.5, rho));
-                tr = __dadd_ru(tr, tb.u_ind[base + i]);
-                tr = __dadd_ru(tr, rm.friction[i]);
-                tb.torque_radius[base + i] = tr;
+        if (group == 0) {
+            for (int i = 0; i < NF; i++) export_torque<NT>(S, tb, rec0 + i, Z.u[i]);
+            if (threadIdx.x == 0) {
+                const size_t base = rec0;
+                // rho = sqrt(sum_i [-r_i, r_i]^2): only the upper end is used; everything rounded up
+                double rho = 0.0;
+                for (int i = 0; i < NF; i++) { const double r = tb.dist_rad[base + i]; rho = __dadd_ru(rho, __dmul_ru(r, r)); }
+                rho = __dsqrt_ru(rho);
+                const double c0 = __dmul_ru(__dmul_ru(rm.alpha, __dadd_ru(rm.M_max, -rm.M_min)), rm.eps);
+                for (int i = 0; i < NF; i++) {
+                    double tr = __dadd_ru(c0, __dmul_ru(0.5, tb.dist_rad[base + i]));
+                    tr = __dadd_ru(tr, __dmul_ru(0.5, rho));
+                    tr = __dadd_ru(tr, tb.u_ind[base + i]);
+                    tr = __dadd_ru(tr, rm.friction[i]);
+                    tb.torque_radius[base + i] = tr;
+                }
             }
         }
         __syncthreads();
     }
+    (void)zero3;
 }
 
 // ---- stand-alone PZsparse arithmetic (PZsparse facade / primitive parity tests) -----------------------
@@ -594,22 +701,23 @@ __global__ void __launch_bounds__(NT) pz_binary_kernel(int op, FlatPZ a, FlatPZ 
 // ---- host-side launch helpers -----------------------------------------------------------------
 cudaError_t upload_robot_model(const RobotModel& rm) { return cudaMemcpyToSymbol(c_robot, &rm, sizeof(RobotModel)); }
 
-size_t reach_smem_bytes(int ncap) { return (size_t)ncap * 20 + (size_t)3 * 1024 * 8; }   // sort ping-pong + per-key staging (Scratch::TCAP)
+size_t reach_smem_bytes(int ncap) { return reach_smem_bytes_dev(ncap); }
 
-// kernel variants: (threads per CTA, CTAs per SM the register allocation is bounded for)
+// kernel variants: (threads per group, CTAs per SM the register allocation is bounded for, thread groups per CTA)
 typedef void (*ReachKernel)(Tables, char*, size_t, int, int, int);
-static ReachKernel pick_reach_kernel(int nt, int minb) {
-    if (nt == 128) return minb >= 4 ? reach_build_kernel<128, 4> : reach_build_kernel<128, 2>;
-    if (nt == 512) return reach_build_kernel<512, 1>;
-    return minb >= 2 ? reach_build_kernel<256, 2> : reach_build_kernel<256, 1>;
+static ReachKernel pick_reach_kernel(int nt, int minb, int groups) {
+    if (groups == 2) return reach_build_kernel<256, 1, 2>;
+    if (nt == 128) return minb >= 4 ? reach_build_kernel<128, 4, 1> : reach_build_kernel<128, 2, 1>;
+    if (nt == 512) return reach_build_kernel<512, 1, 1>;
+    return minb >= 2 ? reach_build_kernel<256, 2, 1> : reach_build_kernel<256, 1, 1>;
 }
-cudaError_t launch_reach_build(const Tables& tb, char* arena, size_t arena_stride, int mcap, int ncap, int n_work, int grid, int nt, int minb, cudaStream_t stream) {
-    const size_t smem = reach_smem_bytes(ncap);
-    ReachKernel k = pick_reach_kernel(nt, minb);
+static int reach_threads(int nt, int groups) { return groups == 2 ? 512 : nt == 128 ? 128 : nt == 512 ? 512 : 256; }
+cudaError_t launch_reach_build(const Tables& tb, char* arena, size_t arena_stride, int mcap, int ncap, int n_work, int grid, int nt, int minb, int groups, cudaStream_t stream) {
+    const size_t smem = reach_smem_bytes(ncap) * (groups == 2 ? 2 : 1);
+    ReachKernel k = pick_reach_kernel(nt, minb, groups);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int threads = nt == 128 ? 128 : nt == 512 ? 512 : 256;
-    k<<<grid, threads, smem, stream>>>(tb, arena, arena_stride, mcap, ncap, n_work);
+    k<<<grid, reach_threads(nt, groups), smem, stream>>>(tb, arena, arena_stride, mcap, ncap, n_work);
     return cudaGetLastError();
 }
 
@@ -637,13 +745,13 @@ void read_phase_cycles(unsigned long long* cycles, unsigned long long* calls, bo
 #endif
 }
 
-int reach_max_ctas_per_sm(int nt, int minb, int ncap) {
+// resident CTAs per SM for a variant; 0 when it does not fit (e.g. two groups with large sort buffers)
+int reach_max_ctas_per_sm(int nt, int minb, int groups, int ncap) {
     int n = 0;
-    const size_t smem = reach_smem_bytes(ncap);
-    ReachKernel k = pick_reach_kernel(nt, minb);
-    const int threads = nt == 128 ? 128 : nt == 512 ? 512 : 256;
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem) != cudaSuccess) return 0;
+    const size_t smem = reach_smem_bytes(ncap) * (groups == 2 ? 2 : 1);
+    ReachKernel k = pick_reach_kernel(nt, minb, groups);
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, reach_threads(nt, groups), smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
 

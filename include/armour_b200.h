@@ -54,7 +54,7 @@ typedef struct armour_config {
     double simplify_threshold;  /* SIMPLIFY_THRESHOLD, default 5e-4                     (Parameters.h:10) */
     int max_obstacles;          /* MAX_OBSTACLE_NUM, default 40                         (Parameters.h:26) */
     int max_monomials;          /* capacity of one PZ's monomial list; default 1024 (0 = default)  */
-    int max_entries;            /* capacity of one sort (candidate monomials of one op); default 4096 (0 = default) */
+    int max_entries;            /* capacity of one sort (candidate monomials of one op); default 3072 (0 = default) */
     int threads_per_cta;        /* 128, 256 or 512; default 256 (0 = default)            */
     int device;                 /* CUDA device ordinal; -1 = current device              */
     int batch;                  /* problems one handle builds per armour_build_batch call; default 1 */
