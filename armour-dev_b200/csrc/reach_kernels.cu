@@ -354,11 +354,12 @@ __device__ __noinline__ void export_torque(Scratch& S, const Tables& tb, size_t 
 struct Slots {
     PZ<3> W[2], WD[2], WA[2], LA[2];
     PZ<3> T[2][5];                       // temporaries, one set per thread group
+    PZ<3> C1[NJ], C2[NJ];                // two-group hand-off: cross(com, F_i), cross(trans_{i+1}, R_{i+1} f_{i+1})
     PZ<3> F[NJ], N[NJ], Fv, Nv, FKT, LINK[NJ], link0[NJ];
     PZ<9> FKR, R[NJ + 1], Rt[NJ];
     PZ<1> qd[NJ], qda[NJ], qdda[NJ], u[NJ], cosq[NJ], sinq[NJ];
 };
-constexpr int N_BIG3 = 8 + 10 + 3 + 3 * NJ;
+constexpr int N_BIG3 = 8 + 10 + 3 + 5 * NJ;
 
 size_t arena_bytes(int mcap, int ncap) {
     size_t b = 0;
@@ -402,6 +403,16 @@ __device__ __forceinline__ void group_wait(Scratch& S, volatile int* flag, int n
     gsync<NT>();
 }
 
+// group-uniform test of a hand-off counter (thread 0 reads, the group barrier broadcasts)
+template <int NT>
+__device__ __forceinline__ bool group_ready(Scratch& S, volatile int* flag, int needed) {
+    if (gtid<NT>() == 0) { const int ok = *flag >= needed; if (ok) __threadfence_block(); S.iscan[33] = ok; }
+    gsync<NT>();
+    const bool r = S.iscan[33] != 0;
+    gsync<NT>();
+    return r;
+}
+
 // ---- the per-interval program, in four pieces --------------------------------------------------------------
 // RNEA forward recursion, joint chain (KPR/Dynamics.cu:102-137): state `p` (after joint i-1) -> state `c`
 template <int NT>
@@ -436,12 +447,12 @@ __device__ void chain_joint(Scratch& S, Slots& Z, PZ<3>* T, int i, int p, int c)
 // F = m * (linear_acc + cross(wdot, com) + cross(w, cross(w_aux, com))), N = I * wdot + cross(w_aux, I * w)
 // from the state after joint i (KPR/Dynamics.cu:146-154)
 template <int NT>
-__device__ void force_joint(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, int i, int c) {
+__device__ void force_joint(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, int i, int c, const PZ<3>& LA) {
     const RobotModel& rm = c_robot;
     pz_cross_const<NT>(S, T[0], Z.WD[c], rm.com[i], false);
     pz_cross_const<NT>(S, T[1], Z.WA[c], rm.com[i], false);
     pz_cross_pp<NT>(S, T[2], Z.W[c], T[1]);
-    pz_add3<NT>(S, T[3], Z.LA[c], T[0]);
+    pz_add3<NT>(S, T[3], LA, T[0]);
     pz_add3<NT>(S, T[3], T[3], T[2]);
     {
         const double m0 = 0.0, m1 = __dmul_ru(tb.mass_unc, fabs(rm.mass[i]));
@@ -456,21 +467,22 @@ __device__ void force_joint(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, in
     pz_cross_pp<NT>(S, T[2], Z.WA[c], T[1]);
     pz_add3<NT>(S, Z.N[i], T[0], T[2]);
 }
-// forward kinematics + reduce_link_PZ (KPR/Dynamics.cu:69-81, armour_main.cu:123-126)
+// forward kinematics + reduce_link_PZ, one joint (KPR/Dynamics.cu:69-81, armour_main.cu:123-126)
 template <int NT>
-__device__ void forward_kinematics(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0) {
+__device__ void fk_joint(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0, int i) {
     const RobotModel& rm = c_robot;
     const double zero3[3] = {0, 0, 0};
-    pz_set_const<NT, 9>(Z.FKR, rm.R0[NJ]);
-    pz_set_const<NT, 3>(Z.FKT, zero3);
-    for (int i = 0; i < NJ; i++) {
-        pz_const_right<NT>(S, T[0], Z.FKR, rm.trans[i]);          // FK_R * P
-        pz_add3<NT>(S, Z.FKT, Z.FKT, T[0]);                       // FK_T = FK_T + FK_R * P
-        pz_mul<NT, 9, 9, 9>(S, Z.FKR, Z.FKR, Z.R[i]);             // FK_R = FK_R * R_i
-        pz_mul<NT, 9, 3, 3>(S, T[1], Z.FKR, Z.link0[i]);          // FK_R * link_i
-        pz_add3<NT>(S, Z.LINK[i], T[1], Z.FKT);                   //          + FK_T
-        export_link<NT>(S, tb, rec0 + i, Z.LINK[i]);
-    }
+    if (i == 0) { pz_set_const<NT, 9>(Z.FKR, rm.R0[NJ]); pz_set_const<NT, 3>(Z.FKT, zero3); }
+    pz_const_right<NT>(S, T[4], Z.FKR, rm.trans[i]);          // FK_R * P
+    pz_add3<NT>(S, Z.FKT, Z.FKT, T[4]);                       // FK_T = FK_T + FK_R * P
+    pz_mul<NT, 9, 9, 9>(S, Z.FKR, Z.FKR, Z.R[i]);             // FK_R = FK_R * R_i
+    pz_mul<NT, 9, 3, 3>(S, T[4], Z.FKR, Z.link0[i]);          // FK_R * link_i
+    pz_add3<NT>(S, Z.LINK[i], T[4], Z.FKT);                   //          + FK_T
+    export_link<NT>(S, tb, rec0 + i, Z.LINK[i]);
+}
+template <int NT>
+__device__ void forward_kinematics(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0) {
+    for (int i = 0; i < NJ; i++) fk_joint<NT>(S, Z, T, tb, rec0, i);
 }
 // RNEA reverse recursion for joint i (KPR/Dynamics.cu:161-180)
 template <int NT>
@@ -495,16 +507,75 @@ __device__ void backward_joint(Scratch& S, Slots& Z, PZ<3>* T, int i) {
     }
 }
 
+// ---- the same program cut for two thread groups ------------------------------------------------------------
+// Group 0 owns the angular recurrence (w, w_aux, wdot), the moment recursion n and — in the time it would spend
+// waiting for group 1 — the forward kinematics; group 1 owns linear_acc, the link forces F / N and the force recursion f.  Operands and operation order of every PZ
+// operation are exactly those of chain_joint / force_joint / backward_joint.
+template <int NT>
+__device__ void angular_joint(Scratch& S, Slots& Z, PZ<3>* T, int i, int p, int c) {
+    const RobotModel& rm = c_robot;
+    const double zero3[3] = {0, 0, 0};
+    const int axis = rm.axes[i];
+    const int row = (axis < 0 ? -axis : axis) - 1;
+    pz_mul<NT, 9, 3, 3>(S, Z.W[c], Z.Rt[i], Z.W[p]);
+    if (axis != 0) pz_add_one_dim<NT>(S, Z.W[c], Z.W[c], Z.qd[i], row);
+    pz_mul<NT, 9, 3, 3>(S, Z.WA[c], Z.Rt[i], Z.WA[p]);
+    pz_mul<NT, 9, 3, 3>(S, Z.WD[c], Z.Rt[i], Z.WD[p]);
+    if (axis != 0) {
+        pz_set_const<NT, 3>(T[0], zero3);
+        pz_add_one_dim<NT>(S, T[0], T[0], Z.qd[i], row);
+        pz_cross_pp<NT>(S, T[1], Z.WA[c], T[0]);
+        pz_add3<NT>(S, Z.WD[c], Z.WD[c], T[1]);
+        pz_add_one_dim<NT>(S, Z.WD[c], Z.WD[c], Z.qdda[i], row);
+        pz_add_one_dim<NT>(S, Z.WA[c], Z.WA[c], Z.qda[i], row);
+    }
+}
+// group 1: linear_acc = R_t * (linear_acc + cross(wdot, trans) + cross(w, cross(w_aux, trans))) from the PREVIOUS
+// angular state (set p)   (KPR/Dynamics.cu:110-112, line 16)
+template <int NT>
+__device__ void linacc_joint(Scratch& S, Slots& Z, PZ<3>* T, int i, int p, PZ<3>& LA) {
+    const RobotModel& rm = c_robot;
+    pz_cross_const<NT>(S, T[0], Z.WD[p], rm.trans[i], false);
+    pz_cross_const<NT>(S, T[1], Z.WA[p], rm.trans[i], false);
+    pz_cross_pp<NT>(S, T[2], Z.W[p], T[1]);
+    pz_add3<NT>(S, T[3], LA, T[0]);
+    pz_add3<NT>(S, T[3], T[3], T[2]);
+    pz_mul<NT, 9, 3, 3>(S, LA, Z.Rt[i], T[3]);
+}
+// group 1, reverse recursion of f and the two cross terms of n (KPR/Dynamics.cu:163-169)
+template <int NT>
+__device__ void side_joint(Scratch& S, Slots& Z, PZ<3>* T, int i) {
+    const RobotModel& rm = c_robot;
+    pz_mul<NT, 9, 3, 3>(S, T[3], Z.R[i + 1], Z.Fv);                       // R * f
+    pz_cross_const<NT>(S, Z.C2[i], T[3], rm.trans[i + 1], true);         // cross(trans, R * f)
+    pz_cross_const<NT>(S, Z.C1[i], Z.F[i], rm.com[i], true);             // cross(com, F)
+    pz_add3<NT>(S, Z.Fv, T[3], Z.F[i]);                                   // f = R * f + F
+}
+// group 0, reverse recursion of n and the torque (KPR/Dynamics.cu:163-179)
+template <int NT>
+__device__ void moment_joint(Scratch& S, Slots& Z, PZ<3>* T, int i) {
+    const RobotModel& rm = c_robot;
+    const int axis = rm.axes[i];
+    const int row = (axis < 0 ? -axis : axis) - 1;
+    pz_mul<NT, 9, 3, 3>(S, T[0], Z.R[i + 1], Z.Nv);
+    pz_add3<NT>(S, T[1], Z.N[i], T[0]);
+    pz_add3<NT>(S, T[1], T[1], Z.C1[i]);
+    pz_add3<NT>(S, Z.Nv, T[1], Z.C2[i]);
+    if (axis != 0) {
+        pz_merge<NT, 3, 1, 1>(S, Z.u[i], view_extract(Z.Nv, row), view_scaled(Z.qdda[i], rm.armature[i]), false);
+        pz_merge<NT, 1, 1, 1>(S, Z.u[i], view(Z.u[i]), view_scaled(Z.qd[i], rm.damping[i]), false);
+    }
+}
+
 // GROUPS == 1: one group of NT threads runs the whole program in the reference's order.
-// GROUPS == 2: group 0 runs the joint chain and then the reverse recursion; group 1 computes each joint's F / N as
-// soon as the chain publishes that joint's state, then the forward kinematics while group 0 recurses backwards.
-// Critical path: 98 + 11 + 70 operations instead of 280.
+// GROUPS == 2: see angular_joint / linacc_joint / side_joint / moment_joint above: the two groups run side by side and
+// hand PZs over through shared-memory counters; the critical path is roughly half of the 280 operations.
 template <int NT, int MINB, int GROUPS>
 __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables tb, char* arena, size_t arena_stride, int mcap, int ncap, int n_work) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Scratch SS[GROUPS];
     __shared__ Slots Z;
-    __shared__ volatile int sig_state, sig_force;
+    __shared__ volatile int sig_la, sig_state, sig_force, sig_side;
     const RobotModel& rm = c_robot;
     const int group = threadIdx.x / NT;
     Scratch& S = SS[group];
@@ -513,6 +584,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
         char* g = arena + (size_t)blockIdx.x * arena_stride;
         for (int k = 0; k < 2; k++) { g = carve<3>(Z.W[k], g, mcap); g = carve<3>(Z.WD[k], g, mcap); g = carve<3>(Z.WA[k], g, mcap); g = carve<3>(Z.LA[k], g, mcap); }
         for (int k = 0; k < 2; k++) for (int t = 0; t < 5; t++) g = carve<3>(Z.T[k][t], g, mcap);
+        for (int i = 0; i < NJ; i++) { g = carve<3>(Z.C1[i], g, mcap); g = carve<3>(Z.C2[i], g, mcap); }
         g = carve<3>(Z.Fv, g, mcap); g = carve<3>(Z.Nv, g, mcap); g = carve<3>(Z.FKT, g, mcap);
         for (int i = 0; i < NJ; i++) { g = carve<3>(Z.F[i], g, mcap); g = carve<3>(Z.N[i], g, mcap); g = carve<3>(Z.LINK[i], g, mcap); g = carve<3>(Z.link0[i], g, SMALL_CAP); }
         g = carve<9>(Z.FKR, g, mcap);
@@ -538,7 +610,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
     for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
         const int prob = work / tb.T, s = work - prob * tb.T;
         const size_t rec0 = ((size_t)prob * tb.T + s) * NJ;
-        if (threadIdx.x == 0) { sig_state = 0; sig_force = 0; }
+        if (threadIdx.x == 0) { sig_la = 0; sig_state = 0; sig_force = 0; sig_side = 0; }
         __syncthreads();
         // ---- stage A: joint reach sets (one thread per joint; tiny scalar work) -------------------
         if (threadIdx.x < NJ) {
@@ -593,35 +665,52 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
             forward_kinematics<NT>(S, Z, T, tb, rec0);                                    // stage B
             for (int i = 0; i < NJ; i++) {                                                 // stage C forward
                 chain_joint<NT>(S, Z, T, i, (i + 1) & 1, i & 1);
-                force_joint<NT>(S, Z, T, tb, i, i & 1);
+                force_joint<NT>(S, Z, T, tb, i, i & 1, Z.LA[i & 1]);
             }
             for (int i = NJ - 1; i >= 0; i--) backward_joint<NT>(S, Z, T, i);             // stage C backward
         }
         else if (group == 0) {
+            // angular recurrence, then the moment recursion; forward-kinematics joints fill the time spent waiting
+            int fk_next = 0;
             for (int i = 0; i < NJ; i++) {
-                if (i >= 2) group_wait<NT>(S, &sig_force, i - 1);    // set i&1 was read by the force step of joint i-2
+                // set i&1 still holds the state of joint i-2, read by group 1 until its linear_acc step of joint i-1 is done
+                if (i >= 1) {
+                    while (fk_next < NJ && !group_ready<NT>(S, &sig_la, i)) { fk_joint<NT>(S, Z, T, tb, rec0, fk_next++); PIECE(pc_fk); }
+                    group_wait<NT>(S, &sig_la, i);
+                }
                 PIECE(pc_wait);
-                chain_joint<NT>(S, Z, T, i, (i + 1) & 1, i & 1);
+                angular_joint<NT>(S, Z, T, i, (i + 1) & 1, i & 1);
                 group_signal<NT>(&sig_state, i + 1);
                 PIECE(pc_chain);
             }
             for (int i = NJ - 1; i >= 0; i--) {
-                group_wait<NT>(S, &sig_force, i + 1);
+                while (fk_next < NJ && !group_ready<NT>(S, &sig_side, NJ - i)) { fk_joint<NT>(S, Z, T, tb, rec0, fk_next++); PIECE(pc_fk); }
+                group_wait<NT>(S, &sig_side, NJ - i);
                 PIECE(pc_wait);
-                backward_joint<NT>(S, Z, T, i);
+                moment_joint<NT>(S, Z, T, i);
                 PIECE(pc_back);
             }
+            while (fk_next < NJ) { fk_joint<NT>(S, Z, T, tb, rec0, fk_next++); PIECE(pc_fk); }
         }
         else {
+            PZ<3>& LA = Z.LA[1];   // group 1's private linear_acc, initialised with gravity in stage A
             for (int i = 0; i < NJ; i++) {
+                group_wait<NT>(S, &sig_state, i);          // state of joint i-1 (the initial state for i = 0)
+                PIECE(pc_wait);
+                linacc_joint<NT>(S, Z, T, i, (i + 1) & 1, LA);
+                group_signal<NT>(&sig_la, i + 1);
+                PIECE(pc_chain);
                 group_wait<NT>(S, &sig_state, i + 1);
                 PIECE(pc_wait);
-                force_joint<NT>(S, Z, T, tb, i, i & 1);
+                force_joint<NT>(S, Z, T, tb, i, i & 1, LA);
                 group_signal<NT>(&sig_force, i + 1);
                 PIECE(pc_force);
             }
-            forward_kinematics<NT>(S, Z, T, tb, rec0);
-            PIECE(pc_fk);
+            for (int i = NJ - 1; i >= 0; i--) {
+                side_joint<NT>(S, Z, T, i);
+                group_signal<NT>(&sig_side, NJ - i);
+                PIECE(pc_back);
+            }
         }
 #ifdef ARMOUR_PHASE_TIMING
         if (blockIdx.x == 64 && gtid<NT>() == 0)
