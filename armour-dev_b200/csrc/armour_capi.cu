@@ -111,7 +111,8 @@ struct armour_handle {
     RobotModel model;
     Tables tb;
     int P = 1, T = 128, max_obs = 40;
-    int mcap = 1024, ncap = 3072, nt = 256, minb = 1, groups = 2, groups_cfg = 2;
+    int mcap = 1024, ncap = 8192, nt = 256, minb = 1, groups = 2, groups_cfg = 2;
+    int scap = 2048, tcap = 512;   // shared-memory sort / staging capacity per thread group (larger operations use global buffers)
     char* arena = nullptr;
     size_t arena_stride = 0;
     int grid = 0;
@@ -151,8 +152,8 @@ int alloc_arena(armour_handle* h) {
     h->arena_stride = arena_bytes(h->mcap, h->ncap);
     // two thread groups per CTA (joint chain || forces + FK) when their sort buffers fit in shared memory
     h->groups = h->groups_cfg;
-    int per_sm = h->groups == 2 ? reach_max_ctas_per_sm(h->nt, h->minb, 2, h->ncap) : 0;
-    if (per_sm < 1) { h->groups = 1; per_sm = reach_max_ctas_per_sm(h->nt, h->minb, 1, h->ncap); }
+    int per_sm = h->groups == 2 ? reach_max_ctas_per_sm(h->nt, h->minb, 2, h->scap, h->tcap) : 0;
+    if (per_sm < 1) { h->groups = 1; per_sm = reach_max_ctas_per_sm(h->nt, h->minb, 1, h->scap, h->tcap); }
     if (per_sm < 1) return fail(ARMOUR_E_CUDA, "reach_build_kernel does not fit on an SM with these capacities");
     const int n_work = h->P * h->T;
     h->grid = std::min(n_work, per_sm * h->sm_count);
@@ -167,7 +168,7 @@ int run_build(armour_handle* h) {   // kernels only; inputs already on the devic
     for (int attempt = 0; attempt < 4; attempt++) {
         CU(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
         CU(cudaEventRecord(h->ev[0], h->stream));
-        CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, n_work, std::min(h->grid, n_work), h->nt, h->minb, h->groups, h->stream));
+        CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, h->scap, h->tcap, n_work, std::min(h->grid, n_work), h->nt, h->minb, h->groups, h->stream));
         CU(cudaEventRecord(h->ev[1], h->stream));
         CU(launch_hyperplanes(tb, h->stream));
         CU(cudaEventRecord(h->ev[2], h->stream));
@@ -183,10 +184,10 @@ int run_build(armour_handle* h) {   // kernels only; inputs already on the devic
         if (err & (8 | 16)) return fail(ARMOUR_E_NUMERIC, "reach-set build: unexpected monomial structure (error word " + std::to_string(err) + ")");
         if (err & 4) return fail(ARMOUR_E_CAPACITY, "k-only monomial table capacity exceeded (UCAP/LCAP)");
         // monomial / entry capacity exceeded: grow and retry (documented in armour_b200.h)
-        if (err & 1) h->ncap = std::min(h->ncap * 2, 65535 & ~1023);
+        if ((err & 1) && h->ncap >= 65534) return fail(ARMOUR_E_CAPACITY, "an operation has more than 65535 candidate monomials");
+        if (err & 1) h->ncap = std::min(h->ncap * 2, 65534);
         if (err & 2) h->mcap *= 2;
-        if (h->ncap < 2 * h->mcap) h->ncap = std::min(2 * h->mcap, 65535 & ~1023);
-        if (reach_smem_bytes(h->ncap) > 200 * 1024) return fail(ARMOUR_E_CAPACITY, "candidate list does not fit in shared memory");
+        if (h->ncap < 2 * h->mcap) h->ncap = std::min(2 * h->mcap, 65534);
         int rc = alloc_arena(h);
         if (rc != ARMOUR_OK) return rc;
     }
@@ -263,7 +264,7 @@ void armour_default_config(armour_config* cfg) {
     cfg->simplify_threshold = 5e-4;
     cfg->max_obstacles = 40;
     cfg->max_monomials = 1024;
-    cfg->max_entries = 3072;
+    cfg->max_entries = 8192;
     cfg->threads_per_cta = 256;
     cfg->device = -1;
     cfg->batch = 1;
@@ -275,7 +276,7 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     if (cfg.num_time_steps <= 0 || (cfg.num_time_steps & 1)) return fail(ARMOUR_E_INVALID, "num_time_steps must be a positive even number");
     if (cfg.max_obstacles < 0) return fail(ARMOUR_E_INVALID, "max_obstacles < 0");
     if (cfg.max_monomials <= 0) cfg.max_monomials = 1024;
-    if (cfg.max_entries <= 0) cfg.max_entries = 3072;
+    if (cfg.max_entries <= 0) cfg.max_entries = 8192;
     if (cfg.threads_per_cta != 128 && cfg.threads_per_cta != 512) cfg.threads_per_cta = 256;
     if (cfg.batch <= 0) cfg.batch = 1;
     int ndev = 0;
@@ -288,13 +289,15 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) { delete h; return fail(ARMOUR_E_CUDA, "cudaGetDeviceProperties failed"); }
     h->sm_count = prop.multiProcessorCount;
     h->P = cfg.batch; h->T = cfg.num_time_steps; h->max_obs = cfg.max_obstacles;
-    h->mcap = cfg.max_monomials; h->ncap = std::min(cfg.max_entries, 65535 & ~1023); h->nt = cfg.threads_per_cta;
+    h->mcap = cfg.max_monomials; h->ncap = std::min(cfg.max_entries, 65534) & ~1; h->nt = cfg.threads_per_cta;
     // register budget: one plan is latency-bound (1 CTA/SM, all registers); a batch wants more resident CTAs
     h->minb = cfg.batch > 1 ? 2 : 1;
     if (const char* e = getenv("ARMOUR_TUNE_MINB")) h->minb = atoi(e);
     // one plan (latency): two thread groups per CTA; a batch (throughput): one group and two resident CTAs per SM
     h->groups_cfg = (cfg.batch > 1 || cfg.threads_per_cta == 128 || cfg.threads_per_cta == 512) ? 1 : 2;
     if (const char* e = getenv("ARMOUR_TUNE_GROUPS")) h->groups_cfg = atoi(e) == 2 ? 2 : 1;
+    if (const char* e = getenv("ARMOUR_TUNE_SCAP")) h->scap = std::max(256, atoi(e));
+    if (const char* e = getenv("ARMOUR_TUNE_TCAP")) h->tcap = std::max(64, atoi(e));
     kinova_model(h->model);
     *out = h;   // so that armour_destroy can clean up after a partial failure
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -604,7 +607,7 @@ int armour_pz_binary(armour_handle* h, int op,
     const int rcap = std::max(cap, 1), ncap = h->ncap;
     // layout of one staging buffer: A keys/coef/center/ind | B ... | R ... | out | tmp | err
     auto pz_bytes = [](int n, int d) { return (size_t)std::max(n, 1) * 8 * (1 + d) + 18 * 8; };
-    const size_t need = pz_bytes(a_n, da) + pz_bytes(b_n, db) + pz_bytes(rcap, 9) + 64 + (size_t)9 * ncap * 8 + 64;
+    const size_t need = pz_bytes(a_n, da) + pz_bytes(b_n, db) + pz_bytes(rcap, 9) + 64 + reach_gmem_bytes(ncap) + 64;
     if (need > h->bin_bytes) { if (h->bin_buf) cudaFree(h->bin_buf); h->bin_buf = nullptr; CU(cudaMalloc((void**)&h->bin_buf, need)); h->bin_bytes = need; }
     std::vector<char> host(need, 0);
     char* base = h->bin_buf;
@@ -632,10 +635,10 @@ int armour_pz_binary(armour_handle* h, int op,
     place(rcap, 9, nullptr, nullptr, nullptr, nullptr, fr);
     fr.n = 0; fr.cap = rcap;
     FlatOut* d_out = (FlatOut*)(base + off); const size_t out_off = off; off += 64;
-    double* d_tmp = (double*)(base + off); off += (size_t)9 * ncap * 8;
+    char* d_gmem = base + off; off += reach_gmem_bytes(ncap);
     int* d_err = (int*)(base + off); const size_t err_off = off; off += 64;
     CU(cudaMemcpyAsync(base, host.data(), need, cudaMemcpyHostToDevice, h->stream));
-    CU(launch_pz_binary(op, fa, fb, fr, d_out, d_tmp, ncap, h->cfg.simplify_threshold, d_err, h->stream));
+    CU(launch_pz_binary(op, fa, fb, fr, d_out, d_gmem, ncap, h->scap, h->tcap, h->cfg.simplify_threshold, d_err, h->stream));
     h->launches += 1;
     CU(cudaMemcpyAsync(host.data(), base, need, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));

@@ -63,32 +63,45 @@ struct Scratch {
     // Sort ping-pong buffers live in dynamic shared memory.  They are kept as shared-window addresses and
     // turned back into pointers with __cvta_shared_to_generic at each use, so that the compiler emits
     // LDS/STS instead of generic loads (a pointer loaded from a struct has no known address space).
-    unsigned skey_a[2];   // u64[ncap]
-    unsigned sidx_a[2];   // u16[ncap]
-    double* tmp;      // global [9][ncap]: per-key results before compaction (operations with more than TCAP candidates)
-    unsigned stmp_a;  // shared [3][TCAP]: the same for small operations (most of them): no L2 round trip
-    int ncap;
-    double thr;   // squared-domain threshold (Scratch::thr_sq)
+    // Operations with more than `scap` candidate monomials (a few per interval) use the same-shaped buffers in
+    // global memory instead: keeping the shared footprint small leaves the SM's L1 to the PZ working set.
+    unsigned skey_a[2];   // shared u64[scap]
+    unsigned sidx_a[2];   // shared u16[scap]
+    unsigned stmp_a;      // shared double[3][tcap]: per-key results before compaction (small operations)
+    u64* gkey[2];         // global u64[ncap]
+    u16* gidx[2];         // global u16[ncap]
+    double* tmp;          // global double[9][ncap]: per-key results before compaction (large operations)
+    int scap, tcap, ncap;
+    double thr;
     double thr_sq;    // largest x with RN(sqrt(x)) <= thr: "norm <= thr" is tested as "squared norm <= thr_sq", exactly
     int* gerr;        // global error word
-    double red[32 * 32];
+    double red[16 * 32];   // per-warp partial sums: up to 16 warps x 32 values
     int iscan[34];
     __device__ __forceinline__ u64* skey(int b) const { return (u64*)__cvta_shared_to_generic((size_t)skey_a[b]); }
     __device__ __forceinline__ u16* sidx(int b) const { return (u16*)__cvta_shared_to_generic((size_t)sidx_a[b]); }
-    static constexpr int TCAP = 1024;
     __device__ __forceinline__ double* stmp() const { return (double*)__cvta_shared_to_generic((size_t)stmp_a); }
-    __device__ void bind(unsigned char* smem, int ncap_) {
+    static __host__ __device__ size_t smem_bytes(int scap_, int tcap_) { return (size_t)scap_ * 20 + (size_t)3 * tcap_ * 8; }
+    static __host__ __device__ size_t gmem_bytes(int ncap_) { return (size_t)ncap_ * 20 + (size_t)9 * ncap_ * 8; }
+    __device__ void bind(unsigned char* smem, int scap_, int tcap_, char* gmem, int ncap_) {
         const unsigned base = (unsigned)__cvta_generic_to_shared(smem);
-        skey_a[0] = base; skey_a[1] = base + (unsigned)ncap_ * 8;
-        sidx_a[0] = base + (unsigned)ncap_ * 16; sidx_a[1] = base + (unsigned)ncap_ * 18;
-        stmp_a = base + (unsigned)ncap_ * 20;
-        ncap = ncap_;
+        skey_a[0] = base; skey_a[1] = base + (unsigned)scap_ * 8;
+        sidx_a[0] = base + (unsigned)scap_ * 16; sidx_a[1] = base + (unsigned)scap_ * 18;
+        stmp_a = base + (unsigned)scap_ * 20;
+        scap = scap_; tcap = tcap_; ncap = ncap_;
+        gkey[0] = (u64*)gmem; gkey[1] = gkey[0] + ncap_;
+        gidx[0] = (u16*)(gkey[1] + ncap_); gidx[1] = gidx[0] + ncap_;
+        tmp = (double*)(gmem + (size_t)ncap_ * 20);
     }
     // per-key staging buffer and its plane stride for an operation with n candidates and D output components
     __device__ __forceinline__ double* staging(int n, int D, int& stride) const {
-        if (D <= 3 && n <= TCAP) { stride = TCAP; return stmp(); }
+        if (D <= 3 && n <= tcap) { stride = tcap; return stmp(); }
         stride = ncap; return tmp;
     }
+};
+// sort buffers of an operation: shared (BIG = false) or global (BIG = true)
+template <bool BIG> struct Buf {
+    static __device__ __forceinline__ u64* key(const Scratch& S, int b) { return BIG ? S.gkey[b] : S.skey(b); }
+    static __device__ __forceinline__ u16* idx(const Scratch& S, int b) { return BIG ? S.gidx[b] : S.sidx(b); }
 };
 
 // exact n / d for n, d < 2^16 with one multiply: q = (n * M) >> 32, M = floor((2^32 - 1) / d) + 1
@@ -253,16 +266,16 @@ __device__ __forceinline__ double block_total(const Scratch& S, int k) {
 // Buffer 0 holds N entries laid out as sorted runs of width W (the last run may be shorter).
 // Returns the buffer that holds the fully sorted sequence.  All (key, idx) pairs are distinct, so
 // ordering by (key, idx) equals a stable sort by key of the list in origin order.
-template <int NT>
+template <int NT, bool BIG>
 __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 magicW) {
     int cur = 0;
     const FastDiv fd(magicW);
     int level = 0;
     for (int w = W; w < N; w <<= 1, level++) {
-        const u64* ki = S.skey(cur);
-        const u16* ii = S.sidx(cur);
-        u64* ko = S.skey(cur ^ 1);
-        u16* io = S.sidx(cur ^ 1);
+        const u64* ki = Buf<BIG>::key(S, cur);
+        const u16* ii = Buf<BIG>::idx(S, cur);
+        u64* ko = Buf<BIG>::key(S, cur ^ 1);
+        u16* io = Buf<BIG>::idx(S, cur ^ 1);
         // rank of each element among its sibling run (binary search; key and index are fetched together so the
         // tie-break does not add a dependent shared-memory round trip)
         for (int g = gtid<NT>(); g < N; g += NT) {
@@ -329,11 +342,11 @@ struct ScalarEpilogue {
 };
 
 // Barriers: one after the segment pass, one inside block_scan_sum, one at the end.
-template <int NT, int DOUT, class Op, class Epi>
+template <int NT, int DOUT, bool BIG, class Op, class Epi>
 __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, PZ<DOUT>& dst, const Epi& epi) {
-    const u64* key = S.skey(buf);
-    const u16* idx = S.sidx(buf);
-    u16* flag = S.sidx(buf ^ 1);
+    const u64* key = Buf<BIG>::key(S, buf);
+    const u16* idx = Buf<BIG>::idx(S, buf);
+    u16* flag = Buf<BIG>::idx(S, buf ^ 1);
     int ncap;
     double* tmp = S.staging(N, DOUT, ncap);
     double red[2 * DOUT];
@@ -393,10 +406,10 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
 
 // elementwise variant: no sort, keys are those of `src` in order; op computes out from index i.
 //   bool Op::finish(int i, double* out, double* drop)
-template <int NT, int DOUT, class Op, class Epi>
+template <int NT, int DOUT, bool BIG, class Op, class Epi>
 __device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* src_keys, Op& op, PZ<DOUT>& dst, const Epi& epi) {
-    u16* flag = S.sidx(0);
-    u64* kcopy = S.skey(0);
+    u16* flag = Buf<BIG>::idx(S, 0);
+    u64* kcopy = Buf<BIG>::key(S, 0);
     double red[2 * DOUT];
 #pragma unroll
     for (int c = 0; c < 2 * DOUT; c++) red[c] = 0.0;
@@ -509,11 +522,11 @@ struct MulOp {
 };
 
 // fill the sort buffer for a product: rows over the smaller operand, width W = max(na, nb)
-template <int NT>
+template <int NT, bool BIG>
 __device__ __forceinline__ int fill_product_keys(Scratch& S, const u64* ka, int na, u64 magic_a, const u64* kb, int nb, u64 magic_b, int& W, u64& magicW) {
     const int N = na + nb + na * nb;
-    u64* key = S.skey(0);
-    u16* idx = S.sidx(0);
+    u64* key = Buf<BIG>::key(S, 0);
+    u16* idx = Buf<BIG>::idx(S, 0);
     if (na == 0 || nb == 0) {   // single sorted run
         W = N > 0 ? N : 1;
         magicW = na ? magic_a : magic_b;
@@ -586,19 +599,24 @@ struct MulEpi {
     }
 };
 
-template <int NT, int DA, int DB, int DO>
-__device__ __noinline__ void pz_mul(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, const PZ<DB>& B) {
+template <int NT, int DA, int DB, int DO, bool BIG>
+__device__ __forceinline__ void pz_mul_impl(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, const PZ<DB>& B, int N) {
     const int na = A.n, nb = B.n;
-    int N = na + nb + na * nb;
-    if (N > S.ncap || N > 65535) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
     int W = 1;
     u64 magicW = 0;
-    if (N > 0) fill_product_keys<NT>(S, A.keys, na, A.divM, B.keys, nb, B.divM, W, magicW);
+    if (N > 0) fill_product_keys<NT, BIG>(S, A.keys, na, A.divM, B.keys, nb, B.divM, W, magicW);
     MulOp<DA, DB, DO> op(A, B, S.thr_sq);
     gsync<NT>();
     phase_mark(PH_FILL);
-    const int buf = merge_sort_runs<NT>(S, N, W, magicW);
-    reduce_emit<NT, DO, MulOp<DA, DB, DO>, MulEpi<DA, DB, DO>>(S, buf, N, op, dst, MulEpi<DA, DB, DO>{A, B});
+    const int buf = merge_sort_runs<NT, BIG>(S, N, W, magicW);
+    reduce_emit<NT, DO, BIG, MulOp<DA, DB, DO>, MulEpi<DA, DB, DO>>(S, buf, N, op, dst, MulEpi<DA, DB, DO>{A, B});
+}
+template <int NT, int DA, int DB, int DO>
+__device__ __noinline__ void pz_mul(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, const PZ<DB>& B) {
+    int N = A.n + B.n + A.n * B.n;
+    if (N > S.ncap || N > 65535) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
+    if (N <= S.scap) pz_mul_impl<NT, DA, DB, DO, false>(S, dst, A, B, N);
+    else pz_mul_impl<NT, DA, DB, DO, true>(S, dst, A, B, N);
 }
 
 // =============================================================================================
@@ -692,13 +710,11 @@ struct MergeEpi {
     }
 };
 // dst = A (+/-) B through views.  Centre and radii of a VIEW_PLACE / VIEW_EXTRACT source are mapped the same way.
-template <int NT, int DA, int DB, int DO>
-__device__ __noinline__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA> A, const View<DB> B, bool negb) {
+template <int NT, int DA, int DB, int DO, bool BIG>
+__device__ __forceinline__ void pz_merge_impl(Scratch& S, PZ<DO>& dst, const View<DA>& A, const View<DB>& B, bool negb, int N) {
     const int na = A.p->n, nb = B.p->n;
-    int N = na + nb;
-    if (N > S.ncap) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
-    u64* key = S.skey(0);
-    u16* idx = S.sidx(0);
+    u64* key = Buf<BIG>::key(S, 0);
+    u16* idx = Buf<BIG>::idx(S, 0);
     int W = 1;
     u64 magicW = 0;
     if (N > 0) {
@@ -717,8 +733,15 @@ __device__ __noinline__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA> A,
     MergeOp<DA, DB, DO> op{A, B, na, negb, S.thr_sq};
     gsync<NT>();
     phase_mark(PH_FILL);
-    const int buf = merge_sort_runs<NT>(S, N, W, magicW);
-    reduce_emit<NT, DO, MergeOp<DA, DB, DO>, MergeEpi<DA, DB>>(S, buf, N, op, dst, MergeEpi<DA, DB>{A, B, negb});
+    const int buf = merge_sort_runs<NT, BIG>(S, N, W, magicW);
+    reduce_emit<NT, DO, BIG, MergeOp<DA, DB, DO>, MergeEpi<DA, DB>>(S, buf, N, op, dst, MergeEpi<DA, DB>{A, B, negb});
+}
+template <int NT, int DA, int DB, int DO>
+__device__ __noinline__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA> A, const View<DB> B, bool negb) {
+    int N = A.p->n + B.p->n;
+    if (N > S.ncap || N > 65535) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
+    if (N <= S.scap) pz_merge_impl<NT, DA, DB, DO, false>(S, dst, A, B, negb, N);
+    else pz_merge_impl<NT, DA, DB, DO, true>(S, dst, A, B, negb, N);
 }
 template <int NT> __device__ __forceinline__ void pz_add3(Scratch& S, PZ<3>& dst, const PZ<3>& a, const PZ<3>& b) { pz_merge<NT, 3, 3, 3>(S, dst, view(a), view(b), false); }
 // dst = a with the scalar PZ s added into row `row`   (addOneDimPZ)
@@ -809,19 +832,24 @@ struct CrossPPEpi {
         r0 = r[0]; r1 = r[1];
     }
 };
-template <int NT>
-__device__ __noinline__ void pz_cross_pp(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B) {
+template <int NT, bool BIG>
+__device__ __forceinline__ void pz_cross_pp_impl(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B, int N) {
     const int na = A.n, nb = B.n;
-    int N = na + nb + na * nb;
-    if (N > S.ncap || N > 65535) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
     int W = 1;
     u64 magicW = 0;
-    if (N > 0) fill_product_keys<NT>(S, A.keys, na, A.divM, B.keys, nb, B.divM, W, magicW);
+    if (N > 0) fill_product_keys<NT, BIG>(S, A.keys, na, A.divM, B.keys, nb, B.divM, W, magicW);
     CrossPPOp op(A, B, S.thr_sq);
     gsync<NT>();
     phase_mark(PH_FILL);
-    const int buf = merge_sort_runs<NT>(S, N, W, magicW);
-    reduce_emit<NT, 3, CrossPPOp, CrossPPEpi>(S, buf, N, op, dst, CrossPPEpi{A, B});
+    const int buf = merge_sort_runs<NT, BIG>(S, N, W, magicW);
+    reduce_emit<NT, 3, BIG, CrossPPOp, CrossPPEpi>(S, buf, N, op, dst, CrossPPEpi{A, B});
+}
+template <int NT>
+__device__ __noinline__ void pz_cross_pp(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B) {
+    int N = A.n + B.n + A.n * B.n;
+    if (N > S.ncap || N > 65535) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
+    if (N <= S.scap) pz_cross_pp_impl<NT, false>(S, dst, A, B, N);
+    else pz_cross_pp_impl<NT, true>(S, dst, A, B, N);
 }
 
 // =============================================================================================
@@ -881,7 +909,8 @@ struct CrossConstEpi {
 template <int NT>
 __device__ __noinline__ void pz_cross_const(Scratch& S, PZ<3>& dst, const PZ<3>& Z, const double* kvec, bool const_first) {
     CrossConstOp op{Z, {kvec[0], kvec[1], kvec[2]}, const_first, S.thr_sq};
-    elementwise_emit<NT, 3, CrossConstOp, CrossConstEpi>(S, Z.n, Z.keys, op, dst, CrossConstEpi{Z, {kvec[0], kvec[1], kvec[2]}, const_first});
+    if (Z.n <= S.scap) elementwise_emit<NT, 3, false, CrossConstOp, CrossConstEpi>(S, Z.n, Z.keys, op, dst, CrossConstEpi{Z, {kvec[0], kvec[1], kvec[2]}, const_first});
+    else elementwise_emit<NT, 3, true, CrossConstOp, CrossConstEpi>(S, Z.n, Z.keys, op, dst, CrossConstEpi{Z, {kvec[0], kvec[1], kvec[2]}, const_first});
 }
 
 // dst(3x1) = M * v with M a monomial-free 3x3 PZ (centre Mc, radii Mi[2]) — I_arr(i) * w
@@ -926,7 +955,8 @@ __device__ __noinline__ void pz_const_left(Scratch& S, PZ<3>& dst, const double*
     ConstLeftOp op{V, {0}, scalar, S.thr_sq};
     const int DM = scalar ? 1 : 9;
     for (int c = 0; c < DM; c++) op.M[c] = Mc[c];
-    elementwise_emit<NT, 3, ConstLeftOp, ConstLeftEpi>(S, V.n, V.keys, op, dst, ConstLeftEpi{V, Mc, Mi0, Mi1, scalar});
+    if (V.n <= S.scap) elementwise_emit<NT, 3, false, ConstLeftOp, ConstLeftEpi>(S, V.n, V.keys, op, dst, ConstLeftEpi{V, Mc, Mi0, Mi1, scalar});
+    else elementwise_emit<NT, 3, true, ConstLeftOp, ConstLeftEpi>(S, V.n, V.keys, op, dst, ConstLeftEpi{V, Mc, Mi0, Mi1, scalar});
 }
 
 // dst(3x1) = R * p with R a 3x3 PZ and p a constant vector — FK_R * P   (KPR/Dynamics.cu:76)
@@ -956,7 +986,8 @@ struct ConstRightEpi {
 template <int NT>
 __device__ __noinline__ void pz_const_right(Scratch& S, PZ<3>& dst, const PZ<9>& R, const double* pvec) {
     ConstRightOp op{R, {pvec[0], pvec[1], pvec[2]}, S.thr_sq};
-    elementwise_emit<NT, 3, ConstRightOp, ConstRightEpi>(S, R.n, R.keys, op, dst, ConstRightEpi{R, {pvec[0], pvec[1], pvec[2]}});
+    if (R.n <= S.scap) elementwise_emit<NT, 3, false, ConstRightOp, ConstRightEpi>(S, R.n, R.keys, op, dst, ConstRightEpi{R, {pvec[0], pvec[1], pvec[2]}});
+    else elementwise_emit<NT, 3, true, ConstRightOp, ConstRightEpi>(S, R.n, R.keys, op, dst, ConstRightEpi{R, {pvec[0], pvec[1], pvec[2]}});
 }
 
 // reset to a monomial-free PZ with centre c (all threads call; thread 0 writes)

@@ -18,8 +18,6 @@ namespace armour {
 
 __constant__ RobotModel c_robot;
 
-// dynamic shared memory of one thread group: sort ping-pong (u64 + u16, twice) + per-key staging (Scratch::TCAP)
-__host__ __device__ inline size_t reach_smem_bytes_dev(int ncap) { return (size_t)ncap * 20 + (size_t)3 * 1024 * 8; }
 
 // ---------------------------------------------------------------------------------------------
 // Directed-rounding interval arithmetic (replaces boost::numeric::interval with
@@ -264,7 +262,7 @@ __device__ void make_poly_zono_joint(const Tables& tb, int prob, int s, int i, P
 template <int NT>
 __device__ __noinline__ void export_link(Scratch& S, const Tables& tb, size_t rec, PZ<3>& L) {
     const int n = L.n;
-    u16* flag = S.sidx(0);
+    u16* flag = n <= S.scap ? S.sidx(0) : S.gidx[0];
     double red[3] = {0, 0, 0};
     double* gens = tb.gens + rec * 18;
     for (int i = gtid<NT>(); i < 18; i += NT) gens[i] = 0.0;
@@ -316,7 +314,7 @@ __device__ __noinline__ void export_link(Scratch& S, const Tables& tb, size_t re
 template <int NT>
 __device__ __noinline__ void export_torque(Scratch& S, const Tables& tb, size_t rec, PZ<1>& U) {
     const int n = U.n;
-    u16* flag = S.sidx(0);
+    u16* flag = n <= S.scap ? S.sidx(0) : S.gidx[0];
     double red[1] = {0};
     for (int i = gtid<NT>(); i < n; i += NT) {
         const u64 k = U.keys[i];
@@ -369,7 +367,7 @@ size_t arena_bytes(int mcap, int ncap) {
     b += (size_t)(2 * NJ + 1) * SMALL_CAP * (8 + 9 * 8);          // R, R_t
     b += (size_t)5 * NJ * SMALL_CAP * 16;                         // qd, qda, qdda, cos, sin
     b += (size_t)NJ * mcap * 16;                                  // u
-    b += (size_t)2 * 9 * ncap * 8;                                // per-group staging for large operations
+    b += 2 * Scratch::gmem_bytes(ncap);                           // per-group sort / staging buffers of large operations
     return (b + 255) & ~(size_t)255;
 }
 
@@ -571,7 +569,7 @@ __device__ void moment_joint(Scratch& S, Slots& Z, PZ<3>* T, int i) {
 // GROUPS == 2: see angular_joint / linacc_joint / side_joint / moment_joint above: the two groups run side by side and
 // hand PZs over through shared-memory counters; the critical path is roughly half of the 280 operations.
 template <int NT, int MINB, int GROUPS>
-__global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables tb, char* arena, size_t arena_stride, int mcap, int ncap, int n_work) {
+__global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables tb, char* arena, size_t arena_stride, int mcap, int ncap, int scap, int tcap, int n_work) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Scratch SS[GROUPS];
     __shared__ Slots Z;
@@ -597,9 +595,8 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
         }
         const double thr_sq = squared_threshold(tb.thr);
         for (int k = 0; k < GROUPS; k++) {
-            SS[k].bind(smem_raw + (size_t)k * reach_smem_bytes_dev(ncap), ncap);
+            SS[k].bind(smem_raw + (size_t)k * Scratch::smem_bytes(scap, tcap), scap, tcap, g + (size_t)k * Scratch::gmem_bytes(ncap), ncap);
             SS[k].thr = tb.thr; SS[k].thr_sq = thr_sq; SS[k].gerr = tb.err;
-            SS[k].tmp = (double*)g + (size_t)k * 9 * ncap;
         }
     }
     __syncthreads();
@@ -760,15 +757,15 @@ __device__ void store_flat(FlatPZ& f, const PZ<D>& z) {
     if (threadIdx.x == 0) { f.n = z.n; f.dim = D; for (int c = 0; c < D; c++) { f.center[c] = z.center[c]; f.ind[c] = z.ind[0][c]; } }
 }
 template <int NT>
-__global__ void __launch_bounds__(NT) pz_binary_kernel(int op, FlatPZ a, FlatPZ b, FlatPZ r, FlatOut* out, double* tmp, int ncap, double thr, int* err) {
+__global__ void __launch_bounds__(NT) pz_binary_kernel(int op, FlatPZ a, FlatPZ b, FlatPZ r, FlatOut* out, char* gmem, int ncap, int scap, int tcap, double thr, int* err) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Scratch S;
     __shared__ PZ<1> a1, b1, r1;
     __shared__ PZ<3> a3, b3, r3;
     __shared__ PZ<9> a9, b9, r9;
     if (threadIdx.x == 0) {
-        S.bind(smem_raw, ncap);
-        S.thr = thr; S.thr_sq = squared_threshold(thr); S.gerr = err; S.tmp = tmp;
+        S.bind(smem_raw, scap, tcap, gmem, ncap);
+        S.thr = thr; S.thr_sq = squared_threshold(thr); S.gerr = err;
         r1.cap = r3.cap = r9.cap = r.cap; r1.keys = r3.keys = r9.keys = r.keys; r1.coef = r3.coef = r9.coef = r.coef;
     }
     __syncthreads();
@@ -790,10 +787,11 @@ __global__ void __launch_bounds__(NT) pz_binary_kernel(int op, FlatPZ a, FlatPZ 
 // ---- host-side launch helpers -----------------------------------------------------------------
 cudaError_t upload_robot_model(const RobotModel& rm) { return cudaMemcpyToSymbol(c_robot, &rm, sizeof(RobotModel)); }
 
-size_t reach_smem_bytes(int ncap) { return reach_smem_bytes_dev(ncap); }
+size_t reach_smem_bytes(int scap, int tcap) { return Scratch::smem_bytes(scap, tcap); }
+size_t reach_gmem_bytes(int ncap) { return Scratch::gmem_bytes(ncap); }
 
 // kernel variants: (threads per group, CTAs per SM the register allocation is bounded for, thread groups per CTA)
-typedef void (*ReachKernel)(Tables, char*, size_t, int, int, int);
+typedef void (*ReachKernel)(Tables, char*, size_t, int, int, int, int, int);
 static ReachKernel pick_reach_kernel(int nt, int minb, int groups) {
     if (groups == 2) return reach_build_kernel<256, 1, 2>;
     if (nt == 128) return minb >= 4 ? reach_build_kernel<128, 4, 1> : reach_build_kernel<128, 2, 1>;
@@ -801,20 +799,20 @@ static ReachKernel pick_reach_kernel(int nt, int minb, int groups) {
     return minb >= 2 ? reach_build_kernel<256, 2, 1> : reach_build_kernel<256, 1, 1>;
 }
 static int reach_threads(int nt, int groups) { return groups == 2 ? 512 : nt == 128 ? 128 : nt == 512 ? 512 : 256; }
-cudaError_t launch_reach_build(const Tables& tb, char* arena, size_t arena_stride, int mcap, int ncap, int n_work, int grid, int nt, int minb, int groups, cudaStream_t stream) {
-    const size_t smem = reach_smem_bytes(ncap) * (groups == 2 ? 2 : 1);
+cudaError_t launch_reach_build(const Tables& tb, char* arena, size_t arena_stride, int mcap, int ncap, int scap, int tcap, int n_work, int grid, int nt, int minb, int groups, cudaStream_t stream) {
+    const size_t smem = reach_smem_bytes(scap, tcap) * (groups == 2 ? 2 : 1);
     ReachKernel k = pick_reach_kernel(nt, minb, groups);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<grid, reach_threads(nt, groups), smem, stream>>>(tb, arena, arena_stride, mcap, ncap, n_work);
+    k<<<grid, reach_threads(nt, groups), smem, stream>>>(tb, arena, arena_stride, mcap, ncap, scap, tcap, n_work);
     return cudaGetLastError();
 }
 
-cudaError_t launch_pz_binary(int op, const FlatPZ& a, const FlatPZ& b, const FlatPZ& r, FlatOut* out, double* tmp, int ncap, double thr, int* err, cudaStream_t stream) {
-    const size_t smem = reach_smem_bytes(ncap);
+cudaError_t launch_pz_binary(int op, const FlatPZ& a, const FlatPZ& b, const FlatPZ& r, FlatOut* out, char* gmem, int ncap, int scap, int tcap, double thr, int* err, cudaStream_t stream) {
+    const size_t smem = reach_smem_bytes(scap, tcap);
     cudaError_t e = cudaFuncSetAttribute(pz_binary_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    pz_binary_kernel<256><<<1, 256, smem, stream>>>(op, a, b, r, out, tmp, ncap, thr, err);
+    pz_binary_kernel<256><<<1, 256, smem, stream>>>(op, a, b, r, out, gmem, ncap, scap, tcap, thr, err);
     return cudaGetLastError();
 }
 
@@ -835,9 +833,9 @@ void read_phase_cycles(unsigned long long* cycles, unsigned long long* calls, bo
 }
 
 // resident CTAs per SM for a variant; 0 when it does not fit (e.g. two groups with large sort buffers)
-int reach_max_ctas_per_sm(int nt, int minb, int groups, int ncap) {
+int reach_max_ctas_per_sm(int nt, int minb, int groups, int scap, int tcap) {
     int n = 0;
-    const size_t smem = reach_smem_bytes(ncap) * (groups == 2 ? 2 : 1);
+    const size_t smem = reach_smem_bytes(scap, tcap) * (groups == 2 ? 2 : 1);
     ReachKernel k = pick_reach_kernel(nt, minb, groups);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, reach_threads(nt, groups), smem) != cudaSuccess) { cudaGetLastError(); return 0; }

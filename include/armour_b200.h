@@ -54,7 +54,8 @@ typedef struct armour_config {
     double simplify_threshold;  /* SIMPLIFY_THRESHOLD, default 5e-4                     (Parameters.h:10) */
     int max_obstacles;          /* MAX_OBSTACLE_NUM, default 40                         (Parameters.h:26) */
     int max_monomials;          /* capacity of one PZ's monomial list; default 1024 (0 = default)  */
-    int max_entries;            /* capacity of one sort (candidate monomials of one op); default 3072 (0 = default) */
+    int max_entries;            /* capacity of one sort (candidate monomials of one op); default 8192, at most 65535 (0 = default).
+                                 * Operations up to 2048 candidates sort in shared memory, larger ones in global memory. */
     int threads_per_cta;        /* 128, 256 or 512; default 256 (0 = default)            */
     int device;                 /* CUDA device ordinal; -1 = current device              */
     int batch;                  /* problems one handle builds per armour_build_batch call; default 1 */
