@@ -22,7 +22,7 @@ PZ_OPS = {"mul": 0, "add": 1, "sub": 2, "cross": 3}
 
 EXPORTS = [
     "armour_default_config", "armour_create", "armour_destroy", "armour_last_error", "armour_build", "armour_build_batch",
-    "armour_select_problem", "armour_get_nlp_info", "armour_get_bounds_info", "armour_get_starting_point", "armour_eval_f",
+    "armour_select_problem", "armour_build_armtd", "armour_get_nlp_info", "armour_get_bounds_info", "armour_get_starting_point", "armour_eval_f",
     "armour_eval_grad_f", "armour_eval_g", "armour_eval_jac_g", "armour_eval_g_jac", "armour_jac_structure", "armour_release_host_buffers", "armour_check_feasible",
     "armour_get_torque_radius", "armour_get_link_generators", "armour_get_link_sliced_center", "armour_get_hyperplanes",
     "armour_get_taylor_remainders", "armour_get_pz", "armour_pz_binary", "armour_last_build_ms", "armour_last_eval_ms",
@@ -168,6 +168,15 @@ class Planner:
         assert obs.size % 12 == 0
         self.n_obs = obs.size // 12
         self._ck(self.L.armour_build(self.h, _dp(_vec(q0, 7)), _dp(_vec(qd0, 7)), _dp(_vec(qdd0, 7)), _dp(obs) if obs.size else None, C.c_int(self.n_obs)))
+        return self.last_build_ms()[0]
+
+    def build_armtd(self, q0, qd0, jrs, k_range, obstacles):
+        """ARMTD comparison planner: jrs[6, 7, T] offline JRS tables, k_range[7]."""
+        obs = _vec(obstacles)
+        self.n_obs = obs.size // 12
+        self.k_range = np.array(k_range, dtype=float)
+        self._ck(self.L.armour_build_armtd(self.h, _dp(_vec(q0, 7)), _dp(_vec(qd0, 7)), _dp(_vec(jrs, 6 * 7 * self.T)), _dp(_vec(k_range, 7)),
+                                           _dp(obs) if obs.size else None, C.c_int(self.n_obs)))
         return self.last_build_ms()[0]
 
     def build_batch(self, q0, qd0, qdd0, obstacles, n_obs):

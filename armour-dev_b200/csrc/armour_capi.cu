@@ -117,6 +117,8 @@ struct armour_handle {
     size_t arena_stride = 0;
     int grid = 0;
     // device buffers
+    double *d_jrs = nullptr, *d_krange = nullptr, *h_jrs = nullptr, *h_krange = nullptr;
+    int mode = 0;   // 0 ARMOUR, 1 ARMTD comparison planner
     double *d_state = nullptr, *d_obs = nullptr, *d_x = nullptr, *d_g = nullptr, *d_jac = nullptr, *d_link_center = nullptr;
     int* d_err = nullptr;
     // pinned host buffers
@@ -144,7 +146,7 @@ struct armour_handle {
 
 namespace {
 
-int m_of(const armour_handle* h) { return NF * h->T + NJ * h->T * h->n_obs + NF * 4; }
+int m_of(const armour_handle* h) { return (h->mode == 0 ? NF * h->T : 0) + NJ * h->T * h->n_obs + NF * 4; }
 
 void free_arena(armour_handle* h) { if (h->arena) cudaFree(h->arena); h->arena = nullptr; }
 int alloc_arena(armour_handle* h) {
@@ -164,7 +166,7 @@ int alloc_arena(armour_handle* h) {
 int run_build(armour_handle* h) {   // kernels only; inputs already on the device
     const int n_work = h->count * h->T;
     Tables tb = h->tb;
-    tb.P = h->count; tb.n_obs = h->n_obs;
+    tb.P = h->count; tb.n_obs = h->n_obs; tb.mode = h->mode; tb.jrs = h->d_jrs; tb.k_range_in = h->d_krange;
     for (int attempt = 0; attempt < 4; attempt++) {
         CU(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
         CU(cudaEventRecord(h->ev[0], h->stream));
@@ -200,7 +202,7 @@ int run_eval(armour_handle* h, const double* x, bool to_host) {
     if (!h->built) return fail(ARMOUR_E_STATE, "eval before build");
     if (x) memcpy(h->h_x, x, sizeof(double) * NF);
     Tables tb = h->tb;
-    tb.P = h->count; tb.n_obs = h->n_obs;
+    tb.P = h->count; tb.n_obs = h->n_obs; tb.mode = h->mode; tb.jrs = h->d_jrs; tb.k_range_in = h->d_krange;
     CU(cudaEventRecord(h->ev[3], h->stream));
     CU(launch_constraint_eval(tb, h->sel, h->h_x, to_host ? h->h_g : h->d_g, to_host ? h->h_jac : h->d_jac, h->d_link_center, h->stream));
     CU(cudaEventRecord(h->ev[4], h->stream));
@@ -310,6 +312,8 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     for (int i = 0; i < NF; i++) tb.k_range[i] = cfg.k_range[i];
     tb.mass_unc = cfg.mass_uncertainty; tb.inertia_unc = cfg.inertia_uncertainty; tb.thr = cfg.simplify_threshold;
     CU(dalloc(&h->d_state, P * 21)); CU(dalloc(&h->d_obs, P * O * 12));
+    CU(dalloc(&h->d_jrs, (size_t)6 * NF * T)); CU(dalloc(&h->d_krange, (size_t)NF));
+    CU(cudaMallocHost((void**)&h->h_jrs, sizeof(double) * 6 * NF * T)); CU(cudaMallocHost((void**)&h->h_krange, sizeof(double) * NF));
     tb.state = h->d_state; tb.obstacles = h->d_obs;
     CU(dalloc(&tb.traj, P * T * TRAJ_TABLES * NJ));
     CU(dalloc(&tb.cos_rem, P * NJ * T * 2)); CU(dalloc(&tb.sin_rem, P * NJ * T * 2));
@@ -337,10 +341,10 @@ void armour_destroy(armour_handle* h) {
     for (auto& p : h->pinned) cudaHostUnregister((void*)p.host);
     cudaGetLastError();
     Tables& tb = h->tb;
-    void* dev[] = {h->d_state, h->d_obs, tb.traj, tb.cos_rem, tb.sin_rem, tb.u_n, tb.u_keys, tb.u_coef, tb.u_center, tb.u_ind, tb.dist_rad, tb.torque_radius,
+    void* dev[] = {h->d_jrs, h->d_krange, h->d_state, h->d_obs, tb.traj, tb.cos_rem, tb.sin_rem, tb.u_n, tb.u_keys, tb.u_coef, tb.u_center, tb.u_ind, tb.dist_rad, tb.torque_radius,
                    tb.l_n, tb.l_keys, tb.l_coef, tb.l_center, tb.l_ind, tb.gens, tb.A, tb.d, tb.delta, h->d_err, h->d_x, h->d_g, h->d_jac, h->d_link_center, h->arena, h->bin_buf};
     for (void* p : dev) if (p) cudaFree(p);
-    void* pinned[] = {h->h_state, h->h_obs, h->h_x, h->h_g, h->h_jac, h->h_torque_radius, h->h_err};
+    void* pinned[] = {h->h_jrs, h->h_krange, h->h_state, h->h_obs, h->h_x, h->h_g, h->h_jac, h->h_torque_radius, h->h_err};
     for (void* p : pinned) if (p) cudaFreeHost(p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -356,7 +360,7 @@ int armour_upload_problems(armour_handle* h, int count, const double* q0, const 
     for (int p = 0; p < count; p++)
         for (int i = 0; i < NF; i++) { h->h_state[p * 21 + i] = q0[p * NF + i]; h->h_state[p * 21 + 7 + i] = qd0[p * NF + i]; h->h_state[p * 21 + 14 + i] = qdd0[p * NF + i]; }
     if (n_obs > 0) memcpy(h->h_obs, obstacles, sizeof(double) * (size_t)count * n_obs * 12);
-    h->count = count; h->n_obs = n_obs; h->sel = 0; h->built = false; h->have_eval = false; h->mirror_valid = false;
+    h->count = count; h->n_obs = n_obs; h->sel = 0; h->built = false; h->have_eval = false; h->mirror_valid = false; h->mode = 0;
     CU(cudaMemcpyAsync(h->d_state, h->h_state, sizeof(double) * (size_t)count * 21, cudaMemcpyHostToDevice, h->stream));
     if (n_obs > 0) CU(cudaMemcpyAsync(h->d_obs, h->h_obs, sizeof(double) * (size_t)count * n_obs * 12, cudaMemcpyHostToDevice, h->stream));
     return ARMOUR_OK;
@@ -373,6 +377,18 @@ int armour_build_batch(armour_handle* h, int count, const double* q0, const doub
 }
 int armour_build(armour_handle* h, const double* q0, const double* qd0, const double* qdd0, const double* obstacles, int n_obs) {
     return armour_build_batch(h, 1, q0, qd0, qdd0, obstacles, n_obs);
+}
+int armour_build_armtd(armour_handle* h, const double* q0, const double* qd0, const double* jrs, const double* k_range, const double* obstacles, int n_obs) {
+    if (!h || !q0 || !qd0 || !jrs || !k_range) return fail(ARMOUR_E_INVALID, "null argument");
+    const double zero[NF] = {0, 0, 0, 0, 0, 0, 0};
+    int rc = armour_upload_problems(h, 1, q0, qd0, zero, obstacles, n_obs);
+    if (rc != ARMOUR_OK) return rc;
+    h->mode = 1;
+    memcpy(h->h_jrs, jrs, sizeof(double) * 6 * NF * h->T);
+    memcpy(h->h_krange, k_range, sizeof(double) * NF);
+    CU(cudaMemcpyAsync(h->d_jrs, h->h_jrs, sizeof(double) * 6 * NF * h->T, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_krange, h->h_krange, sizeof(double) * NF, cudaMemcpyHostToDevice, h->stream));
+    return run_build(h);
 }
 int armour_select_problem(armour_handle* h, int p) {
     if (!h || !h->built) return fail(ARMOUR_E_STATE, "select before build");
@@ -394,9 +410,11 @@ int armour_get_bounds_info(armour_handle* h, double* x_l, double* x_u, double* g
     const double* tr = h->h_torque_radius + (size_t)h->sel * T * NF;
     for (int i = 0; i < NF; i++) { x_l[i] = -1.0; x_u[i] = 1.0; }
     int offset = 0;
-    for (int i = 0; i < T; i++)
-        for (int j = 0; j < NF; j++) { g_l[i * NF + j] = -rm.torque[j] + tr[i * NF + j]; g_u[i * NF + j] = rm.torque[j] - tr[i * NF + j]; }
-    offset += NF * T;
+    if (h->mode == 0) {
+        for (int i = 0; i < T; i++)
+            for (int j = 0; j < NF; j++) { g_l[i * NF + j] = -rm.torque[j] + tr[i * NF + j]; g_u[i * NF + j] = rm.torque[j] - tr[i * NF + j]; }
+        offset += NF * T;
+    }
     for (int i = offset; i < offset + T * NJ * h->n_obs; i++) { g_l[i] = -1e19; g_u[i] = 0; }
     offset += T * NJ * h->n_obs;
     for (int rep = 0; rep < 2; rep++) { for (int i = 0; i < NF; i++) { g_l[offset + i] = rm.state_lb[i] + rm.qe; g_u[offset + i] = rm.state_ub[i] - rm.qe; } offset += NF; }
@@ -413,7 +431,9 @@ int armour_eval_f(armour_handle* h, const double* q_des, double t_plan, const do
     if (h->count < 1) return fail(ARMOUR_E_STATE, "no problem");
     const double* st = h->h_state + (size_t)h->sel * 21;
     double qp[NF];
-    for (int i = 0; i < NF; i++) qp[i] = q_des_host(st[i], st[7 + i], st[14 + i], h->cfg.k_range[i] * x[i], t_plan);
+    for (int i = 0; i < NF; i++)
+        qp[i] = h->mode == 0 ? q_des_host(st[i], st[7 + i], st[14 + i], h->cfg.k_range[i] * x[i], t_plan)
+                             : st[i] + st[7 + i] * 0.5 + h->h_krange[i] * x[i] * 0.125;   // KPA/NLPclass.cu:197
     double v = pow(wrap_to_pi(q_des[0] - qp[0]), 2) + pow(wrap_to_pi(q_des[2] - qp[2]), 2) + pow(wrap_to_pi(q_des[4] - qp[4]), 2) + pow(wrap_to_pi(q_des[6] - qp[6]), 2) +
                pow(q_des[1] - qp[1], 2) + pow(q_des[3] - qp[3], 2) + pow(q_des[5] - qp[5], 2);
     *obj_value = v * COST_SCALE;
@@ -424,8 +444,9 @@ int armour_eval_grad_f(armour_handle* h, const double* q_des, double t_plan, con
     if (h->count < 1) return fail(ARMOUR_E_STATE, "no problem");
     const double* st = h->h_state + (size_t)h->sel * 21;
     for (int i = 0; i < NF; i++) {
-        const double qp = q_des_host(st[i], st[7 + i], st[14 + i], h->cfg.k_range[i] * x[i], t_plan);
-        const double dk = pow(t_plan, 3) * (6 * pow(t_plan, 2) - 15 * t_plan + 10) * h->cfg.k_range[i];
+        const double qp = h->mode == 0 ? q_des_host(st[i], st[7 + i], st[14 + i], h->cfg.k_range[i] * x[i], t_plan)
+                                       : st[i] + st[7 + i] * 0.5 + h->h_krange[i] * x[i] * 0.125;
+        const double dk = h->mode == 0 ? pow(t_plan, 3) * (6 * pow(t_plan, 2) - 15 * t_plan + 10) * h->cfg.k_range[i] : h->h_krange[i] * 0.125;   // KPA/NLPclass.cu:229-230
         grad_f[i] = (i % 2 == 0) ? (2 * wrap_to_pi(qp - q_des[i]) * dk) : (2 * (qp - q_des[i]) * dk);
         grad_f[i] *= COST_SCALE;
     }
@@ -449,7 +470,7 @@ int armour_eval_g_jac(armour_handle* h, const double* x, double* g, double* valu
         if (dg && dj) {
             memcpy(h->h_x, x, sizeof(double) * NF);
             Tables tb = h->tb;
-            tb.P = h->count; tb.n_obs = h->n_obs;
+            tb.P = h->count; tb.n_obs = h->n_obs; tb.mode = h->mode; tb.jrs = h->d_jrs; tb.k_range_in = h->d_krange;
             CU(cudaEventRecord(h->ev[3], h->stream));
             CU(launch_constraint_eval(tb, h->sel, h->h_x, dg, dj, h->d_link_center, h->stream));
             CU(cudaEventRecord(h->ev[4], h->stream));
@@ -497,13 +518,16 @@ int armour_check_feasible(armour_handle* h, const double* g, int* feasible) {
     const double* tr = h->h_torque_radius + (size_t)h->sel * T * NF;
     *feasible = 0;
     int offset = 0;
-    for (int i = 0; i < T; i++)
-        for (int j = 0; j < NF; j++) {
-            const double r = tr[i * NF + j];
-            if (g[i * NF + j] < -rm.torque[j] + r - TORQUE_THRESHOLD || g[i * NF + j] > rm.torque[j] - r + TORQUE_THRESHOLD) return ARMOUR_OK;
-        }
-    offset += NF * T;
-    for (int i = 0; i < NJ; i++) for (int j = 0; j < T; j++) for (int o = 0; o < h->n_obs; o++)
+    if (h->mode == 0) {
+        for (int i = 0; i < T; i++)
+            for (int j = 0; j < NF; j++) {
+                const double r = tr[i * NF + j];
+                if (g[i * NF + j] < -rm.torque[j] + r - TORQUE_THRESHOLD || g[i * NF + j] > rm.torque[j] - r + TORQUE_THRESHOLD) return ARMOUR_OK;
+            }
+        offset += NF * T;
+    }
+    const int links_checked = h->mode == 0 ? NJ : NF - 1;   // the ARMTD planner re-checks links 0..NUM_FACTORS-2 only (KPA/NLPclass.cu:388)
+    for (int i = 0; i < links_checked; i++) for (int j = 0; j < T; j++) for (int o = 0; o < h->n_obs; o++)
         if (g[(i * T + j) * h->n_obs + o + offset] > COLLISION_THRESHOLD) return ARMOUR_OK;
     offset += NJ * T * h->n_obs;
     for (int rep = 0; rep < 2; rep++) { for (int i = 0; i < NF; i++) if (g[offset + i] < rm.state_lb[i] + rm.qe || g[offset + i] > rm.state_ub[i] - rm.qe) return ARMOUR_OK; offset += NF; }
@@ -555,6 +579,12 @@ int armour_get_pz(armour_handle* h, int which, int idx, int t, int* dims, uint64
     int rc = ensure_mirror(h);
     if (rc != ARMOUR_OK) return rc;
     const int T = h->T;
+    if (h->mode == 1 && (which == 8 || which == 9)) {   // no torque PZs in the ARMTD comparison planner
+        if (dims) { dims[0] = 1; dims[1] = 1; }
+        if (center) center[0] = 0.0;
+        if (independent) independent[0] = 0.0;
+        return 0;
+    }
     if (which >= 0 && which <= 6) {
         if (which == 2 && idx == NJ) {   // R(NUM_JOINTS) = identity (KPR/Trajectory.cu:253)
             if (dims) { dims[0] = 3; dims[1] = 3; }

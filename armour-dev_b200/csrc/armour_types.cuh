@@ -43,6 +43,9 @@ struct Tables {
     double k_range[NF];
     double mass_unc, inertia_unc, thr;
     // inputs
+    int mode;                  // 0 ARMOUR (Bezier trajectory + RNEA); 1 ARMTD comparison planner (offline JRS tables, FK only)
+    const double* jrs;         // mode 1: [P][6][NF][T] c_cos, g_cos, r_cos, c_sin, g_sin, r_sin (KPA/armtd_main.cu:41-47)
+    const double* k_range_in;  // mode 1: [P][NF] (k_range is an input of that planner)
     const double* state;       // [P][21] q0, qd0, qdd0
     const double* obstacles;   // [P][n_obs][12]
     // trajectory tables (export)

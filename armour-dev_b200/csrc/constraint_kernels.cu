@@ -135,6 +135,40 @@ __device__ void joint_extremum(double q0, double a, double b, double k, bool vel
     *mn = vmn; *mx = vmx; *gmn = dk(imn); *gmx = dk(imx);
 }
 
+// ARMTD comparison planner: min / max joint position and velocity over the move-then-brake trajectory and the
+// derivative of the selected branch with respect to k_actual (KPA/Trajectory.cu:83-411; no k_range factor there)
+__device__ void armtd_state_extremum(double q0, double qd0, double k_actual, double* ext, double* grad) {
+    const double t_move = 0.5, t_to_stop = 0.5;
+    const double q_peak = q0 + qd0 * t_move + k_actual * t_move * t_move * 0.5;
+    const double q_dot_peak = qd0 + k_actual * t_move;
+    const double q_ddot_to_stop = -q_dot_peak / t_to_stop;
+    const double q_stop = q_peak + q_dot_peak * t_to_stop + 0.5 * q_ddot_to_stop * t_to_stop * t_to_stop;
+    const double t_mm = -qd0 / k_actual;
+    double qe0, qe1, ge0, ge1;
+    if (q_peak >= q0) { qe0 = q0; qe1 = q_peak; ge0 = 0; ge1 = 0.5 * t_move * t_move; }
+    else { qe0 = q_peak; qe1 = q0; ge0 = 0.5 * t_move * t_move; ge1 = 0; }
+    double q_min_pk = qe0, q_max_pk = qe1, g_min_pk = ge0, g_max_pk = ge1;
+    if (t_mm > 0 && t_mm < t_move) {
+        const double qm = q0 + qd0 * t_mm + 0.5 * k_actual * t_mm * t_mm, gm = (0.5 * qd0 * qd0) / (k_actual * k_actual);
+        if (k_actual >= 0) { q_min_pk = qm; g_min_pk = gm; q_max_pk = qe1; g_max_pk = ge1; }
+        else { q_max_pk = qm; g_max_pk = gm; q_min_pk = qe0; g_min_pk = ge0; }
+    }
+    double v_min_pk, v_max_pk, gv_min_pk, gv_max_pk;
+    if (q_dot_peak >= qd0) { v_min_pk = qd0; v_max_pk = q_dot_peak; gv_min_pk = 0; gv_max_pk = t_move; }
+    else { v_min_pk = q_dot_peak; v_max_pk = qd0; gv_min_pk = t_move; gv_max_pk = 0; }
+    double q_min_st, q_max_st, g_min_st, g_max_st;
+    if (q_stop >= q_peak) { q_min_st = q_peak; q_max_st = q_stop; g_min_st = 0.5 * t_move * t_move; g_max_st = 0.5 * t_move * t_move + 0.5 * t_move * t_to_stop; }
+    else { q_min_st = q_stop; q_max_st = q_peak; g_min_st = 0.5 * t_move * t_move + 0.5 * t_move * t_to_stop; g_max_st = 0.5 * t_move * t_move; }
+    double v_min_st, v_max_st, gv_min_st, gv_max_st;
+    if (q_dot_peak >= 0) { v_min_st = 0; v_max_st = q_dot_peak; gv_min_st = 0; gv_max_st = t_move; }
+    else { v_min_st = q_dot_peak; v_max_st = 0; gv_min_st = t_move; gv_max_st = 0; }
+    const bool a = q_min_pk <= q_min_st, b = q_max_pk >= q_max_st, cc = v_min_pk <= v_min_st, d = v_max_pk >= v_max_st;
+    ext[0] = a ? q_min_pk : q_min_st; grad[0] = a ? g_min_pk : g_min_st;
+    ext[1] = b ? q_max_pk : q_max_st; grad[1] = b ? g_max_pk : g_max_st;
+    ext[2] = cc ? v_min_pk : v_min_st; grad[2] = cc ? gv_min_pk : gv_min_st;
+    ext[3] = d ? v_max_pk : v_max_st; grad[3] = d ? gv_max_pk : gv_max_st;
+}
+
 // x^d for d in 0..3 the way std::pow returns it for these exponents (exact products of x)
 __device__ __forceinline__ double powi(double x, int d) { return d == 0 ? 1.0 : d == 1 ? x : d == 2 ? x * x : x * x * x; }
 
@@ -175,8 +209,21 @@ __global__ void __launch_bounds__(EVAL_NT) constraint_eval_kernel(Tables tb, int
     if (tid < NF) x[tid] = xarg.x[tid];
     __syncthreads();
     const int blk = blockIdx.x;
-    const size_t off_obs = (size_t)NF * T, off_lim = off_obs + (size_t)NJ * T * n_obs;
+    const size_t off_obs = tb.mode == 0 ? (size_t)NF * T : 0, off_lim = off_obs + (size_t)NJ * T * n_obs;
     if (blk == T * NJ) {   // limit rows (KPR/NLPclass.cu:319-320, 393-394)
+        if (tb.mode == 1) {   // KPA/NLPclass.cu:275-276
+            if (tid < NF) {
+                const double* st = tb.state + (size_t)prob * 21;
+                double ext[4], gr[4];
+                armtd_state_extremum(st[tid], st[7 + tid], tb.k_range_in[(size_t)prob * NF + tid] * x[tid], ext, gr);
+                for (int r = 0; r < 4; r++) {
+                    const size_t row = off_lim + r * NF + tid;
+                    g[row] = ext[r];
+                    for (int j = 0; j < NF; j++) jac[row * NF + j] = (j == tid) ? gr[r] : 0.0;
+                }
+            }
+            return;
+        }
         if (tid < 2 * NF) {
             const int i = tid % NF;
             const bool velocity = tid >= NF;
@@ -193,7 +240,7 @@ __global__ void __launch_bounds__(EVAL_NT) constraint_eval_kernel(Tables tb, int
     const int t = blk / NJ, j = blk - t * NJ;
     const size_t rec = ((size_t)prob * T + t) * NJ + j;
     // ---- torque row ------------------------------------------------------------------------------
-    const int un = tb.u_n[rec];
+    const int un = tb.mode == 0 ? tb.u_n[rec] : 0;
     for (int e = tid; e < un * 8; e += EVAL_NT) {
         const int m = e >> 3, w = e & 7;
         uterms[w][m] = slice_term(tb.u_coef[rec * UCAP + m], tb.u_keys[rec * UCAP + m], x, w == 0 ? -1 : w - 1);
@@ -206,7 +253,7 @@ __global__ void __launch_bounds__(EVAL_NT) constraint_eval_kernel(Tables tb, int
         terms[w][m] = slice_term(tb.l_coef[(rec * 3 + c) * LCAP + m], tb.l_keys[rec * LCAP + m], x, which - 1);
     }
     __syncthreads();
-    if (tid < 8) {   // sequential sums in key order, like the reference's loop over the monomial list
+    if (tid < 8 && tb.mode == 0) {   // sequential sums in key order, like the reference's loop over the monomial list
         double s = (tid == 0) ? tb.u_center[rec] : 0.0;
         for (int m = 0; m < un; m++) s = s + uterms[tid][m];
         const size_t row = (size_t)t * NF + j;

@@ -114,6 +114,83 @@ __device__ void export_small(SmallRec& r, const PZ<D>& z) {
     for (int c = 0; c < D; c++) { r.center[c] = z.center[c]; r.ind[c] = z.ind[0][c]; }
 }
 
+// ARMTD comparison planner (KPA = kinova_planner_realtime_armtd_comparison): rotation PZs of joint i from the offline
+// JRS zonotopes of cos / sin of the displacement (KPA/Trajectory.cu:29-81)
+__device__ void rotation_from_cos_sin(int i, double cos_center, double cos_c0, double cos_c1, double sin_center, double sin_c0, double sin_c1, PZ<9>& R, PZ<9>& Rt, double thr);
+__device__ void make_poly_zono_armtd(const Tables& tb, int prob, int s, int i, PZ<9>& R, PZ<9>& Rt, PZ<1>& cosq, PZ<1>& sinq, double thr) {
+    const double* st = tb.state + (size_t)prob * 21;
+    const int T = tb.T;
+    const double* J = tb.jrs + (size_t)prob * 6 * NF * T;
+    auto tab = [&](int which) { return J[((size_t)which * NF + i) * T + s]; };
+    const double cos_q0 = cos(st[i]), sin_q0 = sin(st[i]);
+    const double cos_center = cos_q0 * tab(0) - sin_q0 * tab(3);
+    const double cos_c0 = cos_q0 * tab(1) - sin_q0 * tab(4);
+    double cos_c1 = fabs(cos_q0) * tab(2) + fabs(sin_q0) * tab(5);
+    cos_c1 *= 5.0;
+    const double sin_center = cos_q0 * tab(3) + sin_q0 * tab(0);
+    const double sin_c0 = cos_q0 * tab(4) + sin_q0 * tab(1);
+    double sin_c1 = fabs(cos_q0) * tab(5) + fabs(sin_q0) * tab(2);
+    sin_c1 *= 5.0;
+    small_scalar(cosq, cos_center, key_k(i), cos_c0, key_cosqe(i), cos_c1, thr);
+    small_scalar(sinq, sin_center, key_k(i), sin_c0, key_sinqe(i), sin_c1, thr);
+    rotation_from_cos_sin(i, cos_center, cos_c0, cos_c1, sin_center, sin_c0, sin_c1, R, Rt, thr);
+}
+
+// R = R0(rpy) * R_axis(cos, sin) and its transpose   (Trajectory.cu:136-144; 3x3 ctor PZsparse.cu:179-205; operator* :864-994)
+__device__ void rotation_from_cos_sin(int i, double cos_center, double cos_c0, double cos_c1, double sin_center, double sin_c0, double sin_c1, PZ<9>& R, PZ<9>& Rt, double thr) {
+    const RobotModel& rm = c_robot;
+
+        const int axis = rm.axes[i];
+        const double* R0 = rm.R0[i];
+        double Rzc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        double Mk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, Mc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, Ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        // index pairs of the rotation block for axis x / y / z (makeRotationMatrix, PZsparse.cu:211-250)
+        int pcc0 = 0, pcc1 = 4, pns = 3, pps = 1;   // z: (0,0),(1,1) cos; (0,1) -sin; (1,0) +sin
+        if (axis == 1) { pcc0 = 4; pcc1 = 8; pns = 7; pps = 5; }        // x: (1,1),(2,2); (1,2) -sin; (2,1) +sin
+        else if (axis == 2) { pcc0 = 0; pcc1 = 8; pns = 2; pps = 6; }   // y: (0,0),(2,2); (2,0) -sin; (0,2) +sin
+        int n = 0;
+        double zind[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        u64 zk[3]; double zc[3][9];
+        if (axis != 0) {
+            Rzc[pcc0] = cos_center; Rzc[pcc1] = cos_center; Rzc[pns] = -sin_center; Rzc[pps] = sin_center;
+            Mk[pcc0] = cos_c0; Mk[pcc1] = cos_c0; Mk[pns] = -sin_c0; Mk[pps] = sin_c0;   // k_i terms of cos and sin merge
+            Mc[pcc0] = cos_c1; Mc[pcc1] = cos_c1;
+            Ms[pns] = -sin_c1; Ms[pps] = sin_c1;
+            const double* cand[3] = {Mk, Mc, Ms};
+            const u64 ck[3] = {key_k(i), key_cosqe(i), key_sinqe(i)};
+            for (int m = 0; m < 3; m++) {
+                if (norm9(cand[m]) <= thr) { for (int c = 0; c < 9; c++) zind[c] = __dadd_ru(zind[c], __dmul_ru(fabs(cand[m][c]), 1.0 + 0x1p-40)); }
+                else { zk[n] = ck[m]; for (int c = 0; c < 9; c++) zc[n][c] = cand[m][c]; n++; }
+            }
+        }
+        double cen[9], ind[9], absR0[9], abss[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        matmat_rn(R0, Rzc, cen);
+        for (int c = 0; c < 9; c++) absR0[c] = fabs(R0[c]);
+        matmat_ru(absR0, zind, ind);
+        int nr = 0;
+        for (int m = 0; m < n; m++) {
+            double pm[9];
+            matmat_rn(R0, zc[m], pm);
+            if (norm9(pm) <= thr) { for (int c = 0; c < 9; c++) ind[c] = __dadd_ru(ind[c], __dmul_ru(fabs(pm[c]), 1.0 + 0x1p-40)); }
+            else {
+                R.keys[nr] = zk[m];
+                for (int c = 0; c < 9; c++) { R.coef[c * R.cap + nr] = pm[c]; abss[c] = __dadd_ru(abss[c], fabs(pm[c])); }
+                nr++;
+            }
+        }
+        R.n = nr; R.divM = FastDiv::magic(nr);
+        for (int c = 0; c < 9; c++) { R.center[c] = cen[c]; R.ind[0][c] = ind[c]; R.ind[1][c] = ind[c]; R.abss[c] = abss[c]; }
+        // R_t = R.transpose()
+        Rt.n = nr; Rt.divM = FastDiv::magic(nr);
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) {
+                const int src = r + 3 * c, dstp = c + 3 * r;
+                Rt.center[dstp] = cen[src]; Rt.ind[0][dstp] = ind[src]; Rt.ind[1][dstp] = ind[src]; Rt.abss[dstp] = abss[src];
+                for (int m = 0; m < nr; m++) Rt.coef[dstp * Rt.cap + m] = R.coef[src * R.cap + m];
+            }
+        for (int m = 0; m < nr; m++) Rt.keys[m] = R.keys[m];
+    }
+
 // joint i, interval s: everything makePolyZono produces for that joint (KPR/Trajectory.cu:63-254)
 __device__ void make_poly_zono_joint(const Tables& tb, int prob, int s, int i, PZ<9>& R, PZ<9>& Rt, PZ<1>& qd, PZ<1>& qda, PZ<1>& qdda,
                                      PZ<1>& cosq, PZ<1>& sinq, double thr) {   // thr: squared-domain threshold (Scratch::thr_sq)
@@ -173,58 +250,7 @@ __device__ void make_poly_zono_joint(const Tables& tb, int prob, int s, int i, P
     small_scalar(cosq, cos_center, key_k(i), cos_c0, key_cosqe(i), cos_c1, thr);
     small_scalar(sinq, sin_center, key_k(i), sin_c0, key_sinqe(i), sin_c1, thr);
 
-    // R = R0(rpy) * Rz(cos, sin)   (Trajectory.cu:136-144; 3x3 ctor PZsparse.cu:179-205; operator* :864-994)
-    {
-        const int axis = rm.axes[i];
-        const double* R0 = rm.R0[i];
-        double Rzc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-        double Mk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, Mc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, Ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        // index pairs of the rotation block for axis x / y / z (makeRotationMatrix, PZsparse.cu:211-250)
-        int pcc0 = 0, pcc1 = 4, pns = 3, pps = 1;   // z: (0,0),(1,1) cos; (0,1) -sin; (1,0) +sin
-        if (axis == 1) { pcc0 = 4; pcc1 = 8; pns = 7; pps = 5; }        // x: (1,1),(2,2); (1,2) -sin; (2,1) +sin
-        else if (axis == 2) { pcc0 = 0; pcc1 = 8; pns = 2; pps = 6; }   // y: (0,0),(2,2); (2,0) -sin; (0,2) +sin
-        int n = 0;
-        double zind[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        u64 zk[3]; double zc[3][9];
-        if (axis != 0) {
-            Rzc[pcc0] = cos_center; Rzc[pcc1] = cos_center; Rzc[pns] = -sin_center; Rzc[pps] = sin_center;
-            Mk[pcc0] = cos_c0; Mk[pcc1] = cos_c0; Mk[pns] = -sin_c0; Mk[pps] = sin_c0;   // k_i terms of cos and sin merge
-            Mc[pcc0] = cos_c1; Mc[pcc1] = cos_c1;
-            Ms[pns] = -sin_c1; Ms[pps] = sin_c1;
-            const double* cand[3] = {Mk, Mc, Ms};
-            const u64 ck[3] = {key_k(i), key_cosqe(i), key_sinqe(i)};
-            for (int m = 0; m < 3; m++) {
-                if (norm9(cand[m]) <= thr) { for (int c = 0; c < 9; c++) zind[c] = __dadd_ru(zind[c], __dmul_ru(fabs(cand[m][c]), 1.0 + 0x1p-40)); }
-                else { zk[n] = ck[m]; for (int c = 0; c < 9; c++) zc[n][c] = cand[m][c]; n++; }
-            }
-        }
-        double cen[9], ind[9], absR0[9], abss[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        matmat_rn(R0, Rzc, cen);
-        for (int c = 0; c < 9; c++) absR0[c] = fabs(R0[c]);
-        matmat_ru(absR0, zind, ind);
-        int nr = 0;
-        for (int m = 0; m < n; m++) {
-            double pm[9];
-            matmat_rn(R0, zc[m], pm);
-            if (norm9(pm) <= thr) { for (int c = 0; c < 9; c++) ind[c] = __dadd_ru(ind[c], __dmul_ru(fabs(pm[c]), 1.0 + 0x1p-40)); }
-            else {
-                R.keys[nr] = zk[m];
-                for (int c = 0; c < 9; c++) { R.coef[c * R.cap + nr] = pm[c]; abss[c] = __dadd_ru(abss[c], fabs(pm[c])); }
-                nr++;
-            }
-        }
-        R.n = nr; R.divM = FastDiv::magic(nr);
-        for (int c = 0; c < 9; c++) { R.center[c] = cen[c]; R.ind[0][c] = ind[c]; R.ind[1][c] = ind[c]; R.abss[c] = abss[c]; }
-        // R_t = R.transpose()
-        Rt.n = nr; Rt.divM = FastDiv::magic(nr);
-        for (int r = 0; r < 3; r++)
-            for (int c = 0; c < 3; c++) {
-                const int src = r + 3 * c, dstp = c + 3 * r;
-                Rt.center[dstp] = cen[src]; Rt.ind[0][dstp] = ind[src]; Rt.ind[1][dstp] = ind[src]; Rt.abss[dstp] = abss[src];
-                for (int m = 0; m < nr; m++) Rt.coef[dstp * Rt.cap + m] = R.coef[src * R.cap + m];
-            }
-        for (int m = 0; m < nr; m++) Rt.keys[m] = R.keys[m];
-    }
+    rotation_from_cos_sin(i, cos_center, cos_c0, cos_c1, sin_center, sin_c0, sin_c1, R, Rt, thr);
 
     // Part 2: qd_des
     {
@@ -612,7 +638,12 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
         // ---- stage A: joint reach sets (one thread per joint; tiny scalar work) -------------------
         if (threadIdx.x < NJ) {
             const int i = threadIdx.x;
-            make_poly_zono_joint(tb, prob, s, i, Z.R[i], Z.Rt[i], Z.qd[i], Z.qda[i], Z.qdda[i], Z.cosq[i], Z.sinq[i], S.thr_sq);
+            if (tb.mode == 1) {
+                make_poly_zono_armtd(tb, prob, s, i, Z.R[i], Z.Rt[i], Z.cosq[i], Z.sinq[i], S.thr_sq);
+                PZ<1>* unused[3] = {&Z.qd[i], &Z.qda[i], &Z.qdda[i]};
+                for (PZ<1>* z : unused) { z->n = 0; z->divM = FastDiv::magic(0); z->center[0] = 0; z->ind[0][0] = 0; z->ind[1][0] = 0; z->abss[0] = 0; }
+            }
+            else make_poly_zono_joint(tb, prob, s, i, Z.R[i], Z.Rt[i], Z.qd[i], Z.qda[i], Z.qdda[i], Z.cosq[i], Z.sinq[i], S.thr_sq);
             if (tb.traj) {
                 SmallRec* rec = tb.traj + (((size_t)prob * tb.T + s) * TRAJ_TABLES) * NJ;
                 export_small<1>(rec[TRAJ_COS * NJ + i], Z.cosq[i]); export_small<1>(rec[TRAJ_SIN * NJ + i], Z.sinq[i]);
@@ -658,7 +689,10 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
 #define PIECE(acc)
 #endif
         PIECE_T0();
-        if (GROUPS == 1) {
+        if (tb.mode == 1) {   // ARMTD comparison planner: forward kinematics only (KPA/armtd_main.cu:127-145)
+            if (group == 0) forward_kinematics<NT>(S, Z, T, tb, rec0);
+        }
+        else if (GROUPS == 1) {
             forward_kinematics<NT>(S, Z, T, tb, rec0);                                    // stage B
             for (int i = 0; i < NJ; i++) {                                                 // stage C forward
                 chain_joint<NT>(S, Z, T, i, (i + 1) & 1, i & 1);
@@ -715,7 +749,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
 #endif
 
         // ---- stage M: disturbance, reduce(), torque radius (KPR/armour_main.cu:135-205) -------------
-        if (group == 0) {
+        if (group == 0 && tb.mode == 0) {
             for (int i = 0; i < NF; i++) export_torque<NT>(S, tb, rec0 + i, Z.u[i]);
             if (threadIdx.x == 0) {
                 const size_t base = rec0;

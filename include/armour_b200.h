@@ -83,6 +83,16 @@ int armour_build(armour_handle* h, const double* q0, const double* qd0, const do
 int armour_build_batch(armour_handle* h, int count, const double* q0, const double* qd0, const double* qdd0, const double* obstacles, int n_obs);
 int armour_select_problem(armour_handle* h, int p);
 
+/* Second trajectory family: the ARMTD comparison planner (kinova_planner_realtime_armtd_comparison, "KPA"):
+ * constant-acceleration trajectory whose joint reach sets come from OFFLINE JRS tables, forward occupancy only
+ * (no RNEA, no torque rows).  jrs = [6][7][T] doubles in the order c_cos, g_cos, r_cos, c_sin, g_sin, r_sin and
+ * k_range[7] are inputs of that planner (KPA/armtd_main.cu:41-90); use cfg.num_time_steps = 100 for its defaults.
+ * Replaces ConstantAccelerationCurve::makePolyZono (KPA/Trajectory.cu:29-81), KinematicsDynamics::fk,
+ * reduce_link_PZ and Obstacles::initializeHyperPlane.  The TNLP entry points then follow KPA/NLPclass.cu:
+ * m = 7*T*n_obs + 28, obstacle rows first, then the joint state extrema of returnJointStateExtremum[Gradient]
+ * (KPA/Trajectory.cu:83-411; their k-derivatives carry no k_range factor in the reference and none here). */
+int armour_build_armtd(armour_handle* h, const double* q0, const double* qd0, const double* jrs, const double* k_range, const double* obstacles, int n_obs);
+
 /* armtd_NLP::get_nlp_info (KPR/NLPclass.cu:62-82) */
 int armour_get_nlp_info(armour_handle* h, int* n, int* m, int* nnz_jac_g, int* nnz_h_lag);
 /* armtd_NLP::get_bounds_info (:87-165) */

@@ -233,6 +233,10 @@ struct Plan {
     std::vector<Mat> link_sliced_center;      // [t*NJ + l]
     std::vector<Mat> dk_link_sliced_center;   // [(t*NJ + l)*NF + k]
 
+    // second trajectory family: ARMTD comparison planner (KPA = kinova_planner_realtime_armtd_comparison)
+    int mode = 0;                 // 0 ARMOUR (Bezier + RNEA), 1 ARMTD (constant acceleration, offline JRS tables, FK only)
+    std::vector<double> jrs;      // [6][NF][T]: c_cos, g_cos, r_cos, c_sin, g_sin, r_sin (KPA/armtd_main.cu:41-47)
+
     OpStats stats;
     double build_ms = 0;
 
@@ -630,6 +634,92 @@ void returnJointExtremumGradient(const Plan& p, double* grad, const double* k, b
     }
 }
 
+
+// ---- ARMTD comparison planner: KPA/Trajectory.cu ------------------------------------------------------------
+// joint rotation PZs from the offline JRS zonotopes of cos / sin of the displacement (KPA/Trajectory.cu:29-81)
+void makePolyZono_armtd(Plan& p, int s) {
+    const int T = p.T;
+    auto tab = [&](int which, int i) { return p.jrs[((size_t)which * NF + i) * T + s]; };
+    for (int i = 0; i < NF; i++) {
+        const double cos_q0 = std::cos(p.q0[i]), sin_q0 = std::sin(p.q0[i]);
+        double cos_center = cos_q0 * tab(0, i) - sin_q0 * tab(3, i);
+        double cos_coeff[2];
+        cos_coeff[0] = cos_q0 * tab(1, i) - sin_q0 * tab(4, i);
+        cos_coeff[1] = std::fabs(cos_q0) * tab(2, i) + std::fabs(sin_q0) * tab(5, i);
+        cos_coeff[1] *= 5.0;
+        uint64_t cos_deg[2][NVAR] = {{0}};
+        cos_deg[0][i] = 1; cos_deg[1][i + NF * 4] = 1;
+        double sin_center = cos_q0 * tab(3, i) + sin_q0 * tab(0, i);
+        double sin_coeff[2];
+        sin_coeff[0] = cos_q0 * tab(4, i) + sin_q0 * tab(1, i);
+        sin_coeff[1] = std::fabs(cos_q0) * tab(5, i) + std::fabs(sin_q0) * tab(2, i);
+        sin_coeff[1] *= 5.0;
+        uint64_t sin_deg[2][NVAR] = {{0}};
+        sin_deg[0][i] = 1; sin_deg[1][i + NF * 5] = 1;
+        p.at(p.cos_q, i, s) = PZ(cos_center, cos_coeff, cos_deg, 2);   // not kept by the reference; exported for parity tests
+        p.at(p.sin_q, i, s) = PZ(sin_center, sin_coeff, sin_deg, 2);
+        p.at(p.R, i, s) = PZ(rots[i * 3], rots[i * 3 + 1], rots[i * 3 + 2]);
+        if (axes[i] != 0)
+            p.at(p.R, i, s) = p.at(p.R, i, s) * PZ(cos_center, cos_coeff, cos_deg, 2, sin_center, sin_coeff, sin_deg, 2, axes[i]);
+        p.at(p.R_t, i, s) = p.at(p.R, i, s).transpose();
+    }
+    p.at(p.R, NJ, s) = PZ(0.0, 0.0, 0.0);
+}
+// min / max joint position and velocity over the move-then-brake trajectory and the derivative of the selected
+// branch (KPA/Trajectory.cu:83-411).  Note: the reference's derivatives are with respect to k_actual = k_range * k
+// (no k_range factor) and its gradient routine zeroes only 4*NF*NF BYTES of the output; both are kept as they are
+// (off-diagonal entries are written as 0 here).
+void armtd_state_extremum(const Plan& p, const double* k, double* ext, double* grad) {
+    const double t_move = 0.5, t_total = 1.0, t_to_stop = t_total - t_move;
+    for (int i = 0; i < NF; i++) {
+        const double q0 = p.q0[i], qd0 = p.qd0[i];
+        const double k_actual = p.k_range[i] * k[i];
+        const double q_peak = q0 + qd0 * t_move + k_actual * t_move * t_move * 0.5;
+        const double q_dot_peak = qd0 + k_actual * t_move;
+        const double q_ddot_to_stop = -q_dot_peak / t_to_stop;
+        const double q_stop = q_peak + q_dot_peak * t_to_stop + 0.5 * q_ddot_to_stop * t_to_stop * t_to_stop;
+        const double t_mm = -qd0 / k_actual;
+        double qe0, qe1, ge0, ge1;
+        if (q_peak >= q0) { qe0 = q0; qe1 = q_peak; ge0 = 0; ge1 = 0.5 * t_move * t_move; }
+        else { qe0 = q_peak; qe1 = q0; ge0 = 0.5 * t_move * t_move; ge1 = 0; }
+        double q_min_pk, q_max_pk, g_min_pk, g_max_pk;
+        if (t_mm > 0 && t_mm < t_move) {
+            if (k_actual >= 0) {
+                q_min_pk = q0 + qd0 * t_mm + 0.5 * k_actual * t_mm * t_mm; q_max_pk = qe1;
+                g_min_pk = (0.5 * qd0 * qd0) / (k_actual * k_actual); g_max_pk = ge1;
+            }
+            else {
+                q_min_pk = qe0; q_max_pk = q0 + qd0 * t_mm + 0.5 * k_actual * t_mm * t_mm;
+                g_min_pk = ge0; g_max_pk = (0.5 * qd0 * qd0) / (k_actual * k_actual);
+            }
+        }
+        else { q_min_pk = qe0; q_max_pk = qe1; g_min_pk = ge0; g_max_pk = ge1; }
+        double v_min_pk, v_max_pk, gv_min_pk, gv_max_pk;
+        if (q_dot_peak >= qd0) { v_min_pk = qd0; v_max_pk = q_dot_peak; gv_min_pk = 0; gv_max_pk = t_move; }
+        else { v_min_pk = q_dot_peak; v_max_pk = qd0; gv_min_pk = t_move; gv_max_pk = 0; }
+        double q_min_st, q_max_st, g_min_st, g_max_st;
+        if (q_stop >= q_peak) { q_min_st = q_peak; q_max_st = q_stop; g_min_st = 0.5 * t_move * t_move; g_max_st = 0.5 * t_move * t_move + 0.5 * t_move * t_to_stop; }
+        else { q_min_st = q_stop; q_max_st = q_peak; g_min_st = 0.5 * t_move * t_move + 0.5 * t_move * t_to_stop; g_max_st = 0.5 * t_move * t_move; }
+        double v_min_st, v_max_st, gv_min_st, gv_max_st;
+        if (q_dot_peak >= 0) { v_min_st = 0; v_max_st = q_dot_peak; gv_min_st = 0; gv_max_st = t_move; }
+        else { v_min_st = q_dot_peak; v_max_st = 0; gv_min_st = t_move; gv_max_st = 0; }
+        const bool a = q_min_pk <= q_min_st, b = q_max_pk >= q_max_st, c = v_min_pk <= v_min_st, d = v_max_pk >= v_max_st;
+        if (ext) {
+            ext[i] = a ? q_min_pk : q_min_st;
+            ext[i + NF] = b ? q_max_pk : q_max_st;
+            ext[i + 2 * NF] = c ? v_min_pk : v_min_st;
+            ext[i + 3 * NF] = d ? v_max_pk : v_max_st;
+        }
+        if (grad) {
+            for (int r = 0; r < 4; r++) for (int j = 0; j < NF; j++) grad[(i + r * NF) * NF + j] = 0.0;
+            grad[i * NF + i] = a ? g_min_pk : g_min_st;
+            grad[(i + NF) * NF + i] = b ? g_max_pk : g_max_st;
+            grad[(i + 2 * NF) * NF + i] = c ? gv_min_pk : gv_min_st;
+            grad[(i + 3 * NF) * NF + i] = d ? gv_max_pk : gv_max_st;
+        }
+    }
+}
+
 double wrap_to_pi(double angle) {   // KPR/NLPclass.cu:6-15
     double w = angle;
     while (w < -M_PI) w += 2 * M_PI;
@@ -637,7 +727,9 @@ double wrap_to_pi(double angle) {   // KPR/NLPclass.cu:6-15
     return w;
 }
 
-int constraint_number(const Plan& p) { return NF * p.T + NJ * p.T * p.n_obs + NF * 4; }   // KPR/NLPclass.cu:47-49
+int constraint_number(const Plan& p) {   // KPR/NLPclass.cu:47-49; KPA/NLPclass.cu:42-43
+    return (p.mode == 0 ? NF * p.T : 0) + NJ * p.T * p.n_obs + NF * 4;
+}
 
 }  // namespace
 
@@ -672,6 +764,7 @@ int oracle_build(void* h, const double* q0, const double* qd0, const double* qdd
     Plan& p = *(Plan*)h;
     if (n_obs < 0) return -1;
     PZ::threshold() = p.threshold;
+    p.mode = 0;
     p.n_obs = n_obs;
     p.obstacles.assign(obstacles, obstacles + (size_t)n_obs * 12);
     const int T = p.T;
@@ -712,6 +805,50 @@ int oracle_build(void* h, const double* q0, const double* qd0, const double* qdd
     p.dk_link_sliced_center.assign((size_t)T * NJ * NF, Mat(3, 1));
     return 0;
 }
+
+// ARMTD comparison planner build (KPA/armtd_main.cu:110-160): JRS tables -> rotation PZs -> FK -> half-space tables.
+// jrs: [6][7][T] doubles in the order c_cos, g_cos, r_cos, c_sin, g_sin, r_sin; k_range is a per-problem input there.
+int oracle_build_armtd(void* h, const double* q0, const double* qd0, const double* jrs, const double* k_range, const double* obstacles, int n_obs) {
+    Plan& p = *(Plan*)h;
+    if (n_obs < 0) return -1;
+    PZ::threshold() = p.threshold;
+    p.mode = 1;
+    p.n_obs = n_obs;
+    p.obstacles.assign(obstacles, obstacles + (size_t)n_obs * 12);
+    const int T = p.T;
+    p.jrs.assign(jrs, jrs + (size_t)6 * NF * T);
+    for (int i = 0; i < NF; i++) { p.q0[i] = q0[i]; p.qd0[i] = qd0[i]; p.qdd0[i] = 0; p.k_range[i] = k_range[i]; }
+    auto t0 = std::chrono::high_resolution_clock::now();
+    if (p.num_threads > 0) omp_set_num_threads(p.num_threads);
+    p.cos_q.assign((size_t)NF * T, PZ()); p.sin_q.assign((size_t)NF * T, PZ());
+    p.R.assign((size_t)(NJ + 1) * T, PZ()); p.R_t.assign((size_t)NJ * T, PZ());
+    p.qd_des.assign((size_t)NF * T, PZ(1, 1)); p.qda_des.assign((size_t)NF * T, PZ(1, 1)); p.qdda_des.assign((size_t)NF * T, PZ(1, 1));
+    int err = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int s = 0; s < T; s++) {
+        try { makePolyZono_armtd(p, s); } catch (int) { err = -1; }
+    }
+    if (err) return err;
+    kd_init(p);
+    p.link_gens.assign((size_t)T * NJ, Mat());
+#pragma omp parallel for schedule(dynamic)
+    for (int s = 0; s < T; s++) {
+        try {
+            fk(p, s);
+            for (int i = 0; i < NJ; i++) p.link_gens[(size_t)s * NJ + i] = p.at(p.links, i, s).reduce_link_PZ();
+        } catch (int) { err = -1; }
+    }
+    if (err) return err;
+    for (auto& z : p.u_nom) z = PZ(1, 1);
+    for (auto& z : p.u_nom_int) z = PZ(1, 1);
+    p.torque_radius.assign((size_t)NF * T, 0.0);
+    initializeHyperPlane(p);
+    auto t1 = std::chrono::high_resolution_clock::now();
+    p.build_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    p.link_sliced_center.assign((size_t)T * NJ, Mat(3, 1));
+    p.dk_link_sliced_center.assign((size_t)T * NJ * NF, Mat(3, 1));
+    return 0;
+}
 double oracle_build_ms(void* h) { return ((Plan*)h)->build_ms; }
 int oracle_num_threads() { return omp_get_max_threads(); }
 
@@ -733,12 +870,14 @@ int oracle_get_bounds_info(void* h, double* x_l, double* x_u, double* g_l, doubl
     const int T = p.T;
     for (int i = 0; i < NF; i++) { x_l[i] = -1.0; x_u[i] = 1.0; }
     int offset = 0;
-    for (int i = 0; i < T; i++)
-        for (int j = 0; j < NF; j++) {
-            g_l[i * NF + j] = -torque_limits[j] + p.torque_radius[j + (size_t)i * NF];
-            g_u[i * NF + j] = torque_limits[j] - p.torque_radius[j + (size_t)i * NF];
-        }
-    offset += NF * T;
+    if (p.mode == 0) {
+        for (int i = 0; i < T; i++)
+            for (int j = 0; j < NF; j++) {
+                g_l[i * NF + j] = -torque_limits[j] + p.torque_radius[j + (size_t)i * NF];
+                g_u[i * NF + j] = torque_limits[j] - p.torque_radius[j + (size_t)i * NF];
+            }
+        offset += NF * T;
+    }
     for (int i = offset; i < offset + T * NJ * p.n_obs; i++) { g_l[i] = -1e19; g_u[i] = 0; }
     offset += T * NJ * p.n_obs;
     for (int rep = 0; rep < 2; rep++) {
@@ -756,7 +895,9 @@ int oracle_get_starting_point(void*, double* x) { for (int i = 0; i < NF; i++) x
 int oracle_eval_f(void* h, const double* q_des, double t_plan, const double* x, double* obj) {   // :207-236
     Plan& p = *(Plan*)h;
     double qp[NF];
-    for (int i = 0; i < NF; i++) qp[i] = q_des_func(p.q0[i], p.Tqd0[i], p.TTqdd0[i], p.k_range[i] * x[i], t_plan);
+    for (int i = 0; i < NF; i++)
+        qp[i] = p.mode == 0 ? q_des_func(p.q0[i], p.Tqd0[i], p.TTqdd0[i], p.k_range[i] * x[i], t_plan)
+                            : p.q0[i] + p.qd0[i] * 0.5 + p.k_range[i] * x[i] * 0.125;   // KPA/NLPclass.cu:197
     double v = pow(wrap_to_pi(q_des[0] - qp[0]), 2) + pow(wrap_to_pi(q_des[2] - qp[2]), 2) + pow(wrap_to_pi(q_des[4] - qp[4]), 2) +
                pow(wrap_to_pi(q_des[6] - qp[6]), 2) + pow(q_des[1] - qp[1], 2) + pow(q_des[3] - qp[3], 2) + pow(q_des[5] - qp[5], 2);
     *obj = v * COST_SCALE;
@@ -765,8 +906,9 @@ int oracle_eval_f(void* h, const double* q_des, double t_plan, const double* x, 
 int oracle_eval_grad_f(void* h, const double* q_des, double t_plan, const double* x, double* grad) {   // :241-267
     Plan& p = *(Plan*)h;
     for (int i = 0; i < NF; i++) {
-        double qp = q_des_func(p.q0[i], p.Tqd0[i], p.TTqdd0[i], p.k_range[i] * x[i], t_plan);
-        double dk = pow(t_plan, 3) * (6 * pow(t_plan, 2) - 15 * t_plan + 10) * p.k_range[i];
+        double qp = p.mode == 0 ? q_des_func(p.q0[i], p.Tqd0[i], p.TTqdd0[i], p.k_range[i] * x[i], t_plan)
+                                : p.q0[i] + p.qd0[i] * 0.5 + p.k_range[i] * x[i] * 0.125;
+        double dk = p.mode == 0 ? pow(t_plan, 3) * (6 * pow(t_plan, 2) - 15 * t_plan + 10) * p.k_range[i] : p.k_range[i] * 0.125;   // KPA/NLPclass.cu:229-230
         grad[i] = (i % 2 == 0) ? (2 * wrap_to_pi(qp - q_des[i]) * dk) : (2 * (qp - q_des[i]) * dk);
         grad[i] *= COST_SCALE;
     }
@@ -775,6 +917,14 @@ int oracle_eval_grad_f(void* h, const double* q_des, double t_plan, const double
 int oracle_eval_g(void* h, const double* x, double* g) {   // :272-324
     Plan& p = *(Plan*)h;
     const int T = p.T;
+    if (p.mode == 1) {   // KPA/NLPclass.cu:263-277
+#pragma omp parallel for schedule(dynamic)
+        for (int i = 0; i < T; i++)
+            for (int l = 0; l < NJ; l++) p.link_sliced_center[(size_t)i * NJ + l] = p.at(p.links, l, i).sliceCenter(x);
+        linkFRSConstraints(p, g, nullptr);
+        armtd_state_extremum(p, x, g + NJ * T * p.n_obs, nullptr);
+        return 0;
+    }
 #pragma omp parallel for schedule(dynamic)
     for (int i = 0; i < T; i++) {
         for (int k = 0; k < NF; k++) g[i * NF + k] = p.at(p.u_nom, k, i).sliceCenter(x)(0);
@@ -788,6 +938,17 @@ int oracle_eval_g(void* h, const double* x, double* g) {   // :272-324
 int oracle_eval_jac_g(void* h, const double* x, double* values) {   // :330-396 (values != NULL branch)
     Plan& p = *(Plan*)h;
     const int T = p.T;
+    if (p.mode == 1) {   // KPA/NLPclass.cu eval_jac_g
+#pragma omp parallel for schedule(dynamic)
+        for (int i = 0; i < T; i++)
+            for (int l = 0; l < NJ; l++) {
+                p.link_sliced_center[(size_t)i * NJ + l] = p.at(p.links, l, i).sliceCenter(x);
+                p.at(p.links, l, i).sliceGradient(&p.dk_link_sliced_center[((size_t)i * NJ + l) * NF], x);
+            }
+        linkFRSConstraints(p, nullptr, values);
+        armtd_state_extremum(p, x, nullptr, values + (size_t)NJ * T * p.n_obs * NF);
+        return 0;
+    }
 #pragma omp parallel for schedule(dynamic)
     for (int i = 0; i < T; i++) {
         for (int k = 0; k < NF; k++) {
@@ -816,13 +977,16 @@ int oracle_check_feasible(void* h, const double* g) {
     Plan& p = *(Plan*)h;
     const int T = p.T;
     int offset = 0;
-    for (int i = 0; i < T; i++)
-        for (int j = 0; j < NF; j++) {
-            const double r = p.torque_radius[j + (size_t)i * NF];
-            if (g[i * NF + j] < -torque_limits[j] + r - TORQUE_THRESHOLD || g[i * NF + j] > torque_limits[j] - r + TORQUE_THRESHOLD) return 0;
-        }
-    offset += NF * T;
-    for (int i = 0; i < NJ; i++)
+    if (p.mode == 0) {
+        for (int i = 0; i < T; i++)
+            for (int j = 0; j < NF; j++) {
+                const double r = p.torque_radius[j + (size_t)i * NF];
+                if (g[i * NF + j] < -torque_limits[j] + r - TORQUE_THRESHOLD || g[i * NF + j] > torque_limits[j] - r + TORQUE_THRESHOLD) return 0;
+            }
+        offset += NF * T;
+    }
+    const int links_checked = p.mode == 0 ? NJ : NF - 1;   // the ARMTD planner re-checks links 0..NUM_FACTORS-2 only (KPA/NLPclass.cu:388)
+    for (int i = 0; i < links_checked; i++)
         for (int j = 0; j < T; j++)
             for (int o = 0; o < p.n_obs; o++)
                 if (g[(i * T + j) * p.n_obs + o + offset] > COLLISION_THRESHOLD) return 0;

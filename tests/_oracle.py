@@ -110,6 +110,16 @@ class Oracle:
             raise RuntimeError("oracle_build failed: %d" % rc)
         return self.L.oracle_build_ms(self.h)
 
+    def build_armtd(self, q0, qd0, jrs, k_range, obstacles):
+        """ARMTD comparison planner (KPA/armtd_main.cu): jrs[6, 7, T] offline JRS tables, k_range[7]."""
+        obs = _vec(obstacles)
+        self.n_obs = obs.size // 12
+        self.k_range = np.array(k_range, dtype=float)
+        rc = self.L.oracle_build_armtd(self.h, _dp(_vec(q0, 7)), _dp(_vec(qd0, 7)), _dp(_vec(jrs, 6 * 7 * self.T)), _dp(_vec(k_range, 7)), _dp(obs), C.c_int(self.n_obs))
+        if rc != 0:
+            raise RuntimeError("oracle_build_armtd failed: %d" % rc)
+        return self.L.oracle_build_ms(self.h)
+
     def op_stats(self):
         out = np.zeros(8, dtype=np.uint64)
         self.L.oracle_op_stats(self.h, _up(out))

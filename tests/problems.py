@@ -43,3 +43,33 @@ EXAMPLE_OBS = np.array([
     [0.75382, 0.51895, 0.4731, 0.030969, 0, 0, 0, 0.22312, 0, 0, 0, 0.22981],
     [0.75382, 0.51895, 0.4731, 0.030969, 0, 0, 0, 0.22312, 0, 0, 0, 0.22981],
 ]).ravel()
+
+
+def armtd_displacement(qd0, k_actual, t):
+    """Joint displacement of the ARMTD comparison planner's move-then-brake trajectory (KPA/Trajectory.h:6-16,
+    KPA/Trajectory.cu:84-94): constant acceleration k until t = 0.5, then constant deceleration to rest at t = 1."""
+    t = np.asarray(t, dtype=float)
+    move = qd0 * t + 0.5 * k_actual * t ** 2
+    peak, vpeak = qd0 * 0.5 + 0.125 * k_actual, qd0 + 0.5 * k_actual
+    ts = t - 0.5
+    brake = peak + vpeak * ts + 0.5 * (-vpeak / 0.5) * ts ** 2
+    return np.where(t <= 0.5, move, brake)
+
+
+def make_jrs_tables(qd0, k_range, T):
+    """Synthetic stand-ins for the reference's offline JRS tables (kinova_planner_realtime_armtd_comparison/offline_jrs,
+    binary .mat files that cannot travel): per joint and interval a zonotope c + g*k +- r enclosing cos / sin of the
+    displacement.  Returns jrs[6, 7, T] in the reference's order c_cos, g_cos, r_cos, c_sin, g_sin, r_sin."""
+    jrs = np.zeros((6, 7, T))
+    ks = np.linspace(-1, 1, 9)
+    for i in range(7):
+        for s in range(T):
+            ts = np.linspace(s / T, (s + 1) / T, 7)
+            d = np.array([[armtd_displacement(qd0[i], k * k_range[i], t) for t in ts] for k in ks])   # [k, t]
+            for base, f in ((0, np.cos), (3, np.sin)):
+                v = f(d)
+                g = float(np.mean(v[-1] - v[0]) / 2)
+                c = float(np.mean(v - g * ks[:, None]))
+                r = float(np.abs(v - c - g * ks[:, None]).max())
+                jrs[base, i, s], jrs[base + 1, i, s], jrs[base + 2, i, s] = c, g, r
+    return jrs
