@@ -25,6 +25,12 @@ int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
         if (e__ != cudaSuccess) return fail(ARMOUR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
+}  // namespace
+namespace armour {
+int capi_fail(int code, const std::string& msg) { return fail(code, msg); }   // used by controller_kernels.cu
+}
+namespace {
+
 // Kinova Gen3 without gripper (KPR/KinovaWithoutGripperInfo.h:10-112)
 void kinova_model(RobotModel& m) {
     memset(&m, 0, sizeof(m));

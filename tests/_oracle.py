@@ -28,7 +28,7 @@ class OracleConfig(C.Structure):
 
 
 def build_oracle(force=False):
-    src = [os.path.join(ORACLE_DIR, f) for f in ("oracle_armour.cpp", "oracle_pz.hpp", "Makefile")]
+    src = [os.path.join(ORACLE_DIR, f) for f in ("oracle_armour.cpp", "oracle_controller.cpp", "oracle_pz.hpp", "Makefile")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
     return LIB_PATH
@@ -48,6 +48,9 @@ def lib():
         L.oracle_build_ms.restype = C.c_double
         L.oracle_build_ms.argtypes = [C.c_void_p]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_controller_create.restype = C.c_void_p
+        L.oracle_controller_create.argtypes = [C.c_char_p, C.c_double]
+        L.oracle_controller_destroy.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -247,3 +250,61 @@ def pz_binary(op, a, b=None, threshold=5e-4, cap=1 << 16):
     dim = int(dims[0] * dims[1])
     return dict(rows=int(dims[0]), cols=int(dims[1]), keys=keys[:n].copy(), coeffs=coeffs[: n * dim].reshape(n, dim).copy(),
                 center=center[:dim].copy(), independent=indep[:dim].copy())
+
+
+
+class OracleController:
+    """CPU restatement of the robust-controller MEX (oracle/oracle_controller.cpp); same method names as
+    armour_b200.controller.RobustController."""
+
+    def __init__(self, robot_model_file, model_uncertainty=0.03, num_threads=1):
+        h = lib().oracle_controller_create(str(robot_model_file).encode(), float(model_uncertainty))
+        if not h:
+            raise RuntimeError("oracle_controller_create failed for %s" % robot_model_file)
+        self._h = C.c_void_p(h)
+        self.n = lib().oracle_controller_num_joints(self._h)
+        self.num_threads = num_threads
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().oracle_controller_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def model(self):
+        a = np.zeros((self.n, 40))
+        lib().oracle_controller_get_model(self._h, _dp(a))
+        return a
+
+    def _update(self, method, Kr, par, q, q_d, qd, qd_d, qd_dd):
+        arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)).reshape(-1, self.n) for a in (q, q_d, qd, qd_d, qd_dd)]
+        single = np.asarray(q).ndim == 1
+        count = arrs[0].shape[0]
+        Kr = np.ascontiguousarray(np.broadcast_to(np.asarray(Kr, dtype=np.float64), (self.n,)))
+        par = np.ascontiguousarray(np.asarray(par, dtype=np.float64))
+        u, un, v = (np.zeros((count, self.n)) for _ in range(3))
+        ui = np.zeros((count, self.n, 2))
+        Vs = np.zeros(count)
+        outside = lib().oracle_controller_update(self._h, C.c_int(method), C.c_int(count), _dp(Kr), _dp(par), *[_dp(a) for a in arrs],
+                                                 _dp(u), _dp(un), _dp(v), _dp(ui), _dp(Vs), C.c_int(self.num_threads))
+        if single:
+            return u[0], un[0], v[0], ui[0], Vs[0], outside
+        return u, un, v, ui, Vs, outside
+
+    def update(self, Kr, alpha, V_max, r_norm_threshold, q, q_d, qd, qd_d, qd_dd):
+        return self._update(0, Kr, [alpha, V_max, r_norm_threshold], q, q_d, qd, qd_d, qd_dd)
+
+    def update_althoff(self, Kr, Kp, Ki, max_error, q, q_d, qd, qd_d, qd_dd):
+        return self._update(1, Kr, [Kp[0], Kp[1], 0.0], q, q_d, qd, qd_d, qd_dd)
+
+    def rnea(self, q, qd, qda, qdd, gravity=True, interval=False):
+        a = [np.ascontiguousarray(np.asarray(x, dtype=np.float64)) for x in (q, qd, qda, qdd)]
+        if interval:
+            out = np.zeros((self.n, 2))
+            lib().oracle_controller_rnea_interval(self._h, *[_dp(x) for x in a], C.c_int(1 if gravity else 0), _dp(out))
+        else:
+            out = np.zeros(self.n)
+            lib().oracle_controller_rnea(self._h, *[_dp(x) for x in a], C.c_int(1 if gravity else 0), _dp(out))
+        return out

@@ -9,9 +9,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "armour_b200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(armour_[a-z0-9_]+)\s*\(", text)))
+    syms = set()
+    for name in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if not name.endswith(".h"):
+            continue
+        text = open(os.path.join(ROOT, "include", name)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        syms.update(re.findall(r"\b(armour_[a-z0-9_]+)\s*\(", text))
+    return sorted(syms)
 
 
 def test_header_declares_the_tnlp_callbacks():
@@ -26,7 +31,8 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(ab.LIB_PATH)
     missing = [s for s in declared_symbols() if not hasattr(L, s)]
     assert not missing, missing
-    assert sorted(ab.EXPORTS) == declared_symbols()
+    from armour_b200 import controller
+    assert sorted(ab.EXPORTS + controller.EXPORTS) == declared_symbols()
 
 
 def test_default_config_matches_reference_macros():
