@@ -22,6 +22,7 @@
 
 #include <cctype>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -36,6 +37,9 @@ int capi_fail(int code, const std::string& msg);   // armour_capi.cu: sets armou
 
 namespace ctrl {
 constexpr int MAXJ = ARMOUR_CONTROLLER_MAX_JOINTS;
+#ifndef CTRL_MINB
+#define CTRL_MINB 4
+#endif
 
 // ---- scalar adaptors: S is double or Itv ---------------------------------------------------------------------
 template <class S> __device__ __forceinline__ S cst(double v);
@@ -304,7 +308,7 @@ struct UpdateArgs {
 
 // RobustController::update (KRC/robust_controller.cpp:62-171), one sample per thread
 template <bool ARMOUR_METHOD>
-__global__ void __launch_bounds__(128) controller_update_kernel(const __grid_constant__ ControllerModel M, const __grid_constant__ UpdateArgs A) {
+__global__ void __launch_bounds__(128, CTRL_MINB) controller_update_kernel(const __grid_constant__ ControllerModel M, const __grid_constant__ UpdateArgs A) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.count) return;
     const int n = M.n;
@@ -313,6 +317,7 @@ __global__ void __launch_bounds__(128) controller_update_kernel(const __grid_con
     double qa_d[MAXJ], qa_dd[MAXJ], r[MAXJ], un[MAXJ];
     Itv ui[MAXJ], Mr[MAXJ];
     double r_sq = 0;
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
         const double q_diff = wrap_pi(A.qd[o + i] - q[i]);
         const double e_d = A.qd_d[o + i] - q_d[i];
@@ -326,6 +331,7 @@ __global__ void __launch_bounds__(128) controller_update_kernel(const __grid_con
     rnea_chain<Itv, ARMOUR_METHOD>(M, M.unc, M.neg_gravity_itv, true, false, q, q_d, qa_d, qa_dd, r, ui, Mr);
     bool outside = false;
     double bound_sq = 0;
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
         outside |= (un[i] > ui[i].hi) || (un[i] < ui[i].lo);
         const Itv phi = ui[i] - cst<Itv>(un[i]);
@@ -341,12 +347,14 @@ __global__ void __launch_bounds__(128) controller_update_kernel(const __grid_con
         r_norm = sqrt(r_sq);
         active = r_norm > A.par[2];
         Itv V = cst<Itv>(0.0);
+#pragma unroll 1
         for (int i = 0; i < n; i++) V = V + (0.5 * r[i]) * Mr[i];
         V_sup = active ? V.hi : 0.0;
         const double h = -V_sup + A.par[1];
         lambda = fmax(0.0, -A.par[0] * h / r_norm + bound_norm);
         if (A.V_sup) A.V_sup[s] = V_sup;
     }
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
         double vi;
         if (ARMOUR_METHOD) vi = active ? -lambda * r[i] / r_norm : 0.0;
@@ -469,10 +477,20 @@ static int launch_update(armour_controller* c, int method, int count, const doub
     A.V_sup = want_V ? c->d_out + 5 * N : nullptr;
     A.outside = c->d_outside;
     CK(cudaMemsetAsync(c->d_outside, 0, sizeof(int), c->stream));
-    const int threads = 128, blocks = (count + threads - 1) / threads;
+    // ARMOUR_TUNE_CTRL_THREADS / ARMOUR_TUNE_CTRL_SMEM: tuning knobs (block size; dummy dynamic shared memory that
+    // caps the resident blocks per SM so the thread-local working set stays in L1/L2)
+    static const int threads = getenv("ARMOUR_TUNE_CTRL_THREADS") ? atoi(getenv("ARMOUR_TUNE_CTRL_THREADS")) : 128;
+    static const int smem = getenv("ARMOUR_TUNE_CTRL_SMEM") ? atoi(getenv("ARMOUR_TUNE_CTRL_SMEM")) : 0;
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        CK(cudaFuncSetAttribute(controller_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(controller_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    attr_set = true;
+    const int blocks = (count + threads - 1) / threads;
     CK(cudaEventRecord(c->ev0, c->stream));
-    if (method == 0) controller_update_kernel<true><<<blocks, threads, 0, c->stream>>>(c->model, A);
-    else controller_update_kernel<false><<<blocks, threads, 0, c->stream>>>(c->model, A);
+    if (method == 0) controller_update_kernel<true><<<blocks, threads, smem, c->stream>>>(c->model, A);
+    else controller_update_kernel<false><<<blocks, threads, smem, c->stream>>>(c->model, A);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev1, c->stream));
     return ARMOUR_OK;

@@ -789,7 +789,7 @@ size_t reach_gmem_bytes(int ncap) { return Scratch::gmem_bytes(ncap); }
 typedef void (*ReachKernel)(Tables, char*, size_t, int, int, int, int, int);
 static ReachKernel pick_reach_kernel(int nt, int minb, int groups) {
     if (groups == 2) return reach_build_kernel<256, 1, 2>;
-    if (nt == 128) return minb >= 4 ? reach_build_kernel<128, 4, 1> : reach_build_kernel<128, 2, 1>;
+    if (nt == 128) return minb >= 8 ? reach_build_kernel<128, 8, 1> : minb >= 6 ? reach_build_kernel<128, 6, 1> : minb >= 4 ? reach_build_kernel<128, 4, 1> : reach_build_kernel<128, 2, 1>;
     if (nt == 512) return reach_build_kernel<512, 1, 1>;
     return minb >= 2 ? reach_build_kernel<256, 2, 1> : reach_build_kernel<256, 1, 1>;
 }

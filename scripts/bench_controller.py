@@ -10,6 +10,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "armour-dev_b200"), os.path.join(ROOT, "tests")]
 import armour_b200 as ab
+if os.environ.get("ARMOUR_TUNE_LIB"):   # tuning builds
+    ab.LIB_PATH = os.path.join(ab.PKG_DIR, os.environ["ARMOUR_TUNE_LIB"])
 from armour_b200.controller import RobustController
 import _oracle
 from test_controller import states, MODEL, KR, ALPHA, V_MAX, R_THR

@@ -28,9 +28,9 @@ class OracleConfig(C.Structure):
 
 
 def build_oracle(force=False):
-    src = [os.path.join(ORACLE_DIR, f) for f in ("oracle_armour.cpp", "oracle_controller.cpp", "oracle_pz.hpp", "Makefile")]
+    src = [os.path.join(ORACLE_DIR, f) for f in ("oracle_armour.cpp", "oracle_controller.cpp", "oracle_pz.hpp", "oracle_interval.hpp", "Makefile")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
-        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "liboracle.so"])
     return LIB_PATH
 
 
@@ -308,3 +308,84 @@ class OracleController:
             out = np.zeros(self.n)
             lib().oracle_controller_rnea(self._h, *[_dp(x) for x in a], C.c_int(1 if gravity else 0), _dp(out))
         return out
+
+
+REF_LIB_PATH = os.path.join(ORACLE_DIR, "_ref", "libref.so")
+REFERENCE_TREE = "/root/reference/kinova_src/kinova_simulator_interfaces/kinova_planner_realtime"
+
+
+def reference_available():
+    """oracle/_ref/libref.so = the reference's own PZsparse/Trajectory/Dynamics sources compiled against the stand-in
+    Eigen/Boost headers (oracle/Makefile target ref).  Built here when /root/reference is present; on the GPU box only
+    the prebuilt file is used."""
+    if os.path.isdir(REFERENCE_TREE):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "ref"])
+    return os.path.exists(REF_LIB_PATH)
+
+
+class Reference:
+    """The reference's own reach-set build (KPR/armour_main.cu:94-205 call sequence) through oracle/ref_driver.cpp.
+    T, k_range and the thresholds are the reference's compile-time values (T = 128, pi/48, 5e-4)."""
+
+    def __init__(self, num_threads=None):
+        self.L = C.CDLL(REF_LIB_PATH)
+        self.L.ref_build.restype = C.c_void_p
+        self.L.ref_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        self.L.ref_destroy.argtypes = [C.c_void_p]
+        self.L.ref_get_pz.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+        self.L.ref_get_torque_radius.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.ref_get_link_generators.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.ref_slice.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L.ref_k_range.restype = C.c_double
+        self.T = self.L.ref_num_time_steps()
+        self.k_range = np.array([self.L.ref_k_range(i) for i in range(NF)])
+        self.num_threads = num_threads or len(os.sched_getaffinity(0))
+        self.h = None
+
+    def build(self, q0, qd0, qdd0):
+        self.close()
+        a = [np.ascontiguousarray(np.asarray(x, dtype=np.float64)) for x in (q0, qd0, qdd0)]
+        h = self.L.ref_build(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, self.num_threads)
+        if not h:
+            raise RuntimeError("the reference build threw")
+        self.h = C.c_void_p(h)
+
+    def close(self):
+        if self.h:
+            self.L.ref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def get_pz(self, which, idx, s):
+        w = TABLES[which] if isinstance(which, str) else which
+        dims = np.zeros(2, dtype=np.int32)
+        idx, s = int(idx), int(s)
+        n = self.L.ref_get_pz(self.h, w, idx, s, dims.ctypes.data, None, None, None, None)
+        dim = int(dims[0] * dims[1])
+        keys = np.zeros(max(n, 1), dtype=np.uint64)
+        coeffs = np.zeros((max(n, 1), dim))
+        center, indep = np.zeros(dim), np.zeros(dim)
+        self.L.ref_get_pz(self.h, w, idx, s, dims.ctypes.data, keys.ctypes.data, coeffs.ctypes.data, center.ctypes.data, indep.ctypes.data)
+        return dict(rows=int(dims[0]), cols=int(dims[1]), keys=keys[:n], coeffs=coeffs[:n], center=center, independent=indep)
+
+    def torque_radius(self):
+        out = np.zeros(self.T * NF)
+        self.L.ref_get_torque_radius(self.h, out.ctypes.data)
+        return out.reshape(self.T, NF)
+
+    def link_generators(self):
+        out = np.zeros(self.T * NJ * 18)
+        self.L.ref_get_link_generators(self.h, out.ctypes.data)
+        return out.reshape(self.T, NJ, 6, 3).transpose(0, 1, 3, 2)
+
+    def slice(self, which, idx, s, k):
+        w = TABLES[which] if isinstance(which, str) else which
+        k = np.ascontiguousarray(np.asarray(k, dtype=np.float64))
+        lo, hi = np.zeros(9), np.zeros(9)
+        n = self.L.ref_slice(self.h, w, int(idx), int(s), k.ctypes.data, lo.ctypes.data, hi.ctypes.data)
+        return lo[:n], hi[:n]

@@ -1,0 +1,119 @@
+"""Pins the oracle (and, on the GPU box, the device path) against THE REFERENCE'S OWN CODE.
+
+oracle/_ref/libref.so is the reference's PZsparse.cu / Trajectory.cu / Dynamics.cu compiled unmodified from
+/root/reference (oracle/Makefile target `ref`) against minimal stand-in Eigen / Boost.Interval headers (oracle/shim —
+neither library is installed here); oracle/ref_driver.cpp replays the call sequence of the reference's main
+(KPR/armour_main.cu:94-205).  Every PZ operation, simplify/reduce decision, Bezier bound and RNEA step that runs is
+the reference's; the third-party arithmetic underneath (coefficient-order of small Eigen products, Eigen's norm()
+association, Boost's directed rounding) is the stand-in's restatement.
+
+The reference's sizes are compile-time (T = 128, k_range = pi/48, 3 % uncertainty), i.e. BASELINE.json configs[1].
+Bar: monomial keys bit-exact; coefficients, centres, radii within 1e-12 relative (the reference sorts monomials with
+std::sort, the oracle with std::stable_sort, so equal-key terms may be summed in a different order)."""
+import numpy as np
+import pytest
+
+import _oracle
+from problems import make_problem, DEBUG_Q0, DEBUG_QD0, DEBUG_QDD0, DEBUG_K
+
+pytestmark = pytest.mark.skipif(not _oracle.reference_available(), reason="oracle/_ref/libref.so not built and /root/reference absent")
+
+TOL = 1e-12
+
+
+def close(a, b, tol=TOL):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = max(1.0, float(np.abs(b).max(initial=0.0)))
+    return bool(np.all(np.abs(a - b) <= tol * scale))
+
+
+def compare_tables(ref, other, T, steps, names=tuple(_oracle.TABLES), tol=TOL):
+    checked = 0
+    for name in names:
+        for s in steps:
+            for j in range(7):
+                a, b = ref.get_pz(name, j, s), other.get_pz(name, j, s)
+                assert np.array_equal(a["keys"], b["keys"]), (name, j, s, len(a["keys"]), len(b["keys"]))
+                assert close(b["coeffs"], a["coeffs"], tol), (name, j, s)
+                assert close(b["center"], a["center"], tol), (name, j, s)
+                assert close(b["independent"], a["independent"], tol), (name, j, s)
+                checked += len(a["keys"])
+    return checked
+
+
+@pytest.fixture(scope="module")
+def debug_case():
+    """KPR/PZ_tests.cu's hard-coded state."""
+    ref = _oracle.Reference()
+    ref.build(DEBUG_Q0, DEBUG_QD0, DEBUG_QDD0)
+    o = _oracle.Oracle(T=ref.T, num_threads=ref.num_threads)
+    o.build(DEBUG_Q0, DEBUG_QD0, DEBUG_QDD0, np.zeros((0, 12)))
+    return ref, o
+
+
+def test_reference_constants_are_the_defaults(debug_case):
+    ref, _ = debug_case
+    assert ref.T == 128
+    assert np.all(ref.k_range == np.pi / 48)
+
+
+def test_oracle_reach_sets_equal_the_reference(debug_case):
+    ref, o = debug_case
+    n = compare_tables(ref, o, ref.T, range(ref.T))
+    assert n > 20000   # monomials compared
+
+
+def test_oracle_torque_radius_and_link_generators_equal_the_reference(debug_case):
+    ref, o = debug_case
+    assert close(o.torque_radius(), ref.torque_radius())
+    assert close(o.link_generators(), ref.link_generators())
+
+
+def test_oracle_slices_equal_the_reference(debug_case):
+    """armtd_NLP::eval_g's torque rows and link centres are PZsparse::slice of the tables (KPR/NLPclass.cu:289-309)."""
+    ref, o = debug_case
+    g = o.eval_g(DEBUG_K)
+    centers = o.link_sliced_center()
+    for t in range(0, ref.T, 7):
+        for j in range(7):
+            lo, hi = ref.slice("u_nom", j, t, DEBUG_K)
+            assert abs(g[t * 7 + j] - 0.5 * (lo[0] + hi[0])) <= TOL * max(1.0, abs(g[t * 7 + j]))
+            lo, hi = ref.slice("links", j, t, DEBUG_K)
+            assert close(centers[t, j], 0.5 * (lo + hi))
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_oracle_equals_the_reference_on_random_states(seed):
+    q0, qd0, qdd0, _, _ = make_problem(seed, 0)
+    ref = _oracle.Reference()
+    ref.build(q0, qd0, qdd0)
+    o = _oracle.Oracle(T=ref.T, num_threads=ref.num_threads)
+    o.build(q0, qd0, qdd0, np.zeros((0, 12)))
+    compare_tables(ref, o, ref.T, range(0, ref.T, 3))
+    assert close(o.torque_radius(), ref.torque_radius())
+    assert close(o.link_generators(), ref.link_generators())
+
+
+@pytest.mark.gpu
+def test_device_reach_sets_equal_the_reference():
+    """The CUDA path against the reference's own code, no oracle in between.  Radii: the device rounds outward, so
+    they contain the reference's and exceed them by less than 1e-9 (north_star tolerance)."""
+    import armour_b200 as ab
+    for seed in (None, 21):
+        q0, qd0, qdd0 = (DEBUG_Q0, DEBUG_QD0, DEBUG_QDD0) if seed is None else make_problem(seed, 0)[:3]
+        ref = _oracle.Reference()
+        ref.build(q0, qd0, qdd0)
+        p = ab.Planner(T=ref.T, device=0)
+        p.build(q0, qd0, qdd0, np.zeros((0, 12)))
+        for name in _oracle.TABLES:
+            for s in range(0, ref.T, 5):
+                for j in range(7):
+                    a, b = ref.get_pz(name, j, s), p.get_pz(name, j, s)
+                    assert np.array_equal(a["keys"], b["keys"]), (name, j, s)
+                    assert close(b["coeffs"], a["coeffs"], 1e-9) and close(b["center"], a["center"], 1e-9)
+                    assert np.all(b["independent"] >= a["independent"] - 1e-12 * np.maximum(1.0, np.abs(a["independent"])))
+                    assert close(b["independent"], a["independent"], 1e-9)
+        tr_ref, tr = ref.torque_radius(), p.torque_radius()
+        assert np.all(tr >= tr_ref - 1e-12) and close(tr, tr_ref, 1e-9)
+        assert close(p.link_generators(), ref.link_generators(), 1e-9)
+        p.close()
