@@ -3,7 +3,7 @@
 (Kinova Gen3 single plan, T = 128 intervals, 20 obstacles, one fused eval_g/eval_jac_g per build).
 
   python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
-  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port)
+  python bench.py --impl reference --steps K --warmup W    # the reference itself (oracle/_ref, else the oracle port) on the host cores
 
 A "step" is one pass of the hot path for one planning problem: stages A-D of the reference's main()
 (KPR/armour_main.cu:89-226: joint reach sets, PZ forward kinematics, PZ-RNEA nominal+interval, torque radius,
@@ -122,24 +122,46 @@ def eval_algorithmic_bytes(m):
     return table + sliceable + outputs
 
 
-def run_reference(args):
-    """The reference algorithm (CPU restatement in oracle/, the original needs Boost/Eigen/Ipopt which the image
-    lacks) on the box's host cores, all threads, same workload / metric / unit."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def reference_runner(cores):
+    """Callable timing one step (build + eval_g + eval_jac_g) of the reference arm, plus how to describe it.
+    Preferred: oracle/_ref/libref_cuda.so = the reference's OWN sources (PZsparse/Trajectory/Dynamics on the host cores with
+    OpenMP, its CollisionChecking kernels and armtd_NLP callbacks) compiled unmodified against stand-in Eigen/Boost/Ipopt
+    headers (oracle/Makefile target ref).  Fallback: the oracle port."""
+    import torch
     import _oracle
-    cores = len(os.sched_getaffinity(0))   # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+    if os.path.exists(_oracle.REF_CUDA_LIB_PATH) and T == 128 and torch.cuda.is_available():
+        ref = _oracle.ReferenceCuda(num_threads=cores)
+
+        def step(q0, qd0, qdd0, obs, x):
+            t0 = time.perf_counter()
+            ref.build(q0, qd0, qdd0, q0, obs)
+            ref.eval_g(x)
+            ref.eval_jac_g(x)
+            return time.perf_counter() - t0
+        return step, "reference", ("the reference's own sources (oracle/_ref, stand-in Eigen/Boost/Ipopt headers): reach sets on %d host threads "
+                                   "(OpenMP over time intervals, KPR/armour_main.cu:100,118), its half-space / plane-test kernels on the GPU as in the reference" % cores)
     o = _oracle.Oracle(T=T, num_threads=cores)
-    times = []
-    for step in range(args.warmup + args.steps):
-        q0, qd0, qdd0, _, obs = problem_for(0, step)
-        x = x_for(0, step)
+
+    def step(q0, qd0, qdd0, obs, x):
         t0 = time.perf_counter()
         o.build(q0, qd0, qdd0, obs)
         o.eval_g(x)
         o.eval_jac_g(x)
-        dt = time.perf_counter() - t0
+        return time.perf_counter() - t0
+    return step, "port", "oracle port of the reference algorithm on %d host threads (OpenMP over time intervals like KPR/armour_main.cu:100,118)" % cores
+
+
+def run_reference(args):
+    """The reference on the box's host cores, all threads, same workload / metric / unit (see reference_runner)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))   # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+    step_fn, kind, how = reference_runner(cores)
+    times = []
+    for step in range(args.warmup + args.steps):
+        q0, qd0, qdd0, _, obs = problem_for(0, step)
+        dt = step_fn(q0, qd0, qdd0, obs, x_for(0, step))
         if step >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
@@ -148,8 +170,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "time_intervals": T, "obstacles": N_OBS},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d full steps (1 build + eval_g + eval_jac_g each), OpenMP over time intervals like KPR/armour_main.cu:100,118" % args.steps},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "%d full steps (1 build + eval_g + eval_jac_g each); %s" % (args.steps, how)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -286,9 +308,10 @@ def run_ours(args):
         fp64_peak = ab.measure_fp64_peak(local_rank)
         # algorithmic flops per build: the oracle's op counter on the reference op sequence
         import _oracle
-        flops, cpu_t = [], []
+        flops, cpu_t, port_t = [], [], []
         cores = len(os.sched_getaffinity(0))
         o = _oracle.Oracle(T=T, num_threads=cores)
+        ref_step, ref_kind, ref_how = reference_runner(cores) if world == 1 else (None, None, None)
         n_sample = 0
         t_budget = time.perf_counter()
         for s in range(W, W + K):
@@ -296,10 +319,12 @@ def run_ours(args):
             t0 = time.perf_counter()
             o.build(q0, qd0, qdd0, obs)
             o.eval_g(xs[s]); o.eval_jac_g(xs[s])
-            cpu_t.append(time.perf_counter() - t0)
+            port_t.append(time.perf_counter() - t0)
             flops.append(o.op_stats()["flops"])
+            if ref_step is not None:
+                cpu_t.append(ref_step(q0, qd0, qdd0, obs, xs[s]))
             n_sample += 1
-            if time.perf_counter() - t_budget > 15.0:
+            if time.perf_counter() - t_budget > 20.0:
                 break
         flops_per_build = float(np.mean(flops))
         reach_mean_ms = float(np.mean(reach_ms))
@@ -327,8 +352,9 @@ def run_ours(args):
         }
         if world == 1:
             cpu_ms = 1e3 * float(np.mean(cpu_t))
-            line["cpu_baseline"] = {"value": 1e3 / cpu_ms, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": cpu_ms,
-                                    "sample": "%d of the timed steps (same problems), 1 build + eval_g + eval_jac_g each, OpenMP over time intervals" % n_sample}
+            line["cpu_baseline"] = {"value": 1e3 / cpu_ms, "unit": UNIT, "cores": cores, "kind": ref_kind, "ms_per_step": cpu_ms,
+                                    "sample": "%d of the timed steps (same problems), 1 build + eval_g + eval_jac_g each; %s" % (n_sample, ref_how),
+                                    "oracle_port_ms_per_step": 1e3 * float(np.mean(port_t))}
         if extra_sweep:
             line["sweep"] = extra_sweep
         line.update(extra)

@@ -389,3 +389,76 @@ class Reference:
         lo, hi = np.zeros(9), np.zeros(9)
         n = self.L.ref_slice(self.h, w, int(idx), int(s), k.ctypes.data, lo.ctypes.data, hi.ctypes.data)
         return lo[:n], hi[:n]
+
+
+REF_CUDA_LIB_PATH = os.path.join(ORACLE_DIR, "_ref", "libref_cuda.so")
+
+
+class ReferenceCuda:
+    """The reference's complete path, its own CUDA kernels and TNLP callbacks included (oracle/ref_cuda_driver.cu over
+    KPR/*.cu built by nvcc).  Needs a GPU.  Method names follow armtd_NLP."""
+
+    def __init__(self, num_threads=None):
+        self.L = C.CDLL(REF_CUDA_LIB_PATH)
+        self.L.refcuda_build.restype = C.c_void_p
+        self.L.refcuda_build.argtypes = [C.c_void_p] * 4 + [C.c_double, C.c_void_p, C.c_int, C.c_int]
+        self.L.refcuda_destroy.argtypes = [C.c_void_p]
+        self.num_threads = num_threads or len(os.sched_getaffinity(0))
+        self.h = None
+
+    def build(self, q0, qd0, qdd0, q_des, obstacles, t_plan=0.5):
+        self.close()
+        a = [np.ascontiguousarray(np.asarray(x, dtype=np.float64)) for x in (q0, qd0, qdd0, q_des)]
+        obs = np.ascontiguousarray(np.asarray(obstacles, dtype=np.float64).reshape(-1, 12))
+        h = self.L.refcuda_build(*[x.ctypes.data for x in a], float(t_plan), obs.ctypes.data if obs.size else None, obs.shape[0], self.num_threads)
+        if not h:
+            raise RuntimeError("the reference build failed")
+        self.h = C.c_void_p(h)
+        n, m, a_, b_ = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        assert self.L.refcuda_get_nlp_info(self.h, C.byref(n), C.byref(m), C.byref(a_), C.byref(b_)) == 0
+        self.n, self.m, self.nnz_jac_g = n.value, m.value, a_.value
+
+    def close(self):
+        if self.h:
+            self.L.refcuda_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def get_bounds_info(self):
+        xl, xu, gl, gu = np.zeros(self.n), np.zeros(self.n), np.zeros(self.m), np.zeros(self.m)
+        assert self.L.refcuda_get_bounds_info(self.h, self.n, self.m, _dp(xl), _dp(xu), _dp(gl), _dp(gu)) == 0
+        return xl, xu, gl, gu
+
+    def get_starting_point(self):
+        x = np.zeros(self.n)
+        assert self.L.refcuda_get_starting_point(self.h, self.n, self.m, _dp(x)) == 0
+        return x
+
+    def eval_f(self, x):
+        f, g = C.c_double(), np.zeros(self.n)
+        assert self.L.refcuda_eval_f(self.h, _dp(_vec(x, 7)), C.byref(f), _dp(g)) == 0
+        return f.value, g
+
+    def eval_g(self, x):
+        g = np.zeros(self.m)
+        assert self.L.refcuda_eval_g(self.h, _dp(_vec(x, 7)), self.m, _dp(g)) == 0
+        return g
+
+    def eval_jac_g(self, x):
+        v = np.zeros(self.m * 7)
+        assert self.L.refcuda_eval_jac_g(self.h, _dp(_vec(x, 7)), self.m, _dp(v)) == 0
+        return v.reshape(self.m, 7)
+
+    def check_feasible(self, x, g):
+        g = np.ascontiguousarray(np.asarray(g, dtype=np.float64))
+        return bool(self.L.refcuda_check_feasible(self.h, _dp(_vec(x, 7)), self.m, _dp(g)))
+
+    def link_sliced_center(self):
+        out = np.zeros(128 * NJ * 3)
+        self.L.refcuda_get_link_sliced_center(self.h, _dp(out))
+        return out.reshape(128, NJ, 3)

