@@ -14,8 +14,9 @@
 //   KPR/CollisionChecking.cu:26-39,136-299  pair table, bufferObstacles, polytope_PH, checkCollision
 //   KPR/NLPclass.cu:30-538                  TNLP callbacks
 //
-// PARITY UNPINNED: no golden vectors exist in the reference and it cannot be built here
-// (Boost, Eigen, Ipopt, HSL, MATLAB absent).  See oracle/README.md.
+// PARITY: pinned against the reference's own sources compiled here against stand-in Eigen / Boost / Ipopt headers
+// (oracle/_ref, tests/test_reference_pin.py); the ARMTD comparison mode (build_armtd) is pinned by properties only.
+// See oracle/README.md.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library.

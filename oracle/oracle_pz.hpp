@@ -12,10 +12,9 @@
 //   KPR/PZsparse.cu:678-1167  arithmetic, transpose, addOneDimPZ, stack, cross
 //   KPR/Headers.h:26-36       Boost.Interval policy (rounded_transc_std + save_state)
 //
-// PARITY UNPINNED: the reference ships no golden vectors for this path and its
-// dependencies (Boost.Interval, Eigen 3.3.7, Ipopt) are absent from this image, so
-// the restatement cannot be checked against the reference binary.  It is pinned by
-// property tests instead (tests/test_oracle_properties.py).
+// PARITY: pinned against the reference's own sources compiled here (oracle/_ref, see oracle/README.md and
+// tests/test_reference_pin.py: keys bit-exact, values <= 2e-15 at T = 128).  Boost.Interval and Eigen 3.3.7 are absent
+// from this image; their arithmetic is restated (here and in oracle/shim), which is the one thing _ref cannot pin.
 //
 // Design notes (kept deliberately close to the reference so that it is an honest
 // CPU baseline): one heap-allocated coefficient matrix per monomial, range-for by
