@@ -462,3 +462,85 @@ class ReferenceCuda:
         out = np.zeros(128 * NJ * 3)
         self.L.refcuda_get_link_sliced_center(self.h, _dp(out))
         return out.reshape(128, NJ, 3)
+
+
+REF_ARMTD_LIB_PATH = os.path.join(ORACLE_DIR, "_ref", "libref_armtd_cuda.so")
+
+
+class ReferenceArmtd:
+    """The reference's ARMTD comparison planner (KPA/*.cu built by nvcc, oracle/ref_armtd_driver.cu).  Needs a GPU."""
+
+    def __init__(self, num_threads=None):
+        self.L = C.CDLL(REF_ARMTD_LIB_PATH)
+        self.L.refarmtd_build.restype = C.c_void_p
+        self.L.refarmtd_build.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int]
+        self.L.refarmtd_destroy.argtypes = [C.c_void_p]
+        self.L.refarmtd_get_pz.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+        self.L.refarmtd_get_link_generators.argtypes = [C.c_void_p, C.c_void_p]
+        self.T = self.L.refarmtd_num_time_steps()
+        self.num_threads = num_threads or len(os.sched_getaffinity(0))
+        self.h = None
+
+    def build(self, q0, qd0, jrs, k_range, q_des, obstacles):
+        self.close()
+        a = [np.ascontiguousarray(np.asarray(x, dtype=np.float64)) for x in (q0, qd0, jrs, k_range, q_des)]
+        assert a[2].size == 6 * 7 * self.T
+        obs = np.ascontiguousarray(np.asarray(obstacles, dtype=np.float64).reshape(-1, 12))
+        h = self.L.refarmtd_build(*[x.ctypes.data for x in a], obs.ctypes.data if obs.size else None, obs.shape[0], self.num_threads)
+        if not h:
+            raise RuntimeError("the reference build failed")
+        self.h = C.c_void_p(h)
+        n, m, a_, b_ = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        assert self.L.refarmtd_get_nlp_info(self.h, C.byref(n), C.byref(m), C.byref(a_), C.byref(b_)) == 0
+        self.n, self.m, self.nnz_jac_g = n.value, m.value, a_.value
+
+    def close(self):
+        if self.h:
+            self.L.refarmtd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def get_pz(self, which, idx, s):
+        w = TABLES[which] if isinstance(which, str) else which
+        dims = np.zeros(2, dtype=np.int32)
+        n = self.L.refarmtd_get_pz(self.h, w, int(idx), int(s), dims.ctypes.data, None, None, None, None)
+        dim = int(dims[0] * dims[1])
+        keys = np.zeros(max(n, 1), dtype=np.uint64)
+        coeffs = np.zeros((max(n, 1), dim))
+        center, indep = np.zeros(dim), np.zeros(dim)
+        self.L.refarmtd_get_pz(self.h, w, int(idx), int(s), dims.ctypes.data, keys.ctypes.data, coeffs.ctypes.data, center.ctypes.data, indep.ctypes.data)
+        return dict(rows=int(dims[0]), cols=int(dims[1]), keys=keys[:n], coeffs=coeffs[:n], center=center, independent=indep)
+
+    def link_generators(self):
+        out = np.zeros(self.T * NJ * 18)
+        self.L.refarmtd_get_link_generators(self.h, out.ctypes.data)
+        return out.reshape(self.T, NJ, 6, 3).transpose(0, 1, 3, 2)
+
+    def get_bounds_info(self):
+        xl, xu, gl, gu = np.zeros(self.n), np.zeros(self.n), np.zeros(self.m), np.zeros(self.m)
+        assert self.L.refarmtd_get_bounds_info(self.h, self.n, self.m, _dp(xl), _dp(xu), _dp(gl), _dp(gu)) == 0
+        return xl, xu, gl, gu
+
+    def eval_f(self, x):
+        f, g = C.c_double(), np.zeros(self.n)
+        assert self.L.refarmtd_eval_f(self.h, _dp(_vec(x, 7)), C.byref(f), _dp(g)) == 0
+        return f.value, g
+
+    def eval_g(self, x):
+        g = np.zeros(self.m)
+        assert self.L.refarmtd_eval_g(self.h, _dp(_vec(x, 7)), self.m, _dp(g)) == 0
+        return g
+
+    def eval_jac_g(self, x):
+        v = np.zeros(self.m * 7)
+        assert self.L.refarmtd_eval_jac_g(self.h, _dp(_vec(x, 7)), self.m, _dp(v)) == 0
+        return v.reshape(self.m, 7)
+
+    def check_feasible(self, x, g):
+        g = np.ascontiguousarray(np.asarray(g, dtype=np.float64))
+        return bool(self.L.refarmtd_check_feasible(self.h, _dp(_vec(x, 7)), self.m, _dp(g)))

@@ -159,3 +159,44 @@ def test_device_tnlp_callbacks_equal_the_reference(seed, n_obs):
         assert p.check_feasible(g) == ref.check_feasible(k, g_ref)
         assert close(p.link_sliced_center(), ref.link_sliced_center(), 1e-9)
     p.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n_obs", [(41, 8), (42, 20)])
+def test_device_armtd_mode_equals_the_reference_comparison_planner(seed, n_obs):
+    """armour_build_armtd against the reference's own ARMTD comparison planner (KPA/*.cu, T = 100,
+    its CUDA kernels on this GPU): R / R_t / link tables, generator blocks, bounds, constraints, Jacobian, verdict."""
+    import os
+    import armour_b200 as ab
+    from problems import make_jrs_tables
+    if not os.path.exists(_oracle.REF_ARMTD_LIB_PATH):
+        pytest.skip("oracle/_ref/libref_armtd_cuda.so not built")
+    ref = _oracle.ReferenceArmtd()
+    T = ref.T
+    k_range = np.array([np.pi / 24] * 7)
+    q0, qd0, _, q_des, obs = make_problem(seed, n_obs)
+    jrs = make_jrs_tables(qd0, k_range, T)
+    ref.build(q0, qd0, jrs, k_range, q_des, obs)
+    p = ab.Planner(T=T, device=0)
+    p.build_armtd(q0, qd0, jrs, k_range, obs)
+    assert p.get_nlp_info()[:3] == (ref.n, ref.m, ref.nnz_jac_g)
+    for name in ("R", "R_t", "links"):
+        for s in range(0, T, 7):
+            for j in range(7):
+                a, b = ref.get_pz(name, j, s), p.get_pz(name, j, s)
+                assert np.array_equal(a["keys"], b["keys"]), (name, j, s)
+                assert close(b["coeffs"], a["coeffs"], 1e-9) and close(b["center"], a["center"], 1e-9)
+                assert np.all(b["independent"] >= a["independent"] - 1e-12) and close(b["independent"], a["independent"], 1e-9)
+    assert close(p.link_generators(), ref.link_generators(), 1e-9)
+    for a, b in zip(p.get_bounds_info(), ref.get_bounds_info()):
+        assert close(a, b, 1e-9)
+    rng = np.random.default_rng(6)
+    for k in (DEBUG_K, np.zeros(7), rng.uniform(-1, 1, 7)):
+        g_ref, J_ref = ref.eval_g(k), ref.eval_jac_g(k)
+        g, J = p.eval_g_jac(k)
+        J = J.reshape(-1, 7)
+        assert close(g, g_ref, 1e-8), float(np.abs(g - g_ref).max())
+        bad = np.abs(J - J_ref).max(axis=1) > 1e-8 * max(1.0, float(np.abs(J_ref).max()))
+        assert bad.sum() <= 2, int(bad.sum())
+        assert p.check_feasible(g) == ref.check_feasible(k, g_ref)
+    p.close()
