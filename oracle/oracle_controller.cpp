@@ -9,10 +9,10 @@
 //   KRC/robust_controller.cpp:62-171                       RobustController::update, both robust-input methods
 //   KRC/kinova_controller.cpp:15-84, kinova_controller_ALTHOFF.cpp:15-90   the two MEX entry points
 //
-// PARITY UNPINNED, like the rest of oracle/: Eigen and Boost are not in this image, the reference ships no
-// recorded controller outputs.  Pinned by properties instead (tests/test_controller.py): the nominal torque
-// equals an independent numeric RNEA of the planner's robot constants, the interval torque encloses the torque of
-// sampled models inside the uncertainty box, M(q) r from the interval pass encloses the numeric mass matrix.
+// PARITY: pinned against the reference's own KRC sources compiled against the stand-in Eigen / Boost headers
+// (oracle/_ref/libref_controller.so, tests/test_reference_pin.py: u_nominal and the interval RNEA bit-identical, u and v
+// within 7e-15), and by properties (tests/test_controller.py): the nominal torque equals an independent numeric RNEA of
+// the planner's robot constants, the interval torque encloses the torque of sampled models inside the uncertainty box.
 //
 // The spatial algebra is written once over the scalar type (double or orc::Interval); Eigen's evaluation order
 // for 3-vectors / 3x3 matrices is followed (sums in ascending index order, products before sums).

@@ -27,6 +27,7 @@ inline double sub_up(double a, double b) { fesetround(FE_UPWARD);   volatile dou
 inline double mul_dn(double a, double b) { fesetround(FE_DOWNWARD); volatile double r = a * b; return r; }
 inline double mul_up(double a, double b) { fesetround(FE_UPWARD);   volatile double r = a * b; return r; }
 inline double div_dn(double a, double b) { fesetround(FE_DOWNWARD); volatile double r = a / b; return r; }
+inline double div_up(double a, double b) { fesetround(FE_UPWARD);   volatile double r = a / b; return r; }
 inline double cos_dn(double a) { fesetround(FE_DOWNWARD); volatile double r = std::cos(a); return r; }
 inline double cos_up(double a) { fesetround(FE_UPWARD);   volatile double r = std::cos(a); return r; }
 inline double sqrt_dn(double a) { fesetround(FE_DOWNWARD); volatile double r = std::sqrt(a); return r; }

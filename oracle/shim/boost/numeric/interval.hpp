@@ -41,6 +41,15 @@ template <class T, class P> ITV operator-(const ITV& a) { return ITV(-a.raw()); 
 template <class T, class P> ITV operator*(const ITV& a, const ITV& b) { return ITV(a.raw() * b.raw()); }
 template <class T, class P> ITV operator*(const ITV& a, const T& b) { return ITV(b * a.raw()); }
 template <class T, class P> ITV operator*(const T& a, const ITV& b) { return ITV(a * b.raw()); }
+// division by an interval that does not contain zero (only reached through Eigen's normalize(), which the controller
+// path compiles but never calls)
+template <class T, class P> ITV operator/(const ITV& a, const ITV& b) {
+    if (b.lower() <= 0 && b.upper() >= 0) throw "interval division by an interval containing zero";
+    orc::RoundGuard g;
+    const T l = std::min(std::min(orc::div_dn(a.lower(), b.lower()), orc::div_dn(a.lower(), b.upper())), std::min(orc::div_dn(a.upper(), b.lower()), orc::div_dn(a.upper(), b.upper())));
+    const T u = std::max(std::max(orc::div_up(a.lower(), b.lower()), orc::div_up(a.lower(), b.upper())), std::max(orc::div_up(a.upper(), b.lower()), orc::div_up(a.upper(), b.upper())));
+    return ITV(l, u);
+}
 template <class T, class P> ITV cos(const ITV& a) { return ITV(orc::cos(a.raw())); }
 template <class T, class P> ITV sin(const ITV& a) { return ITV(orc::sin(a.raw())); }
 template <class T, class P> ITV sqrt(const ITV& a) { return ITV(orc::sqrt(a.raw())); }

@@ -544,3 +544,51 @@ class ReferenceArmtd:
     def check_feasible(self, x, g):
         g = np.ascontiguousarray(np.asarray(g, dtype=np.float64))
         return bool(self.L.refarmtd_check_feasible(self.h, _dp(_vec(x, 7)), self.m, _dp(g)))
+
+
+REF_CONTROLLER_LIB_PATH = os.path.join(ORACLE_DIR, "_ref", "libref_controller.so")
+
+
+class ReferenceController:
+    """The reference's own robust controller (KRC/*.cpp compiled against the stand-in headers, oracle/ref_controller_driver.cpp):
+    what the two MEX gateways compute per tick."""
+
+    def __init__(self, robot_model_file, model_uncertainty=0.03):
+        self.L = C.CDLL(REF_CONTROLLER_LIB_PATH)
+        self.L.refctrl_create.restype = C.c_void_p
+        self.L.refctrl_create.argtypes = [C.c_char_p, C.c_double]
+        self.L.refctrl_destroy.argtypes = [C.c_void_p]
+        h = self.L.refctrl_create(str(robot_model_file).encode(), float(model_uncertainty))
+        if not h:
+            raise RuntimeError("the reference could not load %s" % robot_model_file)
+        self.h = C.c_void_p(h)
+        self.n = self.L.refctrl_num_joints(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.refctrl_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _update(self, method, Kr, par, q, q_d, qd, qd_d, qd_dd):
+        arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)).reshape(-1, self.n) for a in (q, q_d, qd, qd_d, qd_dd)]
+        count = arrs[0].shape[0]
+        Kr = np.ascontiguousarray(np.broadcast_to(np.asarray(Kr, dtype=np.float64), (self.n,)))
+        par = np.ascontiguousarray(np.asarray(par, dtype=np.float64))
+        u, un, v = (np.zeros((count, self.n)) for _ in range(3))
+        self.L.refctrl_update(self.h, C.c_int(method), C.c_int(count), _dp(Kr), _dp(par), *[_dp(a) for a in arrs], _dp(u), _dp(un), _dp(v))
+        return u, un, v
+
+    def update(self, Kr, alpha, V_max, r_norm_threshold, q, q_d, qd, qd_d, qd_dd):
+        return self._update(0, Kr, [alpha, V_max, r_norm_threshold], q, q_d, qd, qd_d, qd_dd)
+
+    def update_althoff(self, Kr, Kp, Ki, max_error, q, q_d, qd, qd_d, qd_dd):
+        return self._update(1, Kr, [Kp[0], Kp[1], Ki[0], Ki[1], max_error], q, q_d, qd, qd_d, qd_dd)
+
+    def rnea(self, q, qd, qda, qdd, gravity=True):
+        a = [np.ascontiguousarray(np.asarray(x, dtype=np.float64)) for x in (q, qd, qda, qdd)]
+        tau, ti = np.zeros(self.n), np.zeros((self.n, 2))
+        self.L.refctrl_rnea(self.h, *[_dp(x) for x in a], C.c_int(1 if gravity else 0), _dp(tau), _dp(ti))
+        return tau, ti

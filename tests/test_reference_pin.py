@@ -200,3 +200,53 @@ def test_device_armtd_mode_equals_the_reference_comparison_planner(seed, n_obs):
         assert bad.sum() <= 2, int(bad.sum())
         assert p.check_feasible(g) == ref.check_feasible(k, g_ref)
     p.close()
+
+
+# ---- robust low-level controller against the reference's own KRC sources ---------------------
+def _controller_case():
+    import os
+    from test_controller import states, MODEL, KR, ALPHA, V_MAX, R_THR, KP, KI, MAX_ERR
+    if not os.path.exists(_oracle.REF_CONTROLLER_LIB_PATH):
+        pytest.skip("oracle/_ref/libref_controller.so not built")
+    return states, MODEL, (KR, ALPHA, V_MAX, R_THR), (KR, KP, KI, MAX_ERR)
+
+
+def test_oracle_controller_equals_the_reference():
+    states, MODEL, armour, althoff = _controller_case()
+    ref, o = _oracle.ReferenceController(MODEL), _oracle.OracleController(MODEL)
+    st = states(50, 300)
+    u, un, v = ref.update(*armour, *st)
+    uo, uno, vo = o.update(*armour, *st)[:3]
+    assert np.array_equal(un, uno) and close(u, uo) and close(v, vo)
+    u, un, v = ref.update_althoff(*althoff, *st)
+    uo, uno, vo = o.update_althoff(*althoff, *st)[:3]
+    assert np.array_equal(un, uno) and close(u, uo) and close(v, vo)
+    for s in range(5):   # passRNEA / passRNEA_Int, with and without gravity
+        for gravity in (True, False):
+            tau, ti = ref.rnea(st[0][s], st[1][s], st[3][s], st[4][s], gravity)
+            assert np.array_equal(tau, o.rnea(st[0][s], st[1][s], st[3][s], st[4][s], gravity))
+            assert np.array_equal(ti, o.rnea(st[0][s], st[1][s], st[3][s], st[4][s], gravity, interval=True))
+    # the reference's own robot description file gives the same controller as the generated one (when the tree is here)
+    import os
+    theirs = "/root/reference/kinova_src/kinova_simulator_interfaces/kinova_robust_controllers_mex/kinova_without_gripper.txt"
+    if os.path.exists(theirs):
+        a = _oracle.ReferenceController(theirs).update(*armour, *st)
+        b = ref.update(*armour, *st)
+        assert close(a[0], b[0], 1e-10)
+
+
+@pytest.mark.gpu
+def test_device_controller_equals_the_reference():
+    states, MODEL, armour, althoff = _controller_case()
+    from armour_b200.controller import RobustController
+    ref = _oracle.ReferenceController(MODEL)
+    c = RobustController(MODEL, 0.03, device=0)
+    st = states(51, 2000)
+    for a, b in zip(c.update(*armour, *st), ref.update(*armour, *st)):
+        assert close(a, b, 1e-10)
+    for a, b in zip(c.update_althoff(*althoff, *st), ref.update_althoff(*althoff, *st)):
+        assert close(a, b, 1e-10)
+    tau, ti = ref.rnea(st[0][0], st[1][0], st[3][0], st[4][0])
+    assert close(c.rnea(st[0][0], st[1][0], st[3][0], st[4][0]), tau, 1e-10)
+    assert close(c.rnea(st[0][0], st[1][0], st[3][0], st[4][0], interval=True), ti, 1e-10)
+    c.close()
