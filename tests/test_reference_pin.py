@@ -120,7 +120,7 @@ def test_device_reach_sets_equal_the_reference():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed,n_obs", [(None, 10), (31, 20), (32, 3)])
+@pytest.mark.parametrize("seed,n_obs", [(None, 10), (31, 20), (32, 3), (33, 0), (34, 40)])   # 0 and MAX_OBSTACLE_NUM = 40 are the edge cases
 def test_device_tnlp_callbacks_equal_the_reference(seed, n_obs):
     """Constraints, dense Jacobian, bounds, starting point, objective and the feasibility verdict of the device path
     against the reference's own armtd_NLP + Obstacles (its CUDA kernels run on this GPU, oracle/ref_cuda_driver.cu).
