@@ -118,6 +118,8 @@ struct armour_handle {
     Tables tb;
     int P = 1, T = 128, max_obs = 40;
     int mcap = 1024, ncap = 8192, nt = 256, minb = 1, groups = 2, groups_cfg = 2;
+    int task_scap = 1024, task_tcap = 512;
+    int task_groups = 0;   // > 0: single-plan builds run the task-scheduled kernel with this many thread groups (reach_tasks.cuh)
     int scap = 2048, tcap = 512;   // shared-memory sort / staging capacity per thread group (larger operations use global buffers)
     char* arena = nullptr;
     size_t arena_stride = 0;
@@ -158,6 +160,7 @@ void free_arena(armour_handle* h) { if (h->arena) cudaFree(h->arena); h->arena =
 int alloc_arena(armour_handle* h) {
     free_arena(h);
     h->arena_stride = arena_bytes(h->mcap, h->ncap);
+    if (h->task_groups > 0) h->arena_stride = std::max(h->arena_stride, task_arena_bytes(h->mcap, h->ncap, h->task_groups));
     // two thread groups per CTA (joint chain || forces + FK) when their sort buffers fit in shared memory
     h->groups = h->groups_cfg;
     int per_sm = h->groups == 2 ? reach_max_ctas_per_sm(h->nt, h->minb, 2, h->scap, h->tcap) : 0;
@@ -165,6 +168,7 @@ int alloc_arena(armour_handle* h) {
     if (per_sm < 1) return fail(ARMOUR_E_CUDA, "reach_build_kernel does not fit on an SM with these capacities");
     const int n_work = h->P * h->T;
     h->grid = std::min(n_work, per_sm * h->sm_count);
+    if (h->task_groups > 0) h->grid = std::max(h->grid, std::min(n_work, h->sm_count));
     CU(cudaMalloc((void**)&h->arena, h->arena_stride * (size_t)h->grid));
     return ARMOUR_OK;
 }
@@ -176,7 +180,10 @@ int run_build(armour_handle* h) {   // kernels only; inputs already on the devic
     for (int attempt = 0; attempt < 4; attempt++) {
         CU(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
         CU(cudaEventRecord(h->ev[0], h->stream));
-        CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, h->scap, h->tcap, n_work, std::min(h->grid, n_work), h->nt, h->minb, h->groups, h->stream));
+        if (h->task_groups > 0 && h->mode == 0)
+            CU(launch_reach_tasks(tb, h->arena, h->arena_stride, h->mcap, h->ncap, h->task_scap, h->task_tcap, n_work, std::min(h->sm_count, n_work), h->task_groups, h->stream));
+        else
+            CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, h->scap, h->tcap, n_work, std::min(h->grid, n_work), h->nt, h->minb, h->groups, h->stream));
         CU(cudaEventRecord(h->ev[1], h->stream));
         CU(launch_hyperplanes(tb, h->stream));
         CU(cudaEventRecord(h->ev[2], h->stream));
@@ -305,6 +312,11 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     h->groups_cfg = (cfg.batch > 1 || cfg.threads_per_cta == 128 || cfg.threads_per_cta == 512) ? 1 : 2;
     if (const char* e = getenv("ARMOUR_TUNE_GROUPS")) h->groups_cfg = atoi(e) == 2 ? 2 : 1;
     if (const char* e = getenv("ARMOUR_TUNE_SCAP")) h->scap = std::max(256, atoi(e));
+    if (const char* e = getenv("ARMOUR_TUNE_TASKS")) h->task_groups = atoi(e);
+    if (const char* e = getenv("ARMOUR_TUNE_TASK_SCAP")) h->task_scap = std::max(256, atoi(e));
+    if (const char* e = getenv("ARMOUR_TUNE_TASK_TCAP")) h->task_tcap = std::max(64, atoi(e));
+    if (h->task_groups != 0 && h->task_groups != 2 && h->task_groups != 4 && h->task_groups != 8) h->task_groups = 4;
+    if (cfg.batch > 1 || (h->task_groups > 0 && !reach_tasks_fit(h->task_groups, h->task_scap, h->task_tcap))) h->task_groups = 0;
     if (const char* e = getenv("ARMOUR_TUNE_TCAP")) h->tcap = std::max(64, atoi(e));
     kinova_model(h->model);
     *out = h;   // so that armour_destroy can clean up after a partial failure

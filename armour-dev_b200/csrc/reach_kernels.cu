@@ -838,3 +838,5 @@ int reach_max_ctas_per_sm(int nt, int minb, int groups, int scap, int tcap) {
 }
 
 }  // namespace armour
+
+#include "reach_tasks.cuh"
