@@ -479,7 +479,8 @@ static int launch_update(armour_controller* c, int method, int count, const doub
     CK(cudaMemsetAsync(c->d_outside, 0, sizeof(int), c->stream));
     // ARMOUR_TUNE_CTRL_THREADS / ARMOUR_TUNE_CTRL_SMEM: tuning knobs (block size; dummy dynamic shared memory that
     // caps the resident blocks per SM so the thread-local working set stays in L1/L2)
-    static const int threads = getenv("ARMOUR_TUNE_CTRL_THREADS") ? atoi(getenv("ARMOUR_TUNE_CTRL_THREADS")) : 128;
+    static const int threads_env = getenv("ARMOUR_TUNE_CTRL_THREADS") ? atoi(getenv("ARMOUR_TUNE_CTRL_THREADS")) : 128;
+    const int threads = (threads_env == 32 || threads_env == 64) ? threads_env : 128;   // the kernel is bounded for 128 threads
     static const int smem = getenv("ARMOUR_TUNE_CTRL_SMEM") ? atoi(getenv("ARMOUR_TUNE_CTRL_SMEM")) : 0;
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
