@@ -306,6 +306,13 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 mag
     return cur;
 }
 
+#ifdef ARMOUR_OP_TRACE
+__device__ long long g_tr[8];
+#define TR(i) do { if (blockIdx.x == 64 && threadIdx.x == 0) g_tr[i] = clock64(); } while (0)
+#else
+#define TR(i)
+#endif
+
 // ---- generic "segment-reduce, threshold, compact" -------------------------------------------
 // Op interface:
 //   static constexpr int NACC;                          accumulators per key
@@ -354,6 +361,7 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
     for (int c = 0; c < 2 * DOUT; c++) red[c] = 0.0;
     ScalarEpilogue<NT, DOUT> se;
     se.begin(epi);
+    TR(3);
     // pass 1: one thread per segment head
     for (int g = gtid<NT>(); g < N; g += NT) {
         const u64 k = key[g];
@@ -376,7 +384,9 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
         }
         flag[g] = f;
     }
+    TR(4);
     gsync<NT>();
+    TR(5);
     phase_mark(PH_SEGMENT);
     // compaction of the kept keys (blocked ranges keep the order)
     const int ipt = (N + NT - 1) / NT;
@@ -400,7 +410,9 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
         }
     }
     se.finish(S, dst, N, total);
+    TR(6);
     gsync<NT>();
+    TR(7);
     phase_mark(PH_COMPACT);
 }
 
@@ -604,12 +616,20 @@ __device__ __forceinline__ void pz_mul_impl(Scratch& S, PZ<DO>& dst, const PZ<DA
     const int na = A.n, nb = B.n;
     int W = 1;
     u64 magicW = 0;
+    TR(0);
     if (N > 0) fill_product_keys<NT, BIG>(S, A.keys, na, A.divM, B.keys, nb, B.divM, W, magicW);
     MulOp<DA, DB, DO> op(A, B, S.thr_sq);
+    TR(1);
     gsync<NT>();
+    TR(2);
     phase_mark(PH_FILL);
     const int buf = merge_sort_runs<NT, BIG>(S, N, W, magicW);
     reduce_emit<NT, DO, BIG, MulOp<DA, DB, DO>, MulEpi<DA, DB, DO>>(S, buf, N, op, dst, MulEpi<DA, DB, DO>{A, B});
+#ifdef ARMOUR_OP_TRACE
+    if (blockIdx.x == 64 && threadIdx.x == 0)
+        printf("MUL d%d%d na %d nb %d N %d out %d big %d | fill %lld bar %lld sort %lld walk %lld bar %lld scan+emit %lld bar %lld\n", DA, DB, na, nb, N, dst.n, (int)BIG,
+               g_tr[1] - g_tr[0], g_tr[2] - g_tr[1], g_tr[3] - g_tr[2], g_tr[4] - g_tr[3], g_tr[5] - g_tr[4], g_tr[6] - g_tr[5], g_tr[7] - g_tr[6]);
+#endif
 }
 template <int NT, int DA, int DB, int DO>
 __device__ __noinline__ void pz_mul(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, const PZ<DB>& B) {
