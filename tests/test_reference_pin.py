@@ -281,3 +281,29 @@ def test_same_solver_returns_the_same_k_on_reference_and_device_callbacks():
     k_dev = solve(lambda x: p.eval_f(q_des, 0.5, x), lambda x: p.eval_grad_f(q_des, 0.5, x), p.eval_g, lambda x: p.eval_jac_g(x).reshape(-1, 7), p.get_bounds_info())
     assert np.abs(k_ref - k_dev).max() <= 1e-6, (k_ref, k_dev)
     p.close()
+
+
+@pytest.mark.gpu
+def test_device_batched_build_equals_the_reference():
+    """armour_build_batch runs a different kernel variant (one thread group, several CTAs per SM); every problem of the
+    batch must equal the reference's own single-problem build and TNLP callbacks."""
+    import os
+    import armour_b200 as ab
+    if not os.path.exists(_oracle.REF_CUDA_LIB_PATH):
+        pytest.skip("oracle/_ref/libref_cuda.so not built")
+    n_obs, B = 6, 3
+    probs = [make_problem(70 + b, n_obs) for b in range(B)]
+    pb = ab.Planner(T=128, device=0, batch=B)
+    pb.build_batch(np.concatenate([q[0] for q in probs]), np.concatenate([q[1] for q in probs]), np.concatenate([q[2] for q in probs]),
+                   np.concatenate([q[4] for q in probs]), n_obs)
+    ref = _oracle.ReferenceCuda()
+    for b, (q0, qd0, qdd0, q_des, obs) in enumerate(probs):
+        ref.build(q0, qd0, qdd0, q_des, obs)
+        pb.select_problem(b)
+        g, J = pb.eval_g_jac(DEBUG_K)
+        g_ref, J_ref = ref.eval_g(DEBUG_K), ref.eval_jac_g(DEBUG_K)
+        assert close(g, g_ref, 1e-8)
+        bad = np.abs(J.reshape(-1, 7) - J_ref).max(axis=1) > 1e-8 * max(1.0, float(np.abs(J_ref).max()))
+        assert bad.sum() <= 2
+        assert pb.check_feasible(g) == ref.check_feasible(DEBUG_K, g_ref)
+    pb.close()
