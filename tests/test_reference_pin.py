@@ -307,3 +307,38 @@ def test_device_batched_build_equals_the_reference():
         assert bad.sum() <= 2
         assert pb.check_feasible(g) == ref.check_feasible(DEBUG_K, g_ref)
     pb.close()
+
+
+@pytest.mark.gpu
+def test_device_equals_the_reference_on_many_random_problems():
+    """Stress: 12 random states / obstacle worlds at the full size (T = 128).  Keep/drop decisions of simplify() sit on a
+    5e-4 threshold, so this is where an ordering or rounding difference would eventually show as a key mismatch."""
+    import os
+    import armour_b200 as ab
+    if not os.path.exists(_oracle.REF_CUDA_LIB_PATH):
+        pytest.skip("oracle/_ref/libref_cuda.so not built")
+    ref = _oracle.ReferenceCuda()
+    rh = _oracle.Reference()
+    p = ab.Planner(T=128, device=0)
+    rng = np.random.default_rng(99)
+    monomials = 0
+    for seed in range(200, 212):
+        n_obs = int(rng.integers(1, 25))
+        q0, qd0, qdd0, q_des, obs = make_problem(seed, n_obs)
+        ref.build(q0, qd0, qdd0, q_des, obs)
+        rh.build(q0, qd0, qdd0)
+        p.build(q0, qd0, qdd0, obs)
+        for name in ("links", "u_nom"):
+            for s in range(seed % 5, 128, 5):
+                for j in range(7):
+                    a, b = rh.get_pz(name, j, s), p.get_pz(name, j, s)
+                    assert np.array_equal(a["keys"], b["keys"]), (seed, name, j, s)
+                    assert close(b["coeffs"], a["coeffs"], 1e-9)
+                    monomials += len(a["keys"])
+        k = rng.uniform(-1, 1, 7)
+        g, J = p.eval_g_jac(k)
+        g_ref = ref.eval_g(k)
+        assert close(g, g_ref, 1e-8), (seed, float(np.abs(g - g_ref).max()))
+        assert p.check_feasible(g) == ref.check_feasible(k, g_ref)
+    assert monomials > 50000
+    p.close()
