@@ -1,5 +1,6 @@
+"""Reach-kernel time of five single-plan builds (T = 128, 20 obstacles); ARMOUR_TUNE_LIB selects a tuning build of the library."""
 import os, sys
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "armour-dev_b200"), os.path.join(ROOT, "tests")]
 import armour_b200 as ab
 if os.environ.get("ARMOUR_TUNE_LIB"): ab.LIB_PATH = os.path.join(ab.PKG_DIR, os.environ["ARMOUR_TUNE_LIB"])
