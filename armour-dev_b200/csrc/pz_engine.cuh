@@ -471,6 +471,13 @@ __device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* s
     phase_mark(PH_COMPACT);
 }
 
+// load coefficient vector i through a cached (pointer, stride) pair: the descriptor lives in shared memory, and every
+// shared-memory store in between would otherwise force the compiler to re-read coef / cap before each access
+template <int D>
+__device__ __forceinline__ void ldc(const double* __restrict__ coef, int cap, int i, double* v) {
+#pragma unroll
+    for (int c = 0; c < D; c++) v[c] = coef[c * cap + i];
+}
 // load coefficient vector i of a PZ
 template <int D>
 __device__ __forceinline__ void ldc(const PZ<D>& z, int i, double* v) {
@@ -497,7 +504,9 @@ struct MulOp {
     FastDiv fdb;
     double thr;   // squared-domain threshold (Scratch::thr_sq)
     double ca[DA], cb[DB];
-    __device__ MulOp(const PZ<DA>& a, const PZ<DB>& b, double t) : A(a), B(b), na(a.n), nb(b.n), fdb(b.divM), thr(t) {
+    const double* pa; const double* pb;   // coefficient planes and strides, read once
+    int cpa, cpb;
+    __device__ MulOp(const PZ<DA>& a, const PZ<DB>& b, double t) : A(a), B(b), na(a.n), nb(b.n), fdb(b.divM), thr(t), pa(a.coef), pb(b.coef), cpa(a.cap), cpb(b.cap) {
 #pragma unroll
         for (int c = 0; c < DA; c++) ca[c] = a.center[c];
 #pragma unroll
@@ -505,12 +514,12 @@ struct MulOp {
     }
     __device__ __forceinline__ void term(unsigned idx, double* o) const {
         double a[DA], b[DB];
-        if ((int)idx < na) { ldc<DA>(A, idx, a); coef_mul<DA, DB, DO>(a, cb, o); }
-        else if ((int)idx < na + nb) { ldc<DB>(B, idx - na, b); coef_mul<DA, DB, DO>(ca, b, o); }
+        if ((int)idx < na) { ldc<DA>(pa, cpa, idx, a); coef_mul<DA, DB, DO>(a, cb, o); }
+        else if ((int)idx < na + nb) { ldc<DB>(pb, cpb, idx - na, b); coef_mul<DA, DB, DO>(ca, b, o); }
         else {
             const int p = idx - na - nb;
             const int i = fdb.div(p), j = p - i * nb;
-            ldc<DA>(A, i, a); ldc<DB>(B, j, b);
+            ldc<DA>(pa, cpa, i, a); ldc<DB>(pb, cpb, j, b);
             coef_mul<DA, DB, DO>(a, b, o);
         }
     }
@@ -689,10 +698,12 @@ struct MergeOp {
     int na;
     bool negb;
     double thr;   // squared-domain threshold (Scratch::thr_sq)
+    const double* pa; const double* pb;   // coefficient planes and strides, read once
+    int cpa, cpb;
     __device__ __forceinline__ void term(unsigned idx, double* o) const {
-        if ((int)idx < na) { double a[DA]; ldc<DA>(*A.p, idx, a); view_vec<DA, DO>(A, a, o); }
+        if ((int)idx < na) { double a[DA]; ldc<DA>(pa, cpa, idx, a); view_vec<DA, DO>(A, a, o); }
         else {
-            double b[DB]; ldc<DB>(*B.p, idx - na, b); view_vec<DB, DO>(B, b, o);
+            double b[DB]; ldc<DB>(pb, cpb, idx - na, b); view_vec<DB, DO>(B, b, o);
             if (negb) {
 #pragma unroll
                 for (int c = 0; c < DO; c++) o[c] = -o[c];
@@ -750,7 +761,7 @@ __device__ __forceinline__ void pz_merge_impl(Scratch& S, PZ<DO>& dst, const Vie
             for (int i = gtid<NT>(); i < na; i += NT) { key[nb + i] = ka[i]; idx[nb + i] = (u16)i; }
         }
     }
-    MergeOp<DA, DB, DO> op{A, B, na, negb, S.thr_sq};
+    MergeOp<DA, DB, DO> op{A, B, na, negb, S.thr_sq, A.p->coef, B.p->coef, A.p->cap, B.p->cap};
     gsync<NT>();
     phase_mark(PH_FILL);
     const int buf = merge_sort_runs<NT, BIG>(S, N, W, magicW);
@@ -782,17 +793,19 @@ struct CrossPPOp {
     FastDiv fdb;
     double thr;   // squared-domain threshold (Scratch::thr_sq)
     double ca[3], cb[3];
-    __device__ CrossPPOp(const PZ<3>& a, const PZ<3>& b, double t) : A(a), B(b), na(a.n), nb(b.n), fdb(b.divM), thr(t) {
+    const double* pa; const double* pb;
+    int cpa, cpb;
+    __device__ CrossPPOp(const PZ<3>& a, const PZ<3>& b, double t) : A(a), B(b), na(a.n), nb(b.n), fdb(b.divM), thr(t), pa(a.coef), pb(b.coef), cpa(a.cap), cpb(b.cap) {
         for (int c = 0; c < 3; c++) { ca[c] = a.center[c]; cb[c] = b.center[c]; }
     }
     __device__ __forceinline__ void term(unsigned idx, double* o) const {
         double a[3], b[3];
-        if ((int)idx < na) { ldc<3>(A, idx, a); b[0] = cb[0]; b[1] = cb[1]; b[2] = cb[2]; }
-        else if ((int)idx < na + nb) { ldc<3>(B, idx - na, b); a[0] = ca[0]; a[1] = ca[1]; a[2] = ca[2]; }
+        if ((int)idx < na) { ldc<3>(pa, cpa, idx, a); b[0] = cb[0]; b[1] = cb[1]; b[2] = cb[2]; }
+        else if ((int)idx < na + nb) { ldc<3>(pb, cpb, idx - na, b); a[0] = ca[0]; a[1] = ca[1]; a[2] = ca[2]; }
         else {
             const int p = idx - na - nb;
             const int i = fdb.div(p), j = p - i * nb;
-            ldc<3>(A, i, a); ldc<3>(B, j, b);
+            ldc<3>(pa, cpa, i, a); ldc<3>(pb, cpb, j, b);
         }
         o[0] = mul_rn(a[1], b[2]); o[1] = mul_rn(a[2], b[1]);
         o[2] = mul_rn(a[2], b[0]); o[3] = mul_rn(a[0], b[2]);
