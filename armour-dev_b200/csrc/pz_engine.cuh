@@ -276,8 +276,7 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 mag
         const u16* ii = Buf<BIG>::idx(S, cur);
         u64* ko = Buf<BIG>::key(S, cur ^ 1);
         u16* io = Buf<BIG>::idx(S, cur ^ 1);
-        // rank of each element among its sibling run (binary search; key and index are fetched together so the
-        // tie-break does not add a dependent shared-memory round trip)
+        // rank of each element among its sibling run (binary search on the key; the origin index breaks exact ties)
         for (int g = gtid<NT>(); g < N; g += NT) {
             const int r = fd.div(g) >> level;      // g / (W << level)
             const int base = r * w;
@@ -290,8 +289,8 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 mag
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
                     const u64 km = ki[mid];
-                    const unsigned im = ii[mid];
-                    const bool less = (km < k) || (km == k && im < id);
+                    bool less = km < k;
+                    if (km == k) less = ii[mid] < id;   // the index is only needed on an exact tie: no second dependent load otherwise
                     if (less) lo = mid + 1; else hi = mid;
                 }
                 pos = min(base, sb) + (g - base) + (lo - sb);
