@@ -474,6 +474,7 @@ __device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* s
 // shared-memory store in between would otherwise force the compiler to re-read coef / cap before each access
 template <int D>
 __device__ __forceinline__ void ldc(const double* __restrict__ coef, int cap, int i, double* v) {
+    __builtin_assume(__isGlobal(coef));   // PZ storage is always in the global arena: LDG instead of generic LD
 #pragma unroll
     for (int c = 0; c < D; c++) v[c] = coef[c * cap + i];
 }
