@@ -12,7 +12,7 @@ from . import lib, _dp
 EXPORTS = [
     "armour_controller_create", "armour_controller_destroy", "armour_controller_num_joints", "armour_controller_update",
     "armour_controller_update_althoff", "armour_controller_rnea", "armour_controller_upload", "armour_controller_update_resident",
-    "armour_controller_download", "armour_controller_last_ms",
+    "armour_controller_download", "armour_controller_last_ms", "armour_controller_release_host_buffers",
 ]
 
 
@@ -45,6 +45,9 @@ class RobustController:
         _check(L.armour_controller_num_joints(self._h, C.byref(n)))
         self.n = n.value
 
+    def release_host_buffers(self):
+        _check(lib().armour_controller_release_host_buffers(self._h))
+
     def close(self):
         if self._h:
             lib().armour_controller_destroy(self._h)
@@ -64,22 +67,30 @@ class RobustController:
         assert all(a.shape == (count, self.n) for a in arrs)
         return arrs, count, single
 
-    def update(self, Kr, alpha, V_max, r_norm_threshold, q, q_d, qd, qd_d, qd_dd, debug=False):
-        """kinova_controller: ARMOUR robust input.  debug=True also returns (u_interval [..., n, 2], V_sup, outside)."""
+    def update(self, Kr, alpha, V_max, r_norm_threshold, q, q_d, qd, qd_d, qd_dd, debug=False, out=None):
+        """kinova_controller: ARMOUR robust input.  debug=True also returns (u_interval [..., n, 2], V_sup, outside).
+        out=(u, u_nominal, v): reusable [count, n] float64 arrays (large batches page-lock the arrays they are given; arrays
+        allocated here are released again before returning)."""
         arrs, count, single = self._states(q, q_d, qd, qd_d, qd_dd)
         Kr = np.ascontiguousarray(np.broadcast_to(np.asarray(Kr, dtype=np.float64), (self.n,)))
-        u, un, v = (np.zeros((count, self.n)) for _ in range(3))
+        if out is not None:
+            u, un, v = out
+            assert all(a.shape == (count, self.n) and a.dtype == np.float64 and a.flags.c_contiguous for a in out)
+        else:
+            u, un, v = (np.zeros((count, self.n)) for _ in range(3))
         ui = np.zeros((count, self.n, 2)) if debug else None
         Vs = np.zeros(count) if debug else None
         outside = C.c_int()
         rc = lib().armour_controller_update(self._h, C.c_int(count), _dp(Kr), C.c_double(alpha), C.c_double(V_max), C.c_double(r_norm_threshold),
                                             *[_dp(a) for a in arrs], _dp(u), _dp(un), _dp(v), _dp(ui) if debug else None, _dp(Vs) if debug else None,
                                             C.byref(outside))
+        if out is None or debug:
+            self.release_host_buffers()   # arrays allocated here must not stay page-locked after they are freed
         _check(rc)
-        out = (u, un, v) if not single else (u[0], un[0], v[0])
+        res = (u, un, v) if not single else (u[0], un[0], v[0])
         if debug:
-            return out + ((ui, Vs, outside.value) if not single else (ui[0], Vs[0], outside.value))
-        return out
+            return res + ((ui, Vs, outside.value) if not single else (ui[0], Vs[0], outside.value))
+        return res
 
     def update_althoff(self, Kr, Kp, Ki, max_error, q, q_d, qd, qd_d, qd_dd, debug=False):
         """kinova_controller_ALTHOFF."""
@@ -91,6 +102,7 @@ class RobustController:
         outside = C.c_int()
         rc = lib().armour_controller_update_althoff(self._h, C.c_int(count), _dp(Kr), _dp(Kp), _dp(Ki), C.c_double(max_error), *[_dp(a) for a in arrs],
                                                     _dp(u), _dp(un), _dp(v), _dp(ui) if debug else None, C.byref(outside))
+        self.release_host_buffers()
         _check(rc)
         out = (u, un, v) if not single else (u[0], un[0], v[0])
         if debug:

@@ -26,7 +26,9 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/armour_controller_b200.h"
@@ -445,6 +447,11 @@ struct armour_controller {
     double* d_out = nullptr;   // outputs [3][cap][n], then u_interval [cap][n][2], V_sup [cap]
     int cap = 0, resident = 0;
     float last_ms = 0;
+    // large host-buffer calls: chunks ping-pong over two streams so that copies overlap the kernel; caller buffers are
+    // page-locked once and remembered (closed-loop sweeps reuse them every tick)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_join = nullptr;
+    std::vector<std::pair<const char*, size_t>> pinned;
 };
 
 #define CK(call)                                                                                            \
@@ -465,18 +472,20 @@ static int ensure_capacity(armour_controller* c, int count) {
     return ARMOUR_OK;
 }
 
-static int launch_update(armour_controller* c, int method, int count, const double* Kr, const double par[3], bool want_interval, bool want_V) {
-    const size_t n = c->model.n, N = (size_t)c->cap * n;
+static int launch_update(armour_controller* c, int method, int count, const double* Kr, const double par[3], bool want_interval, bool want_V,
+                         cudaStream_t stream = nullptr, size_t first = 0, bool whole_call = true) {
+    if (!stream) stream = c->stream;
+    const size_t n = c->model.n, N = (size_t)c->cap * n, o = first * n;
     UpdateArgs A;
     A.count = count; A.method = method;
     for (int i = 0; i < MAXJ; i++) A.Kr[i] = i < (int)n ? Kr[i] : 0.0;
     for (int i = 0; i < 3; i++) A.par[i] = par[i];
-    A.q = c->d_in; A.q_d = c->d_in + N; A.qd = c->d_in + 2 * N; A.qd_d = c->d_in + 3 * N; A.qd_dd = c->d_in + 4 * N;
-    A.u = c->d_out; A.u_nominal = c->d_out + N; A.v = c->d_out + 2 * N;
-    A.u_interval = want_interval ? c->d_out + 3 * N : nullptr;
-    A.V_sup = want_V ? c->d_out + 5 * N : nullptr;
+    A.q = c->d_in + o; A.q_d = c->d_in + N + o; A.qd = c->d_in + 2 * N + o; A.qd_d = c->d_in + 3 * N + o; A.qd_dd = c->d_in + 4 * N + o;
+    A.u = c->d_out + o; A.u_nominal = c->d_out + N + o; A.v = c->d_out + 2 * N + o;
+    A.u_interval = want_interval ? c->d_out + 3 * N + 2 * o : nullptr;
+    A.V_sup = want_V ? c->d_out + 5 * N + first : nullptr;
     A.outside = c->d_outside;
-    CK(cudaMemsetAsync(c->d_outside, 0, sizeof(int), c->stream));
+    if (whole_call) CK(cudaMemsetAsync(c->d_outside, 0, sizeof(int), stream));
     // ARMOUR_TUNE_CTRL_THREADS / ARMOUR_TUNE_CTRL_SMEM: tuning knobs (block size; dummy dynamic shared memory that
     // caps the resident blocks per SM so the thread-local working set stays in L1/L2)
     static const int threads_env = getenv("ARMOUR_TUNE_CTRL_THREADS") ? atoi(getenv("ARMOUR_TUNE_CTRL_THREADS")) : 128;
@@ -489,11 +498,11 @@ static int launch_update(armour_controller* c, int method, int count, const doub
     }
     attr_set = true;
     const int blocks = (count + threads - 1) / threads;
-    CK(cudaEventRecord(c->ev0, c->stream));
-    if (method == 0) controller_update_kernel<true><<<blocks, threads, smem, c->stream>>>(c->model, A);
-    else controller_update_kernel<false><<<blocks, threads, smem, c->stream>>>(c->model, A);
+    if (whole_call) CK(cudaEventRecord(c->ev0, stream));
+    if (method == 0) controller_update_kernel<true><<<blocks, threads, smem, stream>>>(c->model, A);
+    else controller_update_kernel<false><<<blocks, threads, smem, stream>>>(c->model, A);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(c->ev1, c->stream));
+    if (whole_call) CK(cudaEventRecord(c->ev1, stream));
     return ARMOUR_OK;
 }
 
@@ -513,6 +522,45 @@ static int upload_states(armour_controller* c, int count, const double* const sr
     return ARMOUR_OK;
 }
 
+// page-lock a caller buffer once (best effort: a buffer that cannot be registered is simply copied pageable)
+static void pin_buffer(armour_controller* c, const void* p, size_t bytes) {
+    const char* b = (const char*)p;
+    for (auto& r : c->pinned) if (b >= r.first && b + bytes <= r.first + r.second) return;
+    if (cudaHostRegister((void*)p, bytes, cudaHostRegisterPortable) == cudaSuccess) c->pinned.push_back({b, bytes});
+    else cudaGetLastError();
+}
+static const int PIPE_MIN = 1 << 15, PIPE_CHUNK = 1 << 15;   // ticks
+
+// count >= PIPE_MIN: chunks of PIPE_CHUNK ticks alternate between two streams (H2D, kernel, D2H per chunk)
+static int host_update_pipelined(armour_controller* c, int method, int count, const double* Kr, const double par[3], const double* const src[5],
+                                 double* u, double* u_nominal, double* v, double* u_interval, double* V_sup, int* outside) {
+    const size_t n = c->model.n, N = (size_t)c->cap * n;
+    for (int a = 0; a < 5; a++) pin_buffer(c, src[a], sizeof(double) * count * n);
+    double* dst[3] = {u, u_nominal, v};
+    for (int a = 0; a < 3; a++) pin_buffer(c, dst[a], sizeof(double) * count * n);
+    if (u_interval) pin_buffer(c, u_interval, 2 * sizeof(double) * count * n);
+    if (V_sup) pin_buffer(c, V_sup, sizeof(double) * count);
+    CK(cudaMemsetAsync(c->d_outside, 0, sizeof(int), c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaStreamWaitEvent(c->stream2, c->ev0, 0));
+    int k = 0;
+    for (size_t first = 0; first < (size_t)count; first += PIPE_CHUNK, k++) {
+        const int m = (int)std::min<size_t>(PIPE_CHUNK, count - first);
+        cudaStream_t st = (k & 1) ? c->stream2 : c->stream;
+        const size_t o = first * n, bytes = sizeof(double) * m * n;
+        for (int a = 0; a < 5; a++) CK(cudaMemcpyAsync(c->d_in + a * N + o, src[a] + o, bytes, cudaMemcpyHostToDevice, st));
+        int rc = launch_update(c, method, m, Kr, par, u_interval != nullptr, V_sup != nullptr, st, first, false);
+        if (rc) return rc;
+        for (int a = 0; a < 3; a++) CK(cudaMemcpyAsync(dst[a] + o, c->d_out + a * N + o, bytes, cudaMemcpyDeviceToHost, st));
+        if (u_interval) CK(cudaMemcpyAsync(u_interval + 2 * o, c->d_out + 3 * N + 2 * o, 2 * bytes, cudaMemcpyDeviceToHost, st));
+        if (V_sup) CK(cudaMemcpyAsync(V_sup + first, c->d_out + 5 * N + first, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(c->ev_join, c->stream2));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    return finish_update(c, outside);
+}
+
 static int host_update(armour_controller* c, int method, int count, const double* Kr, const double par[3], const double* q, const double* q_d, const double* qd,
                        const double* qd_d, const double* qd_dd, double* u, double* u_nominal, double* v, double* u_interval, double* V_sup, int* outside) {
     if (!c || !Kr || !q || !q_d || !qd || !qd_d || !qd_dd || !u || !u_nominal || !v) return capi_fail(ARMOUR_E_INVALID, "null argument");
@@ -522,6 +570,7 @@ static int host_update(armour_controller* c, int method, int count, const double
     if (rc) return rc;
     c->resident = 0;
     const double* src[5] = {q, q_d, qd, qd_d, qd_dd};
+    if (count >= PIPE_MIN) return host_update_pipelined(c, method, count, Kr, par, src, u, u_nominal, v, u_interval, V_sup, outside);
     if ((rc = upload_states(c, count, src))) return rc;
     if ((rc = launch_update(c, method, count, Kr, par, u_interval != nullptr, V_sup != nullptr))) return rc;
     const size_t n = c->model.n, N = (size_t)c->cap * n, bytes = sizeof(double) * count * n;
@@ -550,6 +599,8 @@ int armour_controller_create(const char* robot_model_file, double model_uncertai
     c->device = device;
     ControllerModel* d_model = nullptr;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_join);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_outside, sizeof(int));
@@ -575,6 +626,9 @@ void armour_controller_destroy(armour_controller* c) {
     if (c->d_in) cudaFree(c->d_in);
     if (c->d_out) cudaFree(c->d_out);
     if (c->d_outside) cudaFree(c->d_outside);
+    for (auto& r : c->pinned) cudaHostUnregister((void*)r.first);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -661,6 +715,16 @@ int armour_controller_download(armour_controller* c, double* u_unom_v, int* outs
     CK(cudaMemcpyAsync(&bad, c->d_outside, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (outside) *outside = bad;
+    return ARMOUR_OK;
+}
+
+int armour_controller_release_host_buffers(armour_controller* c) {
+    if (!c) return capi_fail(ARMOUR_E_INVALID, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto& r : c->pinned) cudaHostUnregister((void*)r.first);
+    cudaGetLastError();
+    c->pinned.clear();
     return ARMOUR_OK;
 }
 

@@ -61,7 +61,11 @@ int armour_controller_rnea(armour_controller* c, int count, const double* q, con
 int armour_controller_upload(armour_controller* c, int count, const double* states);
 int armour_controller_update_resident(armour_controller* c, const double* Kr, double alpha, double V_max, double r_norm_threshold);
 int armour_controller_download(armour_controller* c, double* u_unom_v, int* outside);
-/* milliseconds of the last update kernel (CUDA events on the controller's stream) */
+/* Calls with count >= 32768 run as a two-stream pipeline of 32768-tick chunks (copy in, kernel, copy out) and page-lock the
+ * caller's arrays the first time they are seen (closed-loop sweeps pass the same arrays every tick).  The arrays stay
+ * page-locked until this call or armour_controller_destroy: call it before freeing them. */
+int armour_controller_release_host_buffers(armour_controller* c);
+/* milliseconds of the last update: the kernel alone for count < 32768, the whole pipeline (copies included) above */
 int armour_controller_last_ms(armour_controller* c, double* kernel_ms);
 
 #ifdef __cplusplus

@@ -228,3 +228,22 @@ def test_device_resident_path_and_golden(device_controller):
     u, un, v, outside = device_controller.download()
     assert outside == 0 and device_controller.last_ms() > 0
     assert close(u, g["u"]) and close(un, g["u_nominal"]) and close(v, g["v"])
+
+
+@pytest.mark.gpu
+def test_device_large_batch_pipeline_equals_small_batches(device_controller):
+    """count >= 32768 runs as a two-stream pipeline of 32768-tick chunks over page-locked caller arrays; the result must
+    be the per-sample result of the plain path (70 000 ticks: two full chunks and a partial one)."""
+    q, q_d, qd, qd_d, qd_dd = states(15, 70000)
+    out = tuple(np.zeros((70000, 7)) for _ in range(3))
+    for _ in range(2):   # second call reuses the registered buffers
+        u, un, v = device_controller.update(KR, ALPHA, V_MAX, R_THR, q, q_d, qd, qd_d, qd_dd, out=out)
+    device_controller.release_host_buffers()
+    for lo in (0, 32768 - 3, 65536 - 5, 70000 - 10):
+        sl = slice(lo, lo + 10)
+        us, uns, vs = device_controller.update(KR, ALPHA, V_MAX, R_THR, q[sl], q_d[sl], qd[sl], qd_d[sl], qd_dd[sl])
+        assert np.array_equal(us, u[sl]) and np.array_equal(uns, un[sl]) and np.array_equal(vs, v[sl])
+    # debug outputs through the pipeline as well
+    r = device_controller.update(KR, ALPHA, V_MAX, R_THR, q, q_d, qd, qd_d, qd_dd, debug=True)
+    assert np.array_equal(r[0], u) and r[5] == 0
+    assert np.all(r[3][..., 0] <= r[1]) and np.all(r[1] <= r[3][..., 1])
