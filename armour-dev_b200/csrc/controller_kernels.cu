@@ -121,13 +121,38 @@ template <class S> DEV Wrench<S> apply(const Inertia<S>& I, const Twist<S>& z) {
     w.f = scaled_by(I.m, z.v) - I.mch * z.w;
     return w;
 }
-// Rodrigues rotation about a body-frame screw axis (KRC/spatial.cpp:156-172, spatial_interval.cpp:145-156)
+// y = M^T x without materialising the transpose (same terms, same association as tr(M) * x)
+template <class S> DEV V3<S> mul_t(const M3<S>& m, const V3<S>& v) {
+    V3<S> r;
+#pragma unroll 1
+    for (int i = 0; i < 3; i++) r.x[i] = (m.a[i] * v.x[0] + m.a[3 + i] * v.x[1]) + m.a[6 + i] * v.x[2];
+    return r;
+}
+// Rodrigues rotation about a body-frame screw axis (KRC/spatial.cpp:156-172, spatial_interval.cpp:145-156):
+//   R = (I + w^ sin) + ((1 - cos) w^) w^ ;  p = -R' (((I - R) w^) v)
+// evaluated entry by entry in that association; the intermediate matrices ((1 - cos) w^, I - R, (I - R) w^, -R') are
+// formed a row at a time in registers instead of as thread-local 3x3 temporaries.
 template <class S> DEV Xf<S> joint_xf(const Twist<S>& z, double sin_theta, double one_minus_cos) {
     const M3<S> wh = hat(z.w);
     Xf<S> x;
-    x.R = (mident<S>() + scaled(wh, sin_theta)) + scaled(wh, one_minus_cos) * wh;
-    const V3<S> p = ((mident<S>() - x.R) * wh) * z.v;
-    x.p = (-tr(x.R)) * p;
+#pragma unroll 1
+    for (int e = 0; e < 9; e++) {
+        const int i = e / 3, j = e - 3 * i;
+        const S t = ((wh.a[i * 3] * one_minus_cos) * wh.a[j] + (wh.a[i * 3 + 1] * one_minus_cos) * wh.a[3 + j]) + (wh.a[i * 3 + 2] * one_minus_cos) * wh.a[6 + j];
+        x.R.a[e] = (cst<S>(i == j ? 1.0 : 0.0) + wh.a[e] * sin_theta) + t;
+    }
+    V3<S> p0;
+#pragma unroll 1
+    for (int i = 0; i < 3; i++) {
+        S m1[3], m2[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) m1[k] = cst<S>(i == k ? 1.0 : 0.0) - x.R.a[i * 3 + k];
+#pragma unroll
+        for (int j = 0; j < 3; j++) m2[j] = (m1[0] * wh.a[j] + m1[1] * wh.a[3 + j]) + m1[2] * wh.a[6 + j];
+        p0.x[i] = (m2[0] * z.v.x[0] + m2[1] * z.v.x[1]) + m2[2] * z.v.x[2];
+    }
+#pragma unroll 1
+    for (int i = 0; i < 3; i++) x.p.x[i] = ((-x.R.a[i]) * p0.x[0] + (-x.R.a[3 + i]) * p0.x[1]) + (-x.R.a[6 + i]) * p0.x[2];
     return x;
 }
 template <class S> DEV Twist<S> apply(const Xf<S>& X, const Twist<S>& z) { Twist<S> r; r.w = X.R * z.w; r.v = X.R * (z.v - cross(X.p, z.w)); return r; }
@@ -136,10 +161,9 @@ template <class S> DEV Twist<S> invapply(const Xf<S>& X, const Twist<S>& z) {
     Twist<S> r; r.w = Rt * z.w; r.v = Rt * z.v + cross(X.p, r.w); return r;
 }
 template <class S> DEV Wrench<S> invapply(const Xf<S>& X, const Wrench<S>& f) {   // KRC/spatial.cpp:210-214
-    const M3<S> Rt = tr(X.R);
-    Wrench<S> r; r.f = Rt * f.f; r.tau = Rt * f.tau + cross(X.p, r.f); return r;
+    Wrench<S> r; r.f = mul_t(X.R, f.f); r.tau = mul_t(X.R, f.tau) + cross(X.p, r.f); return r;
 }
-template <class S> DEV Xf<S> compose(const Xf<S>& X, const Xf<S>& x2) { Xf<S> r; r.R = X.R * x2.R; r.p = x2.p + tr(x2.R) * X.p; return r; }   // :236-243
+template <class S> DEV Xf<S> compose(const Xf<S>& X, const Xf<S>& x2) { Xf<S> r; r.R = X.R * x2.R; r.p = x2.p + mul_t(x2.R, X.p); return r; }   // :236-243
 template <class S> DEV Xf<S> inverse(const Xf<S>& X) { Xf<S> r; r.R = tr(X.R); r.p = (-X.R) * X.p; return r; }
 // rigid inertia seen from a shifted/rotated frame (KRC/spatial.cpp:220-234); model set-up only, doubles only
 DEV Inertia<double> apply(const Xf<double>& X, const Inertia<double>& I) {
