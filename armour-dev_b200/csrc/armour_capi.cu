@@ -315,7 +315,7 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     if (const char* e = getenv("ARMOUR_TUNE_TASKS")) h->task_groups = atoi(e);
     if (const char* e = getenv("ARMOUR_TUNE_TASK_SCAP")) h->task_scap = std::max(256, atoi(e));
     if (const char* e = getenv("ARMOUR_TUNE_TASK_TCAP")) h->task_tcap = std::max(64, atoi(e));
-    if (h->task_groups != 0 && h->task_groups != 2 && h->task_groups != 4 && h->task_groups != 8) h->task_groups = 4;
+    if (h->task_groups != 0) h->task_groups = 4;   // the one instantiated configuration: 4 groups x 128 threads
     if (cfg.batch > 1 || (h->task_groups > 0 && !reach_tasks_fit(h->task_groups, h->task_scap, h->task_tcap))) h->task_groups = 0;
     if (const char* e = getenv("ARMOUR_TUNE_TCAP")) h->tcap = std::max(64, atoi(e));
     kinova_model(h->model);

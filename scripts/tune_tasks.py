@@ -32,7 +32,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         worker()
     else:
-        for tasks, scap, tcap in ((0, 0, 0), (4, 1536, 256), (4, 1792, 256), (4, 1280, 256), (4, 1792, 128), (2, 2048, 512), (2, 4096, 512)):
+        for tasks, scap, tcap in ((0, 0, 0), (4, 1536, 256), (4, 1792, 256), (4, 1280, 256), (4, 1792, 128)):
             env = dict(os.environ, ARMOUR_TUNE_TASKS=str(tasks), ARMOUR_TUNE_TASK_SCAP=str(scap or 1024), ARMOUR_TUNE_TASK_TCAP=str(tcap or 512))
             try:
                 out = subprocess.run([sys.executable, __file__, "one"], env=env, capture_output=True, text=True, timeout=120)
