@@ -115,8 +115,11 @@ template <class S> DEV S dot(const Twist<S>& t, const Wrench<S>& f) { return dot
 template <class S> DEV Twist<S> cross(const Twist<S>& a, const Twist<S>& b) {
     Twist<S> r; r.w = cross(a.w, b.w); r.v = cross(a.w, b.v) + cross(a.v, b.w); return r;
 }
-template <class S> DEV Wrench<S> apply(const Inertia<S>& I, const Twist<S>& z) {   // KRC/spatial.cpp:143-147
+// KRC/spatial.cpp:143-147.  first_moment_zero: m c^ is exactly zero (the model is expressed in body-CoM frames, so it
+// cancels exactly for the robot files checked); its two products are then exact zeros and x + 0 == x, x - 0 == x.
+template <class S> DEV Wrench<S> apply(const Inertia<S>& I, const Twist<S>& z, bool first_moment_zero = false) {
     Wrench<S> w;
+    if (first_moment_zero) { w.tau = I.I_bar * z.w; w.f = scaled_by(I.m, z.v); return w; }
     w.tau = I.I_bar * z.w + I.mch * z.v;
     w.f = scaled_by(I.m, z.v) - I.mch * z.w;
     return w;
@@ -191,6 +194,7 @@ template <class S> struct JointConst {
 };
 struct ControllerModel {
     int n;
+    int mch_zero[MAXJ];   // 1: every entry of m c^ of joint i is exactly zero in both models
     double damping[MAXJ], friction[MAXJ];
     Twist<double> neg_gravity;
     Twist<Itv> neg_gravity_itv;
@@ -256,6 +260,9 @@ __global__ void model_setup_kernel(RawModel raw, double eps, ControllerModel* ou
             M.unc[i].I.I_bar.a[e] = val >= 0 ? itv(val * lowP, val * highP) : itv(val * highP, val * lowP);
         }
         M.unc[i].transI = cst<Itv>(raw.transI[i]);
+        int z = 1;
+        for (int e = 0; e < 9; e++) if (I[i].mch.a[e] != 0.0) z = 0;
+        M.mch_zero[i] = z;
     }
 }
 
@@ -295,8 +302,9 @@ __device__ void rnea_chain(const ControllerModel& M, const JointConst<S>* __rest
         vIv.tau = cross(va.w, Ji.I.I_bar * v.w);
         vIv.tau = vIv.tau + Ji.I.I_bar * cross(va.w, v.w);
         vIv.f = scaled_by(Ji.I.m, cross(va.w, v.v));
-        f[i] = apply(Ji.I, ch[2]) + vIv;
-        if (MR) f2[i] = apply(Ji.I, ch[NCH - 1]);
+        const bool fmz = M.mch_zero[i] != 0;
+        f[i] = apply(Ji.I, ch[2], fmz) + vIv;
+        if (MR) f2[i] = apply(Ji.I, ch[NCH - 1], fmz);
     }
     Wrench<S> acc, acc2;
 #pragma unroll 1
