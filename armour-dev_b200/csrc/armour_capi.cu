@@ -292,8 +292,9 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     if (cfg.max_obstacles < 0) return fail(ARMOUR_E_INVALID, "max_obstacles < 0");
     if (cfg.max_monomials <= 0) cfg.max_monomials = 1024;
     if (cfg.max_entries <= 0) cfg.max_entries = 8192;
-    if (cfg.threads_per_cta != 128 && cfg.threads_per_cta != 512) cfg.threads_per_cta = 256;
     if (cfg.batch <= 0) cfg.batch = 1;
+    const bool nt_default = cfg.threads_per_cta != 128 && cfg.threads_per_cta != 256 && cfg.threads_per_cta != 512;
+    if (nt_default) cfg.threads_per_cta = cfg.batch > 1 ? 128 : 256;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ARMOUR_E_CUDA, "no CUDA device: this library has no CPU fallback");
     armour_handle* h = new armour_handle();
@@ -306,7 +307,9 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     h->P = cfg.batch; h->T = cfg.num_time_steps; h->max_obs = cfg.max_obstacles;
     h->mcap = cfg.max_monomials; h->ncap = std::min(cfg.max_entries, 65534) & ~1; h->nt = cfg.threads_per_cta;
     // register budget: one plan is latency-bound (1 CTA/SM, all registers); a batch wants more resident CTAs
-    h->minb = cfg.batch > 1 ? 2 : 1;
+    // (measured, scripts/tune_batch.py: 128 threads x 4 CTAs/SM with 1024-entry shared sort buffers is the fastest sweep shape)
+    h->minb = cfg.batch > 1 ? (cfg.threads_per_cta == 128 ? 4 : 2) : 1;
+    if (cfg.batch > 1 && cfg.threads_per_cta == 128) { h->scap = 1024; h->tcap = 256; }
     if (const char* e = getenv("ARMOUR_TUNE_MINB")) h->minb = atoi(e);
     // one plan (latency): two thread groups per CTA; a batch (throughput): one group and two resident CTAs per SM
     h->groups_cfg = (cfg.batch > 1 || cfg.threads_per_cta == 128 || cfg.threads_per_cta == 512) ? 1 : 2;

@@ -277,6 +277,7 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 mag
         u64* ko = Buf<BIG>::key(S, cur ^ 1);
         u16* io = Buf<BIG>::idx(S, cur ^ 1);
         // rank of each element among its sibling run (binary search on the key; the origin index breaks exact ties)
+        #pragma unroll 1
         for (int g = gtid<NT>(); g < N; g += NT) {
             const int r = fd.div(g) >> level;      // g / (W << level)
             const int base = r * w;
@@ -315,8 +316,8 @@ __device__ long long g_tr[8];
 // ---- generic "segment-reduce, threshold, compact" -------------------------------------------
 // Op interface:
 //   static constexpr int NACC;                          accumulators per key
-//   void first(unsigned idx, double* acc);              acc  = contribution of the segment's first entry
-//   void next (unsigned idx, double* acc);              acc += contribution (round-to-nearest, in order)
+//   void term(unsigned idx, double* t);                 contribution of candidate `idx` (origin index); reduce_emit adds the
+//                                                       contributions of a key up in list order, round-to-nearest
 //   bool finish(const double* acc, double* out, double* drop);   threshold logic; out[DOUT]; drop[DOUT] = |dropped|
 // Epi interface (scalar epilogue, run by thread c < DOUT only, off the other threads' critical path):
 //   void operator()(int c, double& cen, double& r0, double& r1)   centre and the two radii of component c before the
@@ -362,13 +363,22 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
     se.begin(epi);
     TR(3);
     // pass 1: one thread per segment head
+    #pragma unroll 1
     for (int g = gtid<NT>(); g < N; g += NT) {
         const u64 k = key[g];
         u16 f = 0;
         if (g == 0 || key[g - 1] != k) {
+            // one inlined copy of the term code (first entry: acc = term; later entries: acc += term, in order)
             double acc[Op::NACC];
-            op.first(idx[g], acc);
-            for (int e = g + 1; e < N && key[e] == k; e++) op.next(idx[e], acc);
+            int e = g;
+            #pragma unroll 1
+            do {
+                double t[Op::NACC];
+                op.term(idx[e], t);
+#pragma unroll
+                for (int c = 0; c < Op::NACC; c++) acc[c] = (e == g) ? t[c] : add_rn(acc[c], t[c]);
+                e++;
+            } while (e < N && key[e] == k);
             double out[DOUT], dr[DOUT];
 #pragma unroll
             for (int c = 0; c < DOUT; c++) dr[c] = 0.0;
@@ -391,6 +401,7 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
     const int ipt = (N + NT - 1) / NT;
     const int g0 = min(gtid<NT>() * ipt, N), g1 = min(g0 + ipt, N);
     int cnt = 0;
+    #pragma unroll 1
     for (int g = g0; g < g1; g++) cnt += flag[g];
     int total;
     int off = block_scan_sum<NT, 2 * DOUT>(S, cnt, red, total);
@@ -399,6 +410,7 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
     else {
         u64* dk = dst.keys;
         double* dc = dst.coef;
+        #pragma unroll 1
         for (int g = g0; g < g1; g++) {
             if (flag[g]) {
                 dk[off] = key[g];
@@ -429,6 +441,7 @@ __device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* s
     double* tmp = S.staging(n, DOUT, ncap);
     ScalarEpilogue<NT, DOUT> se;
     se.begin(epi);
+    #pragma unroll 1
     for (int i = gtid<NT>(); i < n; i += NT) {
         double out[DOUT], dr[DOUT];
 #pragma unroll
@@ -448,6 +461,7 @@ __device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* s
     const int ipt = (n + NT - 1) / NT;
     const int g0 = min(gtid<NT>() * ipt, n), g1 = min(g0 + ipt, n);
     int cnt = 0;
+    #pragma unroll 1
     for (int g = g0; g < g1; g++) cnt += flag[g];
     int total;
     int off = block_scan_sum<NT, 2 * DOUT>(S, cnt, red, total);
@@ -456,6 +470,7 @@ __device__ __forceinline__ void elementwise_emit(Scratch& S, int n, const u64* s
     else {
         u64* dk = dst.keys;
         double* dc = dst.coef;
+        #pragma unroll 1
         for (int g = g0; g < g1; g++) {
             if (flag[g]) {
                 dk[off] = kcopy[g];
@@ -513,22 +528,19 @@ struct MulOp {
         for (int c = 0; c < DB; c++) cb[c] = b.center[c];
     }
     __device__ __forceinline__ void term(unsigned idx, double* o) const {
+        // origin index -> (i, j); i < 0 / j < 0 selects the operand's centre.  One copy of the product code.
         double a[DA], b[DB];
-        if ((int)idx < na) { ldc<DA>(pa, cpa, idx, a); coef_mul<DA, DB, DO>(a, cb, o); }
-        else if ((int)idx < na + nb) { ldc<DB>(pb, cpb, idx - na, b); coef_mul<DA, DB, DO>(ca, b, o); }
-        else {
-            const int p = idx - na - nb;
-            const int i = fdb.div(p), j = p - i * nb;
-            ldc<DA>(pa, cpa, i, a); ldc<DB>(pb, cpb, j, b);
-            coef_mul<DA, DB, DO>(a, b, o);
+        int i = (int)idx, j = -1;
+        if (i >= na) {
+            if (i < na + nb) { j = i - na; i = -1; }
+            else { const int p = i - na - nb; i = fdb.div(p); j = p - i * nb; }
         }
-    }
-    __device__ __forceinline__ void first(unsigned idx, double* acc) const { term(idx, acc); }
-    __device__ __forceinline__ void next(unsigned idx, double* acc) const {
-        double t[DO];
-        term(idx, t);
+        __builtin_assume(__isGlobal(pa)); __builtin_assume(__isGlobal(pb));
 #pragma unroll
-        for (int c = 0; c < DO; c++) acc[c] = add_rn(acc[c], t[c]);
+        for (int c = 0; c < DA; c++) a[c] = i >= 0 ? pa[c * cpa + i] : ca[c];
+#pragma unroll
+        for (int c = 0; c < DB; c++) b[c] = j >= 0 ? pb[c * cpb + j] : cb[c];
+        coef_mul<DA, DB, DO>(a, b, o);
     }
     __device__ __forceinline__ bool finish(const double* acc, double* out, double* drop) const {
         if (normD<DO>(acc) <= thr) {
@@ -551,33 +563,40 @@ __device__ __forceinline__ int fill_product_keys(Scratch& S, const u64* ka, int 
     if (na == 0 || nb == 0) {   // single sorted run
         W = N > 0 ? N : 1;
         magicW = na ? magic_a : magic_b;
+        #pragma unroll 1
         for (int g = gtid<NT>(); g < N; g += NT) { key[g] = na ? ka[g] : kb[g]; idx[g] = (u16)g; }
         return N;
     }
     if (nb >= na) {   // runs: i = 0..na-1 (width nb), then B's own list (nb), then A's own list (na <= nb, last)
         W = nb; magicW = magic_b;
         const FastDiv fd(magic_b);
+        #pragma unroll 1
         for (int g = gtid<NT>(); g < na * nb; g += NT) {
             const int i = fd.div(g), j = g - i * nb;
             key[g] = ka[i] + kb[j];   // degrees add; no carry by construction (KPR/PZsparse.cu:938-940)
             idx[g] = (u16)(na + nb + g);
         }
         const int o1 = na * nb;
+        #pragma unroll 1
         for (int j = gtid<NT>(); j < nb; j += NT) { key[o1 + j] = kb[j]; idx[o1 + j] = (u16)(na + j); }
         const int o0 = o1 + nb;
+        #pragma unroll 1
         for (int i = gtid<NT>(); i < na; i += NT) { key[o0 + i] = ka[i]; idx[o0 + i] = (u16)i; }
     }
     else {            // runs: j = 0..nb-1 (width na), then A's own list (na), then B's own list (nb < na, last)
         W = na; magicW = magic_a;
         const FastDiv fd(magic_a);
+        #pragma unroll 1
         for (int g = gtid<NT>(); g < na * nb; g += NT) {
             const int j = fd.div(g), i = g - j * na;
             key[g] = ka[i] + kb[j];
             idx[g] = (u16)(na + nb + i * nb + j);
         }
         const int o0 = na * nb;
+        #pragma unroll 1
         for (int i = gtid<NT>(); i < na; i += NT) { key[o0 + i] = ka[i]; idx[o0 + i] = (u16)i; }
         const int o1 = o0 + na;
+        #pragma unroll 1
         for (int j = gtid<NT>(); j < nb; j += NT) { key[o1 + j] = kb[j]; idx[o1 + j] = (u16)(na + j); }
     }
     return N;
@@ -710,13 +729,6 @@ struct MergeOp {
             }
         }
     }
-    __device__ __forceinline__ void first(unsigned idx, double* acc) const { term(idx, acc); }
-    __device__ __forceinline__ void next(unsigned idx, double* acc) const {
-        double t[DO];
-        term(idx, t);
-#pragma unroll
-        for (int c = 0; c < DO; c++) acc[c] = add_rn(acc[c], t[c]);
-    }
     __device__ __forceinline__ bool finish(const double* acc, double* out, double* drop) const {
         if (normD<DO>(acc) <= thr) {
 #pragma unroll
@@ -752,12 +764,16 @@ __device__ __forceinline__ void pz_merge_impl(Scratch& S, PZ<DO>& dst, const Vie
         const u64* ka = A.p->keys; const u64* kb = B.p->keys;
         if (na >= nb) {   // the longer run first: runs must have uniform width except the last
             W = na > 0 ? na : 1; magicW = A.p->divM;
+            #pragma unroll 1
             for (int i = gtid<NT>(); i < na; i += NT) { key[i] = ka[i]; idx[i] = (u16)i; }
+            #pragma unroll 1
             for (int j = gtid<NT>(); j < nb; j += NT) { key[na + j] = kb[j]; idx[na + j] = (u16)(na + j); }
         }
         else {
             W = nb; magicW = B.p->divM;
+            #pragma unroll 1
             for (int j = gtid<NT>(); j < nb; j += NT) { key[j] = kb[j]; idx[j] = (u16)(na + j); }
+            #pragma unroll 1
             for (int i = gtid<NT>(); i < na; i += NT) { key[nb + i] = ka[i]; idx[nb + i] = (u16)i; }
         }
     }
@@ -800,23 +816,19 @@ struct CrossPPOp {
     }
     __device__ __forceinline__ void term(unsigned idx, double* o) const {
         double a[3], b[3];
-        if ((int)idx < na) { ldc<3>(pa, cpa, idx, a); b[0] = cb[0]; b[1] = cb[1]; b[2] = cb[2]; }
-        else if ((int)idx < na + nb) { ldc<3>(pb, cpb, idx - na, b); a[0] = ca[0]; a[1] = ca[1]; a[2] = ca[2]; }
-        else {
-            const int p = idx - na - nb;
-            const int i = fdb.div(p), j = p - i * nb;
-            ldc<3>(pa, cpa, i, a); ldc<3>(pb, cpb, j, b);
+        int i = (int)idx, j = -1;
+        if (i >= na) {
+            if (i < na + nb) { j = i - na; i = -1; }
+            else { const int p = i - na - nb; i = fdb.div(p); j = p - i * nb; }
         }
+        __builtin_assume(__isGlobal(pa)); __builtin_assume(__isGlobal(pb));
+#pragma unroll
+        for (int c = 0; c < 3; c++) a[c] = i >= 0 ? pa[c * cpa + i] : ca[c];
+#pragma unroll
+        for (int c = 0; c < 3; c++) b[c] = j >= 0 ? pb[c * cpb + j] : cb[c];
         o[0] = mul_rn(a[1], b[2]); o[1] = mul_rn(a[2], b[1]);
         o[2] = mul_rn(a[2], b[0]); o[3] = mul_rn(a[0], b[2]);
         o[4] = mul_rn(a[0], b[1]); o[5] = mul_rn(a[1], b[0]);
-    }
-    __device__ __forceinline__ void first(unsigned idx, double* acc) const { term(idx, acc); }
-    __device__ __forceinline__ void next(unsigned idx, double* acc) const {
-        double t[6];
-        term(idx, t);
-#pragma unroll
-        for (int c = 0; c < 6; c++) acc[c] = add_rn(acc[c], t[c]);
     }
     // stage 1: each scalar product's simplify; stage 2: the difference's simplify; stage 3: stack's simplify
     __device__ __forceinline__ bool finish(const double* acc, double* out, double* drop) const {

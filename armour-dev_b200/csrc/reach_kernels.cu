@@ -359,7 +359,7 @@ size_t arena_bytes(int mcap, int ncap) {
 }
 
 template <int D>
-__device__ char* carve(PZ<D>& z, char* p, int cap) {
+__device__ __noinline__ char* carve(PZ<D>& z, char* p, int cap) {
     z.cap = cap; z.n = 0; z.divM = FastDiv::magic(0);
     z.keys = (u64*)p; p += (size_t)cap * 8;
     z.coef = (double*)p; p += (size_t)cap * 8 * D;
@@ -467,6 +467,7 @@ __device__ void fk_joint(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_
 }
 template <int NT>
 __device__ void forward_kinematics(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0) {
+    #pragma unroll 1
     for (int i = 0; i < NJ; i++) fk_joint<NT>(S, Z, T, tb, rec0, i);
 }
 // RNEA reverse recursion for joint i (KPR/Dynamics.cu:161-180)
@@ -575,6 +576,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
         g = carve<9>(Z.FKR, g, mcap);
         for (int i = 0; i <= NJ; i++) g = carve<9>(Z.R[i], g, SMALL_CAP);
         for (int i = 0; i < NJ; i++) g = carve<9>(Z.Rt[i], g, SMALL_CAP);
+        #pragma unroll 1
         for (int i = 0; i < NJ; i++) {
             g = carve<1>(Z.qd[i], g, SMALL_CAP); g = carve<1>(Z.qda[i], g, SMALL_CAP); g = carve<1>(Z.qdda[i], g, SMALL_CAP);
             g = carve<1>(Z.cosq[i], g, SMALL_CAP); g = carve<1>(Z.sinq[i], g, SMALL_CAP);
@@ -655,15 +657,18 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
         }
         else if (GROUPS == 1) {
             forward_kinematics<NT>(S, Z, T, tb, rec0);                                    // stage B
+            #pragma unroll 1
             for (int i = 0; i < NJ; i++) {                                                 // stage C forward
                 chain_joint<NT>(S, Z, T, i, (i + 1) & 1, i & 1);
                 force_joint<NT>(S, Z, T, tb, i, i & 1, Z.LA[i & 1]);
             }
+            #pragma unroll 1
             for (int i = NJ - 1; i >= 0; i--) backward_joint<NT>(S, Z, T, i);             // stage C backward
         }
         else if (group == 0) {
             // angular recurrence, then the moment recursion; forward-kinematics joints fill the time spent waiting
             int fk_next = 0;
+            #pragma unroll 1
             for (int i = 0; i < NJ; i++) {
                 // set i&1 still holds the state of joint i-2, read by group 1 until its linear_acc step of joint i-1 is done
                 if (i >= 1) {
@@ -675,6 +680,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
                 group_signal<NT>(&sig_state, i + 1);
                 PIECE(pc_chain);
             }
+            #pragma unroll 1
             for (int i = NJ - 1; i >= 0; i--) {
                 while (fk_next < NJ && !group_ready<NT>(S, &sig_side, NJ - i)) { fk_joint<NT>(S, Z, T, tb, rec0, fk_next++); PIECE(pc_fk); }
                 group_wait<NT>(S, &sig_side, NJ - i);
@@ -686,6 +692,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
         }
         else {
             PZ<3>& LA = Z.LA[1];   // group 1's private linear_acc, initialised with gravity in stage A
+            #pragma unroll 1
             for (int i = 0; i < NJ; i++) {
                 group_wait<NT>(S, &sig_state, i);          // state of joint i-1 (the initial state for i = 0)
                 PIECE(pc_wait);
@@ -698,6 +705,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
                 group_signal<NT>(&sig_force, i + 1);
                 PIECE(pc_force);
             }
+            #pragma unroll 1
             for (int i = NJ - 1; i >= 0; i--) {
                 side_joint<NT>(S, Z, T, i);
                 group_signal<NT>(&sig_side, NJ - i);

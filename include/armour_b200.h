@@ -56,7 +56,7 @@ typedef struct armour_config {
     int max_monomials;          /* capacity of one PZ's monomial list; default 1024 (0 = default)  */
     int max_entries;            /* capacity of one sort (candidate monomials of one op); default 8192, at most 65535 (0 = default).
                                  * Operations up to 2048 candidates sort in shared memory, larger ones in global memory. */
-    int threads_per_cta;        /* 128, 256 or 512; default 256 (0 = default)            */
+    int threads_per_cta;        /* 128, 256 or 512; 0 = default (256; 128 for a batch)    */
     int device;                 /* CUDA device ordinal; -1 = current device              */
     int batch;                  /* problems one handle builds per armour_build_batch call; default 1 */
     int pin_user_buffers;       /* 1: armour_eval_g_jac page-locks the caller's g / values arrays (cudaHostRegister) and the
