@@ -13,6 +13,7 @@ sys.path[:0] = [os.path.join(ROOT, "armour-dev_b200"), os.path.join(ROOT, "tests
 
 def worker(T, B, threads):
     import armour_b200 as ab
+    if os.environ.get("ARMOUR_TUNE_LIB"): ab.LIB_PATH = os.path.join(ab.PKG_DIR, os.environ["ARMOUR_TUNE_LIB"])
     from problems import make_problem
     n_obs = 20
     pb = ab.Planner(T=T, max_obstacles=n_obs, device=0, batch=B, threads_per_cta=threads)
@@ -31,7 +32,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         return worker(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
     for B in (64,):
-        for threads, minb, scap, tcap in ((128, 4, 2048, 512), (128, 6, 1024, 256), (128, 8, 1024, 256), (128, 6, 1536, 256), (128, 8, 512, 256), (128, 4, 1024, 256)):
+        for threads, minb, scap, tcap in ((128, 4, 1024, 128), (128, 4, 1024, 64), (128, 4, 768, 256), (128, 4, 768, 128), (128, 4, 512, 128), (128, 4, 512, 64), (128, 5, 768, 128), (128, 5, 512, 128)):
             env = dict(os.environ, ARMOUR_TUNE_MINB=str(minb), ARMOUR_TUNE_SCAP=str(scap), ARMOUR_TUNE_TCAP=str(tcap))
             out = subprocess.run([sys.executable, __file__, "one", "128", str(B), str(threads)], env=env, capture_output=True, text=True)
             res = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]

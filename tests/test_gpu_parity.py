@@ -169,7 +169,9 @@ def test_call_order_errors(gpu_lib):
 
 
 def test_batch_equals_single_builds(gpu_lib):
-    """Independent problems in one launch give bit-identical tables to one-at-a-time builds."""
+    """Independent problems in one launch give the same tables as one-at-a-time builds: monomial keys, coefficients and
+    centres bit-identical.  Interval radii are block-wide round-up sums whose association follows the CTA shape (a sweep
+    runs 128-thread CTAs, one plan two groups of 256), so they and the rows that contain them agree to 1e-12."""
     probs = [make_problem(s, 6) for s in (11, 12, 13)]
     T = 32
     pb = ab.Planner(T=T, batch=3)
@@ -182,8 +184,9 @@ def test_batch_equals_single_builds(gpu_lib):
         pb.select_problem(i)
         g1, J1 = ps.eval_g_jac(x)
         g2, J2 = pb.eval_g_jac(x)
-        assert np.array_equal(g1, g2) and np.array_equal(J1, J2)
-        assert np.array_equal(ps.torque_radius(), pb.torque_radius())
+        np.testing.assert_allclose(g2, g1, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(J2, J1, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(pb.torque_radius(), ps.torque_radius(), rtol=1e-12, atol=0)
         for s in (0, T // 2, T - 1):
             a, b = ps.get_pz("u_nom", 3, s), pb.get_pz("u_nom", 3, s)
             assert np.array_equal(a["keys"], b["keys"]) and np.array_equal(a["coeffs"], b["coeffs"])
