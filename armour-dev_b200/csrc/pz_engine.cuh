@@ -266,10 +266,8 @@ __device__ __forceinline__ double block_total(const Scratch& S, int k) {
 // Buffer 0 holds N entries laid out as sorted runs of width W (the last run may be shorter).
 // Returns the buffer that holds the fully sorted sequence.  All (key, idx) pairs are distinct, so
 // ordering by (key, idx) equals a stable sort by key of the list in origin order.
-// (un-inlined: one copy of the merge loop per kernel instead of one per operation type — the code of an operation is
-//  fetched from L2 almost every time it runs; measured -1.7 % single plan, +1 % sweep)
 template <int NT, bool BIG>
-__device__ __noinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 magicW) {
+__device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 magicW) {
     int cur = 0;
     const FastDiv fd(magicW);
     int level = 0;
@@ -318,8 +316,8 @@ __device__ long long g_tr[8];
 // ---- generic "segment-reduce, threshold, compact" -------------------------------------------
 // Op interface:
 //   static constexpr int NACC;                          accumulators per key
-//   void term(unsigned idx, double* t);                 contribution of candidate `idx` (origin index); reduce_emit adds the
-//                                                       contributions of a key up in list order, round-to-nearest
+//   void first(unsigned idx, double* acc);              acc  = contribution of the segment's first entry
+//   void next (unsigned idx, double* acc);              acc += contribution (round-to-nearest, in order)
 //   bool finish(const double* acc, double* out, double* drop);   threshold logic; out[DOUT]; drop[DOUT] = |dropped|
 // Epi interface (scalar epilogue, run by thread c < DOUT only, off the other threads' critical path):
 //   void operator()(int c, double& cen, double& r0, double& r1)   centre and the two radii of component c before the
@@ -370,17 +368,10 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
         const u64 k = key[g];
         u16 f = 0;
         if (g == 0 || key[g - 1] != k) {
-            // one inlined copy of the term code (first entry: acc = term; later entries: acc += term, in order)
             double acc[Op::NACC];
-            int e = g;
+            op.first(idx[g], acc);
             #pragma unroll 1
-            do {
-                double t[Op::NACC];
-                op.term(idx[e], t);
-#pragma unroll
-                for (int c = 0; c < Op::NACC; c++) acc[c] = (e == g) ? t[c] : add_rn(acc[c], t[c]);
-                e++;
-            } while (e < N && key[e] == k);
+            for (int e = g + 1; e < N && key[e] == k; e++) op.next(idx[e], acc);
             double out[DOUT], dr[DOUT];
 #pragma unroll
             for (int c = 0; c < DOUT; c++) dr[c] = 0.0;
@@ -530,19 +521,22 @@ struct MulOp {
         for (int c = 0; c < DB; c++) cb[c] = b.center[c];
     }
     __device__ __forceinline__ void term(unsigned idx, double* o) const {
-        // origin index -> (i, j); i < 0 / j < 0 selects the operand's centre.  One copy of the product code.
         double a[DA], b[DB];
-        int i = (int)idx, j = -1;
-        if (i >= na) {
-            if (i < na + nb) { j = i - na; i = -1; }
-            else { const int p = i - na - nb; i = fdb.div(p); j = p - i * nb; }
+        if ((int)idx < na) { ldc<DA>(pa, cpa, idx, a); coef_mul<DA, DB, DO>(a, cb, o); }
+        else if ((int)idx < na + nb) { ldc<DB>(pb, cpb, idx - na, b); coef_mul<DA, DB, DO>(ca, b, o); }
+        else {
+            const int p = idx - na - nb;
+            const int i = fdb.div(p), j = p - i * nb;
+            ldc<DA>(pa, cpa, i, a); ldc<DB>(pb, cpb, j, b);
+            coef_mul<DA, DB, DO>(a, b, o);
         }
-        __builtin_assume(__isGlobal(pa)); __builtin_assume(__isGlobal(pb));
+    }
+    __device__ __forceinline__ void first(unsigned idx, double* acc) const { term(idx, acc); }
+    __device__ __forceinline__ void next(unsigned idx, double* acc) const {
+        double t[DO];
+        term(idx, t);
 #pragma unroll
-        for (int c = 0; c < DA; c++) a[c] = i >= 0 ? pa[c * cpa + i] : ca[c];
-#pragma unroll
-        for (int c = 0; c < DB; c++) b[c] = j >= 0 ? pb[c * cpb + j] : cb[c];
-        coef_mul<DA, DB, DO>(a, b, o);
+        for (int c = 0; c < DO; c++) acc[c] = add_rn(acc[c], t[c]);
     }
     __device__ __forceinline__ bool finish(const double* acc, double* out, double* drop) const {
         if (normD<DO>(acc) <= thr) {
@@ -731,6 +725,13 @@ struct MergeOp {
             }
         }
     }
+    __device__ __forceinline__ void first(unsigned idx, double* acc) const { term(idx, acc); }
+    __device__ __forceinline__ void next(unsigned idx, double* acc) const {
+        double t[DO];
+        term(idx, t);
+#pragma unroll
+        for (int c = 0; c < DO; c++) acc[c] = add_rn(acc[c], t[c]);
+    }
     __device__ __forceinline__ bool finish(const double* acc, double* out, double* drop) const {
         if (normD<DO>(acc) <= thr) {
 #pragma unroll
@@ -818,19 +819,23 @@ struct CrossPPOp {
     }
     __device__ __forceinline__ void term(unsigned idx, double* o) const {
         double a[3], b[3];
-        int i = (int)idx, j = -1;
-        if (i >= na) {
-            if (i < na + nb) { j = i - na; i = -1; }
-            else { const int p = i - na - nb; i = fdb.div(p); j = p - i * nb; }
+        if ((int)idx < na) { ldc<3>(pa, cpa, idx, a); b[0] = cb[0]; b[1] = cb[1]; b[2] = cb[2]; }
+        else if ((int)idx < na + nb) { ldc<3>(pb, cpb, idx - na, b); a[0] = ca[0]; a[1] = ca[1]; a[2] = ca[2]; }
+        else {
+            const int p = idx - na - nb;
+            const int i = fdb.div(p), j = p - i * nb;
+            ldc<3>(pa, cpa, i, a); ldc<3>(pb, cpb, j, b);
         }
-        __builtin_assume(__isGlobal(pa)); __builtin_assume(__isGlobal(pb));
-#pragma unroll
-        for (int c = 0; c < 3; c++) a[c] = i >= 0 ? pa[c * cpa + i] : ca[c];
-#pragma unroll
-        for (int c = 0; c < 3; c++) b[c] = j >= 0 ? pb[c * cpb + j] : cb[c];
         o[0] = mul_rn(a[1], b[2]); o[1] = mul_rn(a[2], b[1]);
         o[2] = mul_rn(a[2], b[0]); o[3] = mul_rn(a[0], b[2]);
         o[4] = mul_rn(a[0], b[1]); o[5] = mul_rn(a[1], b[0]);
+    }
+    __device__ __forceinline__ void first(unsigned idx, double* acc) const { term(idx, acc); }
+    __device__ __forceinline__ void next(unsigned idx, double* acc) const {
+        double t[6];
+        term(idx, t);
+#pragma unroll
+        for (int c = 0; c < 6; c++) acc[c] = add_rn(acc[c], t[c]);
     }
     // stage 1: each scalar product's simplify; stage 2: the difference's simplify; stage 3: stack's simplify
     __device__ __forceinline__ bool finish(const double* acc, double* out, double* drop) const {
