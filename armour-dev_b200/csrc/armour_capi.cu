@@ -307,9 +307,9 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     h->P = cfg.batch; h->T = cfg.num_time_steps; h->max_obs = cfg.max_obstacles;
     h->mcap = cfg.max_monomials; h->ncap = std::min(cfg.max_entries, 65534) & ~1; h->nt = cfg.threads_per_cta;
     // register budget: one plan is latency-bound (1 CTA/SM, all registers); a batch wants more resident CTAs
-    // (measured, scripts/tune_batch.py: 128 threads x 4 CTAs/SM with 1024-entry shared sort buffers is the fastest sweep shape)
+    // (measured, scripts/tune_batch.py: 128 threads x 4 CTAs/SM with 1408-entry shared sort buffers is the fastest sweep shape)
     h->minb = cfg.batch > 1 ? (cfg.threads_per_cta == 128 ? 4 : 2) : 1;
-    if (cfg.batch > 1 && cfg.threads_per_cta == 128) { h->scap = 1024; h->tcap = 256; }
+    if (cfg.batch > 1 && cfg.threads_per_cta == 128) { h->scap = 1408; h->tcap = 300; }
     if (const char* e = getenv("ARMOUR_TUNE_MINB")) h->minb = atoi(e);
     // one plan (latency): two thread groups per CTA; a batch (throughput): one group and two resident CTAs per SM
     h->groups_cfg = (cfg.batch > 1 || cfg.threads_per_cta == 128 || cfg.threads_per_cta == 512) ? 1 : 2;

@@ -32,7 +32,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         return worker(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
     for B in (64,):
-        for threads, minb, scap, tcap in ((128, 4, 1024, 256), (128, 6, 512, 256), (128, 6, 512, 128), (128, 6, 640, 64), (128, 8, 512, 128), (128, 8, 256, 64), (128, 6, 256, 64)):
+        for threads, minb, scap, tcap in ((128, 4, 1024, 256), (128, 4, 1408, 300), (128, 4, 768, 128), (128, 3, 2048, 512), (128, 6, 512, 256), (256, 2, 2048, 512), (256, 2, 1024, 256)):
             env = dict(os.environ, ARMOUR_TUNE_MINB=str(minb), ARMOUR_TUNE_SCAP=str(scap), ARMOUR_TUNE_TCAP=str(tcap))
             out = subprocess.run([sys.executable, __file__, "one", "128", str(B), str(threads)], env=env, capture_output=True, text=True)
             res = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
