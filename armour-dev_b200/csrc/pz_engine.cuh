@@ -276,6 +276,45 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 mag
         const u16* ii = Buf<BIG>::idx(S, cur);
         u64* ko = Buf<BIG>::key(S, cur ^ 1);
         u16* io = Buf<BIG>::idx(S, cur ^ 1);
+        if constexpr (NT >= 256) {   // one plan (measured: -4 %); the sweep shape keeps the per-candidate search (merge path there: -2 %)
+        // merge path: every thread owns a chunk of consecutive OUTPUT positions; one binary search along the chunk's
+        // diagonal finds how many elements of each run precede it, then the chunk is merged sequentially.  (One search
+        // per thread and level instead of one per candidate; order by (key, origin index), all pairs distinct.)
+        {
+            const int ipt = (N + NT - 1) / NT;
+            int o = min(gtid<NT>() * ipt, N);
+            const int oend = min(o + ipt, N);
+            const int w2 = w << 1;
+            #pragma unroll 1
+            while (o < oend) {
+                const int base = (fd.div(o) >> (level + 1)) * w2;
+                const int la = min(w, N - base), lb = max(0, min(w, N - base - w));
+                const int cend = min(oend, base + la + lb);
+                const int bb = base + w;
+                const int d = o - base;
+                int lo = max(0, d - lb), hi = min(d, la);
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const u64 ka = ki[base + mid], kb = ki[bb + d - 1 - mid];
+                    bool less = ka < kb;
+                    if (ka == kb) less = ii[base + mid] < ii[bb + d - 1 - mid];
+                    if (less) lo = mid + 1; else hi = mid;
+                }
+                int i = lo, j = d - lo;
+                u64 ka = i < la ? ki[base + i] : ~0ull, kb = j < lb ? ki[bb + j] : ~0ull;
+                #pragma unroll 1
+                for (; o < cend; o++) {
+                    bool ta;
+                    if (j >= lb) ta = true;
+                    else if (i >= la) ta = false;
+                    else { ta = ka < kb; if (ka == kb) ta = ii[base + i] < ii[bb + j]; }
+                    if (ta) { ko[o] = ka; io[o] = ii[base + i]; i++; ka = i < la ? ki[base + i] : ~0ull; }
+                    else { ko[o] = kb; io[o] = ii[bb + j]; j++; kb = j < lb ? ki[bb + j] : ~0ull; }
+                }
+            }
+        }
+        }
+        else {
         // rank of each element among its sibling run (binary search on the key; the origin index breaks exact ties)
         #pragma unroll 1
         for (int g = gtid<NT>(); g < N; g += NT) {
@@ -298,6 +337,7 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 mag
             }
             ko[pos] = k;
             io[pos] = (u16)id;
+        }
         }
         gsync<NT>();
         phase_mark(PH_SORT);

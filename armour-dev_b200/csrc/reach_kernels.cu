@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Scratch SS[GROUPS];
     __shared__ Slots Z;
-    __shared__ volatile int sig_la, sig_state, sig_force, sig_side;
+    __shared__ volatile int sig_la, sig_state, sig_force, sig_side, sig_u;
     const RobotModel& rm = c_robot;
     const int group = threadIdx.x / NT;
     Scratch& S = SS[group];
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
     for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
         const int prob = work / tb.T, s = work - prob * tb.T;
         const size_t rec0 = ((size_t)prob * tb.T + s) * NJ;
-        if (threadIdx.x == 0) { sig_la = 0; sig_state = 0; sig_force = 0; sig_side = 0; }
+        if (threadIdx.x == 0) { sig_la = 0; sig_state = 0; sig_force = 0; sig_side = 0; sig_u = 0; }
         __syncthreads();
         // ---- stage A: joint reach sets (one thread per joint; tiny scalar work) -------------------
         if (threadIdx.x < NJ) {
@@ -686,6 +686,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
                 group_wait<NT>(S, &sig_side, NJ - i);
                 PIECE(pc_wait);
                 moment_joint<NT>(S, Z, T, i);
+                group_signal<NT>(&sig_u, NJ - i);          // u_i is final: group 1 exports it (stage M) beside the next joint
                 PIECE(pc_back);
             }
             while (fk_next < NJ) { fk_joint<NT>(S, Z, T, tb, rec0, fk_next++); PIECE(pc_fk); }
@@ -711,6 +712,12 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
                 group_signal<NT>(&sig_side, NJ - i);
                 PIECE(pc_back);
             }
+            // stage M exports (disturbance radius, reduce(), torque table) in the time this group would idle
+            #pragma unroll 1
+            for (int i = NJ - 1; i >= 0; i--) {
+                group_wait<NT>(S, &sig_u, NJ - i);
+                export_torque<NT>(S, tb, rec0 + i, Z.u[i]);
+            }
         }
 #ifdef ARMOUR_PHASE_TIMING
         if (blockIdx.x == 64 && gtid<NT>() == 0)
@@ -718,8 +725,9 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
 #endif
 
         // ---- stage M: disturbance, reduce(), torque radius (KPR/armour_main.cu:135-205) -------------
+        if (GROUPS == 2 && tb.mode == 0) __syncthreads();   // group 1's exports are visible to thread 0
         if (group == 0 && tb.mode == 0) {
-            for (int i = 0; i < NF; i++) export_torque<NT>(S, tb, rec0 + i, Z.u[i]);
+            if (GROUPS == 1) for (int i = 0; i < NF; i++) export_torque<NT>(S, tb, rec0 + i, Z.u[i]);
             if (threadIdx.x == 0) {
                 const size_t base = rec0;
                 // rho = sqrt(sum_i [-r_i, r_i]^2): only the upper end is used; everything rounded up

@@ -13,6 +13,8 @@ half-space tables) followed by one evaluation of all constraints and their Jacob
 `e2e` times the same step through the public C ABI with host buffers, host<->device copies included.
 N > 1: independent problems per rank (weak scaling), one NCCL all_gather of per-problem result records.
 """
+import os as _os
+_os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
 import argparse
 import json
 import os
