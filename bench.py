@@ -14,7 +14,18 @@ half-space tables) followed by one evaluation of all constraints and their Jacob
 N > 1: independent problems per rank (weak scaling), one NCCL all_gather of per-problem result records.
 """
 import os as _os
-_os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
+import sys as _sys
+# stdout carries the one JSON line only: everything libraries print while the bench runs (e.g. NCCL's version banner) goes
+# to stderr; _emit() writes the line to the real stdout.
+_REAL_STDOUT = _os.dup(1)
+_os.dup2(2, 1)
+
+
+def _emit(text):
+    _sys.stdout.flush()
+    _os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 import argparse
 import json
 import os
@@ -176,7 +187,7 @@ def run_reference(args):
                          "sample": "%d full steps (1 build + eval_g + eval_jac_g each); %s" % (args.steps, how)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 def run_ours(args):
@@ -360,7 +371,7 @@ def run_ours(args):
         if extra_sweep:
             line["sweep"] = extra_sweep
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        _emit(json.dumps(line))
     p.close()
     if world > 1:
         dist.barrier()
