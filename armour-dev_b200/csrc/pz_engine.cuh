@@ -276,7 +276,7 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 mag
         const u16* ii = Buf<BIG>::idx(S, cur);
         u64* ko = Buf<BIG>::key(S, cur ^ 1);
         u16* io = Buf<BIG>::idx(S, cur ^ 1);
-        if constexpr (NT >= 256) {   // one plan (measured: -4 %); the sweep shape keeps the per-candidate search (merge path there: -2 %)
+        if (NT >= 256 && N > NT) {   // one plan, more than one candidate per thread (measured: -4 %); the sweep shape keeps the per-candidate search (merge path there: -2 %)
         // merge path: every thread owns a chunk of consecutive OUTPUT positions; one binary search along the chunk's
         // diagonal finds how many elements of each run precede it, then the chunk is merged sequentially.  (One search
         // per thread and level instead of one per candidate; order by (key, origin index), all pairs distinct.)
