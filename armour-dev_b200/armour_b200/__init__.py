@@ -44,6 +44,7 @@ class ArmourConfig(C.Structure):
         ("device", C.c_int),
         ("batch", C.c_int),
         ("pin_user_buffers", C.c_int),
+        ("export_trajectory_tables", C.c_int),
     ]
 
 
@@ -116,7 +117,7 @@ class Planner:
     planning problem (or a batch of independent ones)."""
 
     def __init__(self, T=128, k_range=None, mass_uncertainty=0.03, inertia_uncertainty=0.03, threshold=5e-4, max_obstacles=40,
-                 max_monomials=0, max_entries=0, threads_per_cta=0, device=-1, batch=1, pin_user_buffers=False):
+                 max_monomials=0, max_entries=0, threads_per_cta=0, device=-1, batch=1, pin_user_buffers=False, export_trajectory_tables=0):
         self.L = lib()
         cfg = default_config()
         cfg.num_time_steps = T
@@ -133,6 +134,7 @@ class Planner:
         cfg.device = device
         cfg.batch = batch
         cfg.pin_user_buffers = 1 if pin_user_buffers else 0
+        cfg.export_trajectory_tables = int(export_trajectory_tables)
         self.T = T
         self.batch = batch
         self.k_range = np.array([cfg.k_range[i] for i in range(7)])

@@ -118,8 +118,6 @@ struct armour_handle {
     Tables tb;
     int P = 1, T = 128, max_obs = 40;
     int mcap = 1024, ncap = 8192, nt = 256, minb = 1, groups = 2, groups_cfg = 2;
-    int task_scap = 1024, task_tcap = 512;
-    int task_groups = 0;   // > 0: single-plan builds run the task-scheduled kernel with this many thread groups (reach_tasks.cuh)
     int scap = 2048, tcap = 512;   // shared-memory sort / staging capacity per thread group (larger operations use global buffers)
     char* arena = nullptr;
     size_t arena_stride = 0;
@@ -159,16 +157,14 @@ int m_of(const armour_handle* h) { return (h->mode == 0 ? NF * h->T : 0) + NJ * 
 void free_arena(armour_handle* h) { if (h->arena) cudaFree(h->arena); h->arena = nullptr; }
 int alloc_arena(armour_handle* h) {
     free_arena(h);
-    h->arena_stride = arena_bytes(h->mcap, h->ncap);
-    if (h->task_groups > 0) h->arena_stride = std::max(h->arena_stride, task_arena_bytes(h->mcap, h->ncap, h->task_groups));
     // two thread groups per CTA (joint chain || forces + FK) when their sort buffers fit in shared memory
     h->groups = h->groups_cfg;
     int per_sm = h->groups == 2 ? reach_max_ctas_per_sm(h->nt, h->minb, 2, h->scap, h->tcap) : 0;
     if (per_sm < 1) { h->groups = 1; per_sm = reach_max_ctas_per_sm(h->nt, h->minb, 1, h->scap, h->tcap); }
     if (per_sm < 1) return fail(ARMOUR_E_CUDA, "reach_build_kernel does not fit on an SM with these capacities");
+    h->arena_stride = arena_bytes(h->mcap, h->ncap, h->groups);
     const int n_work = h->P * h->T;
     h->grid = std::min(n_work, per_sm * h->sm_count);
-    if (h->task_groups > 0) h->grid = std::max(h->grid, std::min(n_work, h->sm_count));
     CU(cudaMalloc((void**)&h->arena, h->arena_stride * (size_t)h->grid));
     return ARMOUR_OK;
 }
@@ -178,12 +174,9 @@ int run_build(armour_handle* h) {   // kernels only; inputs already on the devic
     Tables tb = h->tb;
     tb.P = h->count; tb.n_obs = h->n_obs; tb.mode = h->mode; tb.jrs = h->d_jrs; tb.k_range_in = h->d_krange;
     for (int attempt = 0; attempt < 4; attempt++) {
-        CU(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
+        CU(cudaMemsetAsync(h->d_err, 0, 2 * sizeof(int), h->stream));   // error word, work counter
         CU(cudaEventRecord(h->ev[0], h->stream));
-        if (h->task_groups > 0 && h->mode == 0)
-            CU(launch_reach_tasks(tb, h->arena, h->arena_stride, h->mcap, h->ncap, h->task_scap, h->task_tcap, n_work, std::min(h->sm_count, n_work), h->task_groups, h->stream));
-        else
-            CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, h->scap, h->tcap, n_work, std::min(h->grid, n_work), h->nt, h->minb, h->groups, h->stream));
+        CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, h->scap, h->tcap, n_work, std::min(h->grid, n_work), h->nt, h->minb, h->groups, h->stream));
         CU(cudaEventRecord(h->ev[1], h->stream));
         CU(launch_hyperplanes(tb, h->stream));
         CU(cudaEventRecord(h->ev[2], h->stream));
@@ -247,7 +240,7 @@ int ensure_mirror(armour_handle* h) {
     h->m_ukeys.resize(T * NF * UCAP); h->m_ucoef.resize(T * NF * UCAP); h->m_ucenter.resize(T * NF); h->m_uind.resize(T * NF); h->m_dist.resize(T * NF);
     h->m_lkeys.resize(T * NJ * LCAP); h->m_lcoef.resize(T * NJ * 3 * LCAP); h->m_lcenter.resize(T * NJ * 3); h->m_lind.resize(T * NJ * 3);
     const Tables& tb = h->tb;
-    CU(cudaMemcpy(h->m_traj.data(), tb.traj + p * T * TRAJ_TABLES * NJ, sizeof(SmallRec) * h->m_traj.size(), cudaMemcpyDeviceToHost));
+    if (tb.traj) CU(cudaMemcpy(h->m_traj.data(), tb.traj + p * T * TRAJ_TABLES * NJ, sizeof(SmallRec) * h->m_traj.size(), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(h->m_un.data(), tb.u_n + p * T * NF, sizeof(int) * T * NF, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(h->m_ln.data(), tb.l_n + p * T * NJ, sizeof(int) * T * NJ, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(h->m_ukeys.data(), tb.u_keys + p * T * NF * UCAP, 8 * h->m_ukeys.size(), cudaMemcpyDeviceToHost));
@@ -293,7 +286,9 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     if (cfg.max_monomials <= 0) cfg.max_monomials = 1024;
     if (cfg.max_entries <= 0) cfg.max_entries = 8192;
     if (cfg.batch <= 0) cfg.batch = 1;
-    const bool nt_default = cfg.threads_per_cta != 128 && cfg.threads_per_cta != 256 && cfg.threads_per_cta != 512;
+    if (const char* e = getenv("ARMOUR_TUNE_NT")) cfg.threads_per_cta = atoi(e);
+    const int nt_in = cfg.threads_per_cta;
+    const bool nt_default = nt_in != 32 && nt_in != 64 && nt_in != 128 && nt_in != 256 && nt_in != 512;
     if (nt_default) cfg.threads_per_cta = cfg.batch > 1 ? 128 : 256;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ARMOUR_E_CUDA, "no CUDA device: this library has no CPU fallback");
@@ -308,19 +303,19 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     h->mcap = cfg.max_monomials; h->ncap = std::min(cfg.max_entries, 65534) & ~1; h->nt = cfg.threads_per_cta;
     // register budget: one plan is latency-bound (1 CTA/SM, all registers); a batch wants more resident CTAs
     // (measured, scripts/tune_batch.py: 128 threads x 4 CTAs/SM with 1408-entry shared sort buffers is the fastest sweep shape)
-    h->minb = cfg.batch > 1 ? (cfg.threads_per_cta == 128 ? 4 : 2) : 1;
-    if (cfg.batch > 1 && cfg.threads_per_cta == 128) { h->scap = 1408; h->tcap = 300; }
+    const int nt = cfg.threads_per_cta;
+    h->minb = nt == 32 ? 16 : nt == 64 ? 8 : cfg.batch > 1 ? (nt == 128 ? 4 : 2) : 1;
+    if (cfg.batch > 1 && nt == 128) { h->scap = 1408; h->tcap = 300; }
+    if (nt == 64) { h->scap = 768; h->tcap = 192; }
+    if (nt == 32) { h->scap = 512; h->tcap = 128; }
     if (const char* e = getenv("ARMOUR_TUNE_MINB")) h->minb = atoi(e);
-    // one plan (latency): two thread groups per CTA; a batch (throughput): one group and two resident CTAs per SM
-    h->groups_cfg = (cfg.batch > 1 || cfg.threads_per_cta == 128 || cfg.threads_per_cta == 512) ? 1 : 2;
+    if (const char* e = getenv("ARMOUR_TUNE_MCAP")) h->mcap = std::max(64, atoi(e));
+    if (const char* e = getenv("ARMOUR_TUNE_NCAP")) h->ncap = std::min(std::max(256, atoi(e)), 65534) & ~1;
+    // one plan (latency): two thread groups per CTA; a batch (throughput): one group per CTA and several resident CTAs per SM
+    h->groups_cfg = (cfg.batch > 1 || nt != 256) ? 1 : 2;
     if (const char* e = getenv("ARMOUR_TUNE_GROUPS")) h->groups_cfg = atoi(e) == 2 ? 2 : 1;
-    if (const char* e = getenv("ARMOUR_TUNE_SCAP")) h->scap = std::max(256, atoi(e));
-    if (const char* e = getenv("ARMOUR_TUNE_TASKS")) h->task_groups = atoi(e);
-    if (const char* e = getenv("ARMOUR_TUNE_TASK_SCAP")) h->task_scap = std::max(256, atoi(e));
-    if (const char* e = getenv("ARMOUR_TUNE_TASK_TCAP")) h->task_tcap = std::max(64, atoi(e));
-    if (h->task_groups != 0) h->task_groups = 4;   // the one instantiated configuration: 4 groups x 128 threads
-    if (cfg.batch > 1 || (h->task_groups > 0 && !reach_tasks_fit(h->task_groups, h->task_scap, h->task_tcap))) h->task_groups = 0;
-    if (const char* e = getenv("ARMOUR_TUNE_TCAP")) h->tcap = std::max(64, atoi(e));
+    if (const char* e = getenv("ARMOUR_TUNE_SCAP")) h->scap = std::max(128, atoi(e)) & ~1;
+    if (const char* e = getenv("ARMOUR_TUNE_TCAP")) h->tcap = std::max(32, atoi(e)) & ~1;
     kinova_model(h->model);
     *out = h;   // so that armour_destroy can clean up after a partial failure
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -336,14 +331,15 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     CU(dalloc(&h->d_jrs, (size_t)6 * NF * T)); CU(dalloc(&h->d_krange, (size_t)NF));
     CU(cudaMallocHost((void**)&h->h_jrs, sizeof(double) * 6 * NF * T)); CU(cudaMallocHost((void**)&h->h_krange, sizeof(double) * NF));
     tb.state = h->d_state; tb.obstacles = h->d_obs;
-    CU(dalloc(&tb.traj, P * T * TRAJ_TABLES * NJ));
+    const bool want_traj = cfg.export_trajectory_tables > 0 || (cfg.export_trajectory_tables == 0 && cfg.batch == 1);
+    if (want_traj) CU(dalloc(&tb.traj, P * T * TRAJ_TABLES * NJ));
     CU(dalloc(&tb.cos_rem, P * NJ * T * 2)); CU(dalloc(&tb.sin_rem, P * NJ * T * 2));
     CU(dalloc(&tb.u_n, P * T * NF)); CU(dalloc(&tb.u_keys, P * T * NF * UCAP)); CU(dalloc(&tb.u_coef, P * T * NF * UCAP));
     CU(dalloc(&tb.u_center, P * T * NF)); CU(dalloc(&tb.u_ind, P * T * NF)); CU(dalloc(&tb.dist_rad, P * T * NF)); CU(dalloc(&tb.torque_radius, P * T * NF));
     CU(dalloc(&tb.l_n, P * T * NJ)); CU(dalloc(&tb.l_keys, P * T * NJ * LCAP)); CU(dalloc(&tb.l_coef, P * T * NJ * 3 * LCAP));
     CU(dalloc(&tb.l_center, P * T * NJ * 3)); CU(dalloc(&tb.l_ind, P * T * NJ * 3)); CU(dalloc(&tb.gens, P * T * NJ * 18));
     CU(dalloc(&tb.A, P * T * NJ * O * COMB * 3)); CU(dalloc(&tb.d, P * T * NJ * O * COMB)); CU(dalloc(&tb.delta, P * T * NJ * O * COMB));
-    CU(dalloc(&h->d_err, 1)); tb.err = h->d_err;
+    CU(dalloc(&h->d_err, 2)); tb.err = h->d_err;
     const size_t mmax = NF * T + NJ * T * O + NF * 4;
     CU(dalloc(&h->d_x, NF)); CU(dalloc(&h->d_g, mmax)); CU(dalloc(&h->d_jac, mmax * NF)); CU(dalloc(&h->d_link_center, T * NJ * 3));
     CU(cudaMallocHost((void**)&h->h_state, sizeof(double) * P * 21)); CU(cudaMallocHost((void**)&h->h_obs, sizeof(double) * P * O * 12));
@@ -613,6 +609,7 @@ int armour_get_pz(armour_handle* h, int which, int idx, int t, int* dims, uint64
             return 0;
         }
         if (idx >= NJ) return fail(ARMOUR_E_INVALID, "joint index out of range");
+        if (!h->tb.traj) return fail(ARMOUR_E_STATE, "trajectory tables were not exported (cfg.export_trajectory_tables)");
         const SmallRec& r = h->m_traj[((size_t)t * TRAJ_TABLES + which) * NJ + idx];
         const int dim = r.dim;
         if (dims) { dims[0] = dim == 9 ? 3 : 1; dims[1] = dim == 9 ? 3 : 1; }

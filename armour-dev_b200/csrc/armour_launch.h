@@ -9,14 +9,10 @@ struct FlatPZ { int n, dim, cap; u64* keys; double* coef; double* center; double
 struct FlatOut { int n, dim; };
 
 cudaError_t upload_robot_model(const RobotModel& rm);
-size_t arena_bytes(int mcap, int ncap);
-size_t reach_smem_bytes(int scap, int tcap);
+size_t arena_bytes(int mcap, int ncap, int groups);
 size_t reach_gmem_bytes(int ncap);
 int reach_max_ctas_per_sm(int nt, int minb, int groups, int scap, int tcap);
 cudaError_t launch_reach_build(const Tables& tb, char* arena, size_t arena_stride, int mcap, int ncap, int scap, int tcap, int n_work, int grid, int nt, int minb, int groups, cudaStream_t stream);
-size_t task_arena_bytes(int mcap, int ncap, int groups);
-bool reach_tasks_fit(int groups, int scap, int tcap);
-cudaError_t launch_reach_tasks(const Tables& tb, char* arena, size_t arena_stride, int mcap, int ncap, int scap, int tcap, int n_work, int grid, int groups, cudaStream_t stream);
 cudaError_t launch_pz_binary(int op, const FlatPZ& a, const FlatPZ& b, const FlatPZ& r, FlatOut* out, char* gmem, int ncap, int scap, int tcap, double thr, int* err, cudaStream_t stream);
 cudaError_t launch_hyperplanes(const Tables& tb, cudaStream_t stream);
 cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* x_host, double* g, double* jac, double* link_center, cudaStream_t stream);

@@ -68,6 +68,7 @@ struct Scratch {
     unsigned skey_a[2];   // shared u64[scap]
     unsigned sidx_a[2];   // shared u16[scap]
     unsigned stmp_a;      // shared double[3][tcap]: per-key results before compaction (small operations)
+    unsigned red_a;       // shared double[nwarps][32]: per-warp partial sums of block_scan_sum
     u64* gkey[2];         // global u64[ncap]
     u16* gidx[2];         // global u16[ncap]
     double* tmp;          // global double[9][ncap]: per-key results before compaction (large operations)
@@ -75,18 +76,20 @@ struct Scratch {
     double thr;
     double thr_sq;    // largest x with RN(sqrt(x)) <= thr: "norm <= thr" is tested as "squared norm <= thr_sq", exactly
     int* gerr;        // global error word
-    double red[16 * 32];   // per-warp partial sums: up to 16 warps x 32 values
-    int iscan[34];
+    int iscan[18];         // per-warp scan totals (<= 16 warps); [17] is a group-uniform flag (group_ready)
     __device__ __forceinline__ u64* skey(int b) const { return (u64*)__cvta_shared_to_generic((size_t)skey_a[b]); }
     __device__ __forceinline__ u16* sidx(int b) const { return (u16*)__cvta_shared_to_generic((size_t)sidx_a[b]); }
     __device__ __forceinline__ double* stmp() const { return (double*)__cvta_shared_to_generic((size_t)stmp_a); }
-    static __host__ __device__ size_t smem_bytes(int scap_, int tcap_) { return (size_t)scap_ * 20 + (size_t)3 * tcap_ * 8; }
+    __device__ __forceinline__ double* red() const { return (double*)__cvta_shared_to_generic((size_t)red_a); }
+    // scap and tcap must be even (8-byte alignment of the regions that follow the 2-byte index buffers)
+    static __host__ __device__ size_t smem_bytes(int scap_, int tcap_, int nwarps) { return (size_t)scap_ * 20 + (size_t)3 * tcap_ * 8 + (size_t)nwarps * 32 * 8; }
     static __host__ __device__ size_t gmem_bytes(int ncap_) { return (size_t)ncap_ * 20 + (size_t)9 * ncap_ * 8; }
     __device__ void bind(unsigned char* smem, int scap_, int tcap_, char* gmem, int ncap_) {
         const unsigned base = (unsigned)__cvta_generic_to_shared(smem);
         skey_a[0] = base; skey_a[1] = base + (unsigned)scap_ * 8;
         sidx_a[0] = base + (unsigned)scap_ * 16; sidx_a[1] = base + (unsigned)scap_ * 18;
         stmp_a = base + (unsigned)scap_ * 20;
+        red_a = stmp_a + (unsigned)tcap_ * 24;
         scap = scap_; tcap = tcap_; ncap = ncap_;
         gkey[0] = (u64*)gmem; gkey[1] = gkey[0] + ncap_;
         gidx[0] = (u16*)(gkey[1] + ncap_); gidx[1] = gidx[0] + ncap_;
@@ -119,7 +122,10 @@ __device__ __forceinline__ void set_err(Scratch& S, int e) { atomicOr(S.gerr, e)
 // gtid<NT>() is the thread's index in its group, gsync<NT>() a named barrier (id 1 + group) over the group's NT
 // threads.  With a single group this is __syncthreads() under another name.
 template <int NT> __device__ __forceinline__ int gtid() { return (int)(threadIdx.x & (NT - 1)); }
-template <int NT> __device__ __forceinline__ void gsync() { asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x / NT)), "n"(NT) : "memory"); }
+template <int NT> __device__ __forceinline__ void gsync() {
+    if (NT == 32) __syncwarp();   // a one-warp group: warp-level barrier with memory ordering among its lanes
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x / NT)), "n"(NT) : "memory");
+}
 
 // sqrt is monotone, so {x : RN(sqrt(x)) <= thr} is a down-set {x <= X}.  Find X once per kernel; the hot loops then
 // compare squared norms and never take a square root, with bit-identical keep/drop decisions.
@@ -245,7 +251,7 @@ __device__ __forceinline__ int block_scan_sum(Scratch& S, int cnt, const double 
     for (int k = 0; k < VP; k++) v[k] = k < V ? red[k] : 0.0;
     warp_multi_sum_ru<VP>(v);
     if (lane == 31) S.iscan[warp] = incl;
-    if ((lane & ((32 >> Log2<VP>::value) - 1)) == 0) S.red[warp * VP + (lane >> (5 - Log2<VP>::value))] = v[0];
+    if ((lane & ((32 >> Log2<VP>::value) - 1)) == 0) S.red()[warp * VP + (lane >> (5 - Log2<VP>::value))] = v[0];
     gsync<NT>();
     int before = 0, all = 0;
 #pragma unroll
@@ -257,10 +263,24 @@ template <int NT, int V>
 __device__ __forceinline__ double block_total(const Scratch& S, int k) {
     constexpr int VP = Pow2Ceil<V>::value;
     double s = 0.0;
+    const double* red = S.red();
 #pragma unroll
-    for (int w = 0; w < NT / 32; w++) s = __dadd_ru(s, S.red[w * VP + k]);
+    for (int w = 0; w < NT / 32; w++) s = __dadd_ru(s, red[w * VP + k]);
     return s;
 }
+
+// Merge levels with at least this many candidates per thread use the merge-path merge (one diagonal search per thread,
+// then a sequential merge of the thread's output chunk) instead of one binary search per candidate.
+#ifndef ARMOUR_MERGE_PATH_MIN
+#define ARMOUR_MERGE_PATH_MIN 2
+#endif
+template <int NT> struct MergePathPolicy {
+    static __device__ __forceinline__ bool use(int N) {
+        if (NT >= 256) return N > NT;
+        if (NT == 128) return false;   // measured in round 1: the per-candidate search is 2 % faster at 128 threads x 4 CTAs per SM
+        return N > ARMOUR_MERGE_PATH_MIN * NT;
+    }
+};
 
 // ---- run-structured merge sort on (key, idx) ------------------------------------------------
 // Buffer 0 holds N entries laid out as sorted runs of width W (the last run may be shorter).
@@ -276,7 +296,7 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 mag
         const u16* ii = Buf<BIG>::idx(S, cur);
         u64* ko = Buf<BIG>::key(S, cur ^ 1);
         u16* io = Buf<BIG>::idx(S, cur ^ 1);
-        if (NT >= 256 && N > NT) {   // one plan, more than one candidate per thread (measured: -4 %); the sweep shape keeps the per-candidate search (merge path there: -2 %)
+        if (MergePathPolicy<NT>::use(N)) {   // more than MIN candidates per thread (one plan at 256 threads: -4 %; the narrow sweep shapes run several candidates per lane)
         // merge path: every thread owns a chunk of consecutive OUTPUT positions; one binary search along the chunk's
         // diagonal finds how many elements of each run precede it, then the chunk is merged sequentially.  (One search
         // per thread and level instead of one per candidate; order by (key, origin index), all pairs distinct.)

@@ -336,25 +336,37 @@ __device__ __noinline__ void export_torque(Scratch& S, const Tables& tb, size_t 
 // ---------------------------------------------------------------------------------------------
 // Working set of one interval.  The RNEA joint state (w, wdot, w_aux, linear_acc) is double-buffered by joint
 // parity so that the force/moment computation of joint i can run beside the chain update of joint i + 1.
-struct Slots {
+// Descriptors are split by how often they are touched.  The hot ones (the recursion state, read and rewritten by nearly every
+// operation) always live in shared memory, next to the per-group temporaries; the per-joint ones (each used by a handful of
+// operations of one joint) live in shared memory in the one-plan shapes and in the CTA's arena slice (global memory, L1-cached)
+// in the narrow sweep shapes, where 12-24 CTAs share an SM's shared memory.
+struct HotSlots {
     PZ<3> W[2], WD[2], WA[2], LA[2];
-    PZ<3> T[2][5];                       // temporaries, one set per thread group
+    PZ<3> Fv, Nv, FKT;
+    PZ<9> FKR;
+};
+struct ColdSlots {
     PZ<3> C1[NJ], C2[NJ];                // two-group hand-off: cross(com, F_i), cross(trans_{i+1}, R_{i+1} f_{i+1})
-    PZ<3> F[NJ], N[NJ], Fv, Nv, FKT, LINK[NJ], link0[NJ];
-    PZ<9> FKR, R[NJ + 1], Rt[NJ];
+    PZ<3> F[NJ], N[NJ], LINK[NJ], link0[NJ];
+    PZ<9> R[NJ + 1], Rt[NJ];
     PZ<1> qd[NJ], qda[NJ], qdda[NJ], u[NJ], cosq[NJ], sinq[NJ];
 };
-constexpr int N_BIG3 = 8 + 10 + 3 + 5 * NJ;
+struct Slots {
+    HotSlots& h;
+    ColdSlots& c;
+};
+constexpr int N_BIG3 = 8 + 10 + 3 + 5 * NJ;   // W/WD/WA/LA x 2, two temporary sets, Fv/Nv/FKT, C1/C2/F/N/LINK per joint
 
-size_t arena_bytes(int mcap, int ncap) {
-    size_t b = 0;
+__host__ __device__ constexpr size_t cold_arena_bytes() { return (sizeof(ColdSlots) + 255) & ~(size_t)255; }
+size_t arena_bytes(int mcap, int ncap, int groups) {
+    size_t b = cold_arena_bytes();                                // per-joint descriptors (narrow sweep shapes)
     b += (size_t)N_BIG3 * mcap * (8 + 3 * 8);                    // big 3-vectors
     b += (size_t)NJ * SMALL_CAP * (8 + 3 * 8);                    // link0
     b += (size_t)mcap * (8 + 9 * 8);                              // FK_R
     b += (size_t)(2 * NJ + 1) * SMALL_CAP * (8 + 9 * 8);          // R, R_t
     b += (size_t)5 * NJ * SMALL_CAP * 16;                         // qd, qda, qdda, cos, sin
     b += (size_t)NJ * mcap * 16;                                  // u
-    b += 2 * Scratch::gmem_bytes(ncap);                           // per-group sort / staging buffers of large operations
+    b += (size_t)groups * Scratch::gmem_bytes(ncap);              // per-group sort / staging buffers of large operations
     return (b + 255) & ~(size_t)255;
 }
 
@@ -391,9 +403,9 @@ __device__ __forceinline__ void group_wait(Scratch& S, volatile int* flag, int n
 // group-uniform test of a hand-off counter (thread 0 reads, the group barrier broadcasts)
 template <int NT>
 __device__ __forceinline__ bool group_ready(Scratch& S, volatile int* flag, int needed) {
-    if (gtid<NT>() == 0) { const int ok = *flag >= needed; if (ok) __threadfence_block(); S.iscan[33] = ok; }
+    if (gtid<NT>() == 0) { const int ok = *flag >= needed; if (ok) __threadfence_block(); S.iscan[17] = ok; }
     gsync<NT>();
-    const bool r = S.iscan[33] != 0;
+    const bool r = S.iscan[17] != 0;
     gsync<NT>();
     return r;
 }
@@ -407,26 +419,26 @@ __device__ void chain_joint(Scratch& S, Slots& Z, PZ<3>* T, int i, int p, int c)
     const int axis = rm.axes[i];
     const int row = (axis < 0 ? -axis : axis) - 1;
     // linear_acc = R_t * (linear_acc + cross(wdot, trans) + cross(w, cross(w_aux, trans)))   (line 16)
-    pz_cross_const<NT>(S, T[0], Z.WD[p], rm.trans[i], false);
-    pz_cross_const<NT>(S, T[1], Z.WA[p], rm.trans[i], false);
-    pz_cross_pp<NT>(S, T[2], Z.W[p], T[1]);
-    pz_add3<NT>(S, T[3], Z.LA[p], T[0]);
+    pz_cross_const<NT>(S, T[0], Z.h.WD[p], rm.trans[i], false);
+    pz_cross_const<NT>(S, T[1], Z.h.WA[p], rm.trans[i], false);
+    pz_cross_pp<NT>(S, T[2], Z.h.W[p], T[1]);
+    pz_add3<NT>(S, T[3], Z.h.LA[p], T[0]);
     pz_add3<NT>(S, T[3], T[3], T[2]);
-    pz_mul<NT, 9, 3, 3>(S, Z.LA[c], Z.Rt[i], T[3]);
+    pz_mul<NT, 9, 3, 3>(S, Z.h.LA[c], Z.c.Rt[i], T[3]);
     // w = R_t * w (+ qd_des on the joint axis)                                               (line 13)
-    pz_mul<NT, 9, 3, 3>(S, Z.W[c], Z.Rt[i], Z.W[p]);
-    if (axis != 0) pz_add_one_dim<NT>(S, Z.W[c], Z.W[c], Z.qd[i], row);
+    pz_mul<NT, 9, 3, 3>(S, Z.h.W[c], Z.c.Rt[i], Z.h.W[p]);
+    if (axis != 0) pz_add_one_dim<NT>(S, Z.h.W[c], Z.h.W[c], Z.c.qd[i], row);
     // w_aux = R_t * w_aux                                                                     (line 14)
-    pz_mul<NT, 9, 3, 3>(S, Z.WA[c], Z.Rt[i], Z.WA[p]);
+    pz_mul<NT, 9, 3, 3>(S, Z.h.WA[c], Z.c.Rt[i], Z.h.WA[p]);
     // wdot = R_t * wdot (+ cross(w_aux, qd_des * z) + qdda_des on the axis)                   (line 15)
-    pz_mul<NT, 9, 3, 3>(S, Z.WD[c], Z.Rt[i], Z.WD[p]);
+    pz_mul<NT, 9, 3, 3>(S, Z.h.WD[c], Z.c.Rt[i], Z.h.WD[p]);
     if (axis != 0) {
         pz_set_const<NT, 3>(T[0], zero3);
-        pz_add_one_dim<NT>(S, T[0], T[0], Z.qd[i], row);
-        pz_cross_pp<NT>(S, T[1], Z.WA[c], T[0]);
-        pz_add3<NT>(S, Z.WD[c], Z.WD[c], T[1]);
-        pz_add_one_dim<NT>(S, Z.WD[c], Z.WD[c], Z.qdda[i], row);
-        pz_add_one_dim<NT>(S, Z.WA[c], Z.WA[c], Z.qda[i], row);
+        pz_add_one_dim<NT>(S, T[0], T[0], Z.c.qd[i], row);
+        pz_cross_pp<NT>(S, T[1], Z.h.WA[c], T[0]);
+        pz_add3<NT>(S, Z.h.WD[c], Z.h.WD[c], T[1]);
+        pz_add_one_dim<NT>(S, Z.h.WD[c], Z.h.WD[c], Z.c.qdda[i], row);
+        pz_add_one_dim<NT>(S, Z.h.WA[c], Z.h.WA[c], Z.c.qda[i], row);
     }
 }
 // F = m * (linear_acc + cross(wdot, com) + cross(w, cross(w_aux, com))), N = I * wdot + cross(w_aux, I * w)
@@ -434,36 +446,36 @@ __device__ void chain_joint(Scratch& S, Slots& Z, PZ<3>* T, int i, int p, int c)
 template <int NT>
 __device__ void force_joint(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, int i, int c, const PZ<3>& LA) {
     const RobotModel& rm = c_robot;
-    pz_cross_const<NT>(S, T[0], Z.WD[c], rm.com[i], false);
-    pz_cross_const<NT>(S, T[1], Z.WA[c], rm.com[i], false);
-    pz_cross_pp<NT>(S, T[2], Z.W[c], T[1]);
+    pz_cross_const<NT>(S, T[0], Z.h.WD[c], rm.com[i], false);
+    pz_cross_const<NT>(S, T[1], Z.h.WA[c], rm.com[i], false);
+    pz_cross_pp<NT>(S, T[2], Z.h.W[c], T[1]);
     pz_add3<NT>(S, T[3], LA, T[0]);
     pz_add3<NT>(S, T[3], T[3], T[2]);
     {
         const double m0 = 0.0, m1 = __dmul_ru(tb.mass_unc, fabs(rm.mass[i]));
-        pz_const_left<NT>(S, Z.F[i], &rm.mass[i], &m0, &m1, true, T[3]);
+        pz_const_left<NT>(S, Z.c.F[i], &rm.mass[i], &m0, &m1, true, T[3]);
     }
     {
         double I0[9], I1[9];
         for (int k = 0; k < 9; k++) { I0[k] = 0.0; I1[k] = __dmul_ru(tb.inertia_unc, fabs(rm.inertia[i][k])); }
-        pz_const_left<NT>(S, T[0], rm.inertia[i], I0, I1, false, Z.WD[c]);
-        pz_const_left<NT>(S, T[1], rm.inertia[i], I0, I1, false, Z.W[c]);
+        pz_const_left<NT>(S, T[0], rm.inertia[i], I0, I1, false, Z.h.WD[c]);
+        pz_const_left<NT>(S, T[1], rm.inertia[i], I0, I1, false, Z.h.W[c]);
     }
-    pz_cross_pp<NT>(S, T[2], Z.WA[c], T[1]);
-    pz_add3<NT>(S, Z.N[i], T[0], T[2]);
+    pz_cross_pp<NT>(S, T[2], Z.h.WA[c], T[1]);
+    pz_add3<NT>(S, Z.c.N[i], T[0], T[2]);
 }
 // forward kinematics + reduce_link_PZ, one joint (KPR/Dynamics.cu:69-81, armour_main.cu:123-126)
 template <int NT>
 __device__ void fk_joint(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0, int i) {
     const RobotModel& rm = c_robot;
     const double zero3[3] = {0, 0, 0};
-    if (i == 0) { pz_set_const<NT, 9>(Z.FKR, rm.R0[NJ]); pz_set_const<NT, 3>(Z.FKT, zero3); }
-    pz_const_right<NT>(S, T[4], Z.FKR, rm.trans[i]);          // FK_R * P
-    pz_add3<NT>(S, Z.FKT, Z.FKT, T[4]);                       // FK_T = FK_T + FK_R * P
-    pz_mul<NT, 9, 9, 9>(S, Z.FKR, Z.FKR, Z.R[i]);             // FK_R = FK_R * R_i
-    pz_mul<NT, 9, 3, 3>(S, T[4], Z.FKR, Z.link0[i]);          // FK_R * link_i
-    pz_add3<NT>(S, Z.LINK[i], T[4], Z.FKT);                   //          + FK_T
-    export_link<NT>(S, tb, rec0 + i, Z.LINK[i]);
+    if (i == 0) { pz_set_const<NT, 9>(Z.h.FKR, rm.R0[NJ]); pz_set_const<NT, 3>(Z.h.FKT, zero3); }
+    pz_const_right<NT>(S, T[4], Z.h.FKR, rm.trans[i]);          // FK_R * P
+    pz_add3<NT>(S, Z.h.FKT, Z.h.FKT, T[4]);                       // FK_T = FK_T + FK_R * P
+    pz_mul<NT, 9, 9, 9>(S, Z.h.FKR, Z.h.FKR, Z.c.R[i]);             // FK_R = FK_R * R_i
+    pz_mul<NT, 9, 3, 3>(S, T[4], Z.h.FKR, Z.c.link0[i]);          // FK_R * link_i
+    pz_add3<NT>(S, Z.c.LINK[i], T[4], Z.h.FKT);                   //          + FK_T
+    export_link<NT>(S, tb, rec0 + i, Z.c.LINK[i]);
 }
 template <int NT>
 __device__ void forward_kinematics(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0) {
@@ -477,19 +489,19 @@ __device__ void backward_joint(Scratch& S, Slots& Z, PZ<3>* T, int i) {
     const int axis = rm.axes[i];
     const int row = (axis < 0 ? -axis : axis) - 1;
     // n = N + R * n + cross(com, F) + cross(trans_{i+1}, R * f)                              (line 29)
-    pz_mul<NT, 9, 3, 3>(S, T[0], Z.R[i + 1], Z.Nv);
-    pz_add3<NT>(S, T[1], Z.N[i], T[0]);
-    pz_cross_const<NT>(S, T[2], Z.F[i], rm.com[i], true);
+    pz_mul<NT, 9, 3, 3>(S, T[0], Z.c.R[i + 1], Z.h.Nv);
+    pz_add3<NT>(S, T[1], Z.c.N[i], T[0]);
+    pz_cross_const<NT>(S, T[2], Z.c.F[i], rm.com[i], true);
     pz_add3<NT>(S, T[1], T[1], T[2]);
-    pz_mul<NT, 9, 3, 3>(S, T[3], Z.R[i + 1], Z.Fv);             // R * f (the reference evaluates it twice)
+    pz_mul<NT, 9, 3, 3>(S, T[3], Z.c.R[i + 1], Z.h.Fv);             // R * f (the reference evaluates it twice)
     pz_cross_const<NT>(S, T[2], T[3], rm.trans[i + 1], true);
-    pz_add3<NT>(S, Z.Nv, T[1], T[2]);
+    pz_add3<NT>(S, Z.h.Nv, T[1], T[2]);
     // f = R * f + F                                                                           (line 28)
-    pz_add3<NT>(S, Z.Fv, T[3], Z.F[i]);
+    pz_add3<NT>(S, Z.h.Fv, T[3], Z.c.F[i]);
     if (axis != 0) {
         // u = n(axis) + armature * qdda_des + damping * qd_des
-        pz_merge<NT, 3, 1, 1>(S, Z.u[i], view_extract(Z.Nv, row), view_scaled(Z.qdda[i], rm.armature[i]), false);
-        pz_merge<NT, 1, 1, 1>(S, Z.u[i], view(Z.u[i]), view_scaled(Z.qd[i], rm.damping[i]), false);
+        pz_merge<NT, 3, 1, 1>(S, Z.c.u[i], view_extract(Z.h.Nv, row), view_scaled(Z.c.qdda[i], rm.armature[i]), false);
+        pz_merge<NT, 1, 1, 1>(S, Z.c.u[i], view(Z.c.u[i]), view_scaled(Z.c.qd[i], rm.damping[i]), false);
     }
 }
 
@@ -503,17 +515,17 @@ __device__ void angular_joint(Scratch& S, Slots& Z, PZ<3>* T, int i, int p, int 
     const double zero3[3] = {0, 0, 0};
     const int axis = rm.axes[i];
     const int row = (axis < 0 ? -axis : axis) - 1;
-    pz_mul<NT, 9, 3, 3>(S, Z.W[c], Z.Rt[i], Z.W[p]);
-    if (axis != 0) pz_add_one_dim<NT>(S, Z.W[c], Z.W[c], Z.qd[i], row);
-    pz_mul<NT, 9, 3, 3>(S, Z.WA[c], Z.Rt[i], Z.WA[p]);
-    pz_mul<NT, 9, 3, 3>(S, Z.WD[c], Z.Rt[i], Z.WD[p]);
+    pz_mul<NT, 9, 3, 3>(S, Z.h.W[c], Z.c.Rt[i], Z.h.W[p]);
+    if (axis != 0) pz_add_one_dim<NT>(S, Z.h.W[c], Z.h.W[c], Z.c.qd[i], row);
+    pz_mul<NT, 9, 3, 3>(S, Z.h.WA[c], Z.c.Rt[i], Z.h.WA[p]);
+    pz_mul<NT, 9, 3, 3>(S, Z.h.WD[c], Z.c.Rt[i], Z.h.WD[p]);
     if (axis != 0) {
         pz_set_const<NT, 3>(T[0], zero3);
-        pz_add_one_dim<NT>(S, T[0], T[0], Z.qd[i], row);
-        pz_cross_pp<NT>(S, T[1], Z.WA[c], T[0]);
-        pz_add3<NT>(S, Z.WD[c], Z.WD[c], T[1]);
-        pz_add_one_dim<NT>(S, Z.WD[c], Z.WD[c], Z.qdda[i], row);
-        pz_add_one_dim<NT>(S, Z.WA[c], Z.WA[c], Z.qda[i], row);
+        pz_add_one_dim<NT>(S, T[0], T[0], Z.c.qd[i], row);
+        pz_cross_pp<NT>(S, T[1], Z.h.WA[c], T[0]);
+        pz_add3<NT>(S, Z.h.WD[c], Z.h.WD[c], T[1]);
+        pz_add_one_dim<NT>(S, Z.h.WD[c], Z.h.WD[c], Z.c.qdda[i], row);
+        pz_add_one_dim<NT>(S, Z.h.WA[c], Z.h.WA[c], Z.c.qda[i], row);
     }
 }
 // group 1: linear_acc = R_t * (linear_acc + cross(wdot, trans) + cross(w, cross(w_aux, trans))) from the PREVIOUS
@@ -521,21 +533,21 @@ __device__ void angular_joint(Scratch& S, Slots& Z, PZ<3>* T, int i, int p, int 
 template <int NT>
 __device__ void linacc_joint(Scratch& S, Slots& Z, PZ<3>* T, int i, int p, PZ<3>& LA) {
     const RobotModel& rm = c_robot;
-    pz_cross_const<NT>(S, T[0], Z.WD[p], rm.trans[i], false);
-    pz_cross_const<NT>(S, T[1], Z.WA[p], rm.trans[i], false);
-    pz_cross_pp<NT>(S, T[2], Z.W[p], T[1]);
+    pz_cross_const<NT>(S, T[0], Z.h.WD[p], rm.trans[i], false);
+    pz_cross_const<NT>(S, T[1], Z.h.WA[p], rm.trans[i], false);
+    pz_cross_pp<NT>(S, T[2], Z.h.W[p], T[1]);
     pz_add3<NT>(S, T[3], LA, T[0]);
     pz_add3<NT>(S, T[3], T[3], T[2]);
-    pz_mul<NT, 9, 3, 3>(S, LA, Z.Rt[i], T[3]);
+    pz_mul<NT, 9, 3, 3>(S, LA, Z.c.Rt[i], T[3]);
 }
 // group 1, reverse recursion of f and the two cross terms of n (KPR/Dynamics.cu:163-169)
 template <int NT>
 __device__ void side_joint(Scratch& S, Slots& Z, PZ<3>* T, int i) {
     const RobotModel& rm = c_robot;
-    pz_mul<NT, 9, 3, 3>(S, T[3], Z.R[i + 1], Z.Fv);                       // R * f
-    pz_cross_const<NT>(S, Z.C2[i], T[3], rm.trans[i + 1], true);         // cross(trans, R * f)
-    pz_cross_const<NT>(S, Z.C1[i], Z.F[i], rm.com[i], true);             // cross(com, F)
-    pz_add3<NT>(S, Z.Fv, T[3], Z.F[i]);                                   // f = R * f + F
+    pz_mul<NT, 9, 3, 3>(S, T[3], Z.c.R[i + 1], Z.h.Fv);                       // R * f
+    pz_cross_const<NT>(S, Z.c.C2[i], T[3], rm.trans[i + 1], true);         // cross(trans, R * f)
+    pz_cross_const<NT>(S, Z.c.C1[i], Z.c.F[i], rm.com[i], true);             // cross(com, F)
+    pz_add3<NT>(S, Z.h.Fv, T[3], Z.c.F[i]);                                   // f = R * f + F
 }
 // group 0, reverse recursion of n and the torque (KPR/Dynamics.cu:163-179)
 template <int NT>
@@ -543,48 +555,55 @@ __device__ void moment_joint(Scratch& S, Slots& Z, PZ<3>* T, int i) {
     const RobotModel& rm = c_robot;
     const int axis = rm.axes[i];
     const int row = (axis < 0 ? -axis : axis) - 1;
-    pz_mul<NT, 9, 3, 3>(S, T[0], Z.R[i + 1], Z.Nv);
-    pz_add3<NT>(S, T[1], Z.N[i], T[0]);
-    pz_add3<NT>(S, T[1], T[1], Z.C1[i]);
-    pz_add3<NT>(S, Z.Nv, T[1], Z.C2[i]);
+    pz_mul<NT, 9, 3, 3>(S, T[0], Z.c.R[i + 1], Z.h.Nv);
+    pz_add3<NT>(S, T[1], Z.c.N[i], T[0]);
+    pz_add3<NT>(S, T[1], T[1], Z.c.C1[i]);
+    pz_add3<NT>(S, Z.h.Nv, T[1], Z.c.C2[i]);
     if (axis != 0) {
-        pz_merge<NT, 3, 1, 1>(S, Z.u[i], view_extract(Z.Nv, row), view_scaled(Z.qdda[i], rm.armature[i]), false);
-        pz_merge<NT, 1, 1, 1>(S, Z.u[i], view(Z.u[i]), view_scaled(Z.qd[i], rm.damping[i]), false);
+        pz_merge<NT, 3, 1, 1>(S, Z.c.u[i], view_extract(Z.h.Nv, row), view_scaled(Z.c.qdda[i], rm.armature[i]), false);
+        pz_merge<NT, 1, 1, 1>(S, Z.c.u[i], view(Z.c.u[i]), view_scaled(Z.c.qd[i], rm.damping[i]), false);
     }
 }
 
 // GROUPS == 1: one group of NT threads runs the whole program in the reference's order.
 // GROUPS == 2: see angular_joint / linacc_joint / side_joint / moment_joint above: the two groups run side by side and
 // hand PZs over through shared-memory counters; the critical path is roughly half of the 280 operations.
-template <int NT, int MINB, int GROUPS>
+// COLD_GLOBAL: the per-joint descriptors live in the CTA's arena slice instead of shared memory (narrow sweep shapes).
+template <int NT, int MINB, int GROUPS, bool COLD_GLOBAL>
 __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables tb, char* arena, size_t arena_stride, int mcap, int ncap, int scap, int tcap, int n_work) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Scratch SS[GROUPS];
-    __shared__ Slots Z;
+    __shared__ HotSlots ZH;
+    __shared__ PZ<3> TT[GROUPS][5];                        // temporaries, one set per thread group
     __shared__ volatile int sig_la, sig_state, sig_force, sig_side, sig_u;
     const RobotModel& rm = c_robot;
     const int group = threadIdx.x / NT;
     Scratch& S = SS[group];
-    PZ<3>* T = Z.T[group];
+    PZ<3>* T = TT[group];
+    constexpr size_t COLD_SMEM = COLD_GLOBAL ? 0 : (sizeof(ColdSlots) + 15) & ~(size_t)15;
+    ColdSlots& ZC = COLD_GLOBAL ? *reinterpret_cast<ColdSlots*>(arena + (size_t)blockIdx.x * arena_stride)
+                                : *reinterpret_cast<ColdSlots*>(smem_raw);
+    Slots Z{ZH, ZC};
     if (threadIdx.x == 0) {
-        char* g = arena + (size_t)blockIdx.x * arena_stride;
-        for (int k = 0; k < 2; k++) { g = carve<3>(Z.W[k], g, mcap); g = carve<3>(Z.WD[k], g, mcap); g = carve<3>(Z.WA[k], g, mcap); g = carve<3>(Z.LA[k], g, mcap); }
-        for (int k = 0; k < 2; k++) for (int t = 0; t < 5; t++) g = carve<3>(Z.T[k][t], g, mcap);
-        for (int i = 0; i < NJ; i++) { g = carve<3>(Z.C1[i], g, mcap); g = carve<3>(Z.C2[i], g, mcap); }
-        g = carve<3>(Z.Fv, g, mcap); g = carve<3>(Z.Nv, g, mcap); g = carve<3>(Z.FKT, g, mcap);
-        for (int i = 0; i < NJ; i++) { g = carve<3>(Z.F[i], g, mcap); g = carve<3>(Z.N[i], g, mcap); g = carve<3>(Z.LINK[i], g, mcap); g = carve<3>(Z.link0[i], g, SMALL_CAP); }
-        g = carve<9>(Z.FKR, g, mcap);
-        for (int i = 0; i <= NJ; i++) g = carve<9>(Z.R[i], g, SMALL_CAP);
-        for (int i = 0; i < NJ; i++) g = carve<9>(Z.Rt[i], g, SMALL_CAP);
+        char* g = arena + (size_t)blockIdx.x * arena_stride + cold_arena_bytes();
+        for (int k = 0; k < 2; k++) { g = carve<3>(Z.h.W[k], g, mcap); g = carve<3>(Z.h.WD[k], g, mcap); g = carve<3>(Z.h.WA[k], g, mcap); g = carve<3>(Z.h.LA[k], g, mcap); }
+        for (int k = 0; k < GROUPS; k++) for (int t = 0; t < 5; t++) g = carve<3>(TT[k][t], g, mcap);
+        for (int i = 0; i < NJ; i++) { g = carve<3>(Z.c.C1[i], g, mcap); g = carve<3>(Z.c.C2[i], g, mcap); }
+        g = carve<3>(Z.h.Fv, g, mcap); g = carve<3>(Z.h.Nv, g, mcap); g = carve<3>(Z.h.FKT, g, mcap);
+        for (int i = 0; i < NJ; i++) { g = carve<3>(Z.c.F[i], g, mcap); g = carve<3>(Z.c.N[i], g, mcap); g = carve<3>(Z.c.LINK[i], g, mcap); g = carve<3>(Z.c.link0[i], g, SMALL_CAP); }
+        g = carve<9>(Z.h.FKR, g, mcap);
+        for (int i = 0; i <= NJ; i++) g = carve<9>(Z.c.R[i], g, SMALL_CAP);
+        for (int i = 0; i < NJ; i++) g = carve<9>(Z.c.Rt[i], g, SMALL_CAP);
         #pragma unroll 1
         for (int i = 0; i < NJ; i++) {
-            g = carve<1>(Z.qd[i], g, SMALL_CAP); g = carve<1>(Z.qda[i], g, SMALL_CAP); g = carve<1>(Z.qdda[i], g, SMALL_CAP);
-            g = carve<1>(Z.cosq[i], g, SMALL_CAP); g = carve<1>(Z.sinq[i], g, SMALL_CAP);
-            g = carve<1>(Z.u[i], g, mcap);
+            g = carve<1>(Z.c.qd[i], g, SMALL_CAP); g = carve<1>(Z.c.qda[i], g, SMALL_CAP); g = carve<1>(Z.c.qdda[i], g, SMALL_CAP);
+            g = carve<1>(Z.c.cosq[i], g, SMALL_CAP); g = carve<1>(Z.c.sinq[i], g, SMALL_CAP);
+            g = carve<1>(Z.c.u[i], g, mcap);
         }
         const double thr_sq = squared_threshold(tb.thr);
+        const size_t group_smem = Scratch::smem_bytes(scap, tcap, NT / 32);
         for (int k = 0; k < GROUPS; k++) {
-            SS[k].bind(smem_raw + (size_t)k * Scratch::smem_bytes(scap, tcap), scap, tcap, g + (size_t)k * Scratch::gmem_bytes(ncap), ncap);
+            SS[k].bind(smem_raw + COLD_SMEM + (size_t)k * group_smem, scap, tcap, g + (size_t)k * Scratch::gmem_bytes(ncap), ncap);
             SS[k].thr = tb.thr; SS[k].thr_sq = thr_sq; SS[k].gerr = tb.err;
         }
     }
@@ -593,7 +612,10 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
 #ifdef ARMOUR_PHASE_TIMING
     if (threadIdx.x == 0) g_phase_clock.last = clock64();
 #endif
-    for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+    // persistent CTAs: the first gridDim.x work items are taken by block index, the rest from a global counter (interval
+    // cost varies about 2x along the trajectory and between problems, so a static stride leaves CTAs idle at the end)
+    __shared__ int next_work;
+    for (int work = blockIdx.x; work < n_work; work = next_work) {
         const int prob = work / tb.T, s = work - prob * tb.T;
         const size_t rec0 = ((size_t)prob * tb.T + s) * NJ;
         if (threadIdx.x == 0) { sig_la = 0; sig_state = 0; sig_force = 0; sig_side = 0; sig_u = 0; }
@@ -602,20 +624,20 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
         if (threadIdx.x < NJ) {
             const int i = threadIdx.x;
             if (tb.mode == 1) {
-                make_poly_zono_armtd(tb, prob, s, i, Z.R[i], Z.Rt[i], Z.cosq[i], Z.sinq[i], S.thr_sq);
-                PZ<1>* unused[3] = {&Z.qd[i], &Z.qda[i], &Z.qdda[i]};
+                make_poly_zono_armtd(tb, prob, s, i, Z.c.R[i], Z.c.Rt[i], Z.c.cosq[i], Z.c.sinq[i], S.thr_sq);
+                PZ<1>* unused[3] = {&Z.c.qd[i], &Z.c.qda[i], &Z.c.qdda[i]};
                 for (PZ<1>* z : unused) { z->n = 0; z->divM = FastDiv::magic(0); z->center[0] = 0; z->ind[0][0] = 0; z->ind[1][0] = 0; z->abss[0] = 0; }
             }
-            else make_poly_zono_joint(tb, prob, s, i, Z.R[i], Z.Rt[i], Z.qd[i], Z.qda[i], Z.qdda[i], Z.cosq[i], Z.sinq[i], S.thr_sq);
+            else make_poly_zono_joint(tb, prob, s, i, Z.c.R[i], Z.c.Rt[i], Z.c.qd[i], Z.c.qda[i], Z.c.qdda[i], Z.c.cosq[i], Z.c.sinq[i], S.thr_sq);
             if (tb.traj) {
                 SmallRec* rec = tb.traj + (((size_t)prob * tb.T + s) * TRAJ_TABLES) * NJ;
-                export_small<1>(rec[TRAJ_COS * NJ + i], Z.cosq[i]); export_small<1>(rec[TRAJ_SIN * NJ + i], Z.sinq[i]);
-                export_small<9>(rec[TRAJ_R * NJ + i], Z.R[i]); export_small<9>(rec[TRAJ_RT * NJ + i], Z.Rt[i]);
-                export_small<1>(rec[TRAJ_QD * NJ + i], Z.qd[i]); export_small<1>(rec[TRAJ_QDA * NJ + i], Z.qda[i]);
-                export_small<1>(rec[TRAJ_QDDA * NJ + i], Z.qdda[i]);
+                export_small<1>(rec[TRAJ_COS * NJ + i], Z.c.cosq[i]); export_small<1>(rec[TRAJ_SIN * NJ + i], Z.c.sinq[i]);
+                export_small<9>(rec[TRAJ_R * NJ + i], Z.c.R[i]); export_small<9>(rec[TRAJ_RT * NJ + i], Z.c.Rt[i]);
+                export_small<1>(rec[TRAJ_QD * NJ + i], Z.c.qd[i]); export_small<1>(rec[TRAJ_QDA * NJ + i], Z.c.qda[i]);
+                export_small<1>(rec[TRAJ_QDDA * NJ + i], Z.c.qdda[i]);
             }
             // original link boxes: stack of three scalar PZs, one generator each (KPR/Dynamics.cu:51-66)
-            PZ<3>& L0 = Z.link0[i];
+            PZ<3>& L0 = Z.c.link0[i];
             int n = 0;
             double ind[3] = {0, 0, 0}, abss[3] = {0, 0, 0};
             const u64 gk[3] = {key_qde(0), key_qdae(0), key_qddae(0)};
@@ -633,12 +655,12 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
             for (int c = 0; c < 3; c++) { L0.center[c] = rm.link_c[i][c]; L0.ind[0][c] = ind[c]; L0.ind[1][c] = ind[c]; L0.abss[c] = abss[c]; }
         }
         if (threadIdx.x == NJ) {   // R(NUM_JOINTS) = identity; initial RNEA state (KPR/Dynamics.cu:87-99) in set 1 (= "before joint 0")
-            PZ<9>& R = Z.R[NJ];
+            PZ<9>& R = Z.c.R[NJ];
             R.n = 0; R.divM = FastDiv::magic(0);
             for (int c = 0; c < 9; c++) { R.center[c] = rm.R0[NJ][c]; R.ind[0][c] = 0; R.ind[1][c] = 0; R.abss[c] = 0; }
-            PZ<3>* init[6] = {&Z.W[1], &Z.WD[1], &Z.WA[1], &Z.LA[1], &Z.Fv, &Z.Nv};
+            PZ<3>* init[6] = {&Z.h.W[1], &Z.h.WD[1], &Z.h.WA[1], &Z.h.LA[1], &Z.h.Fv, &Z.h.Nv};
             for (PZ<3>* z : init) { z->n = 0; z->divM = FastDiv::magic(0); for (int c = 0; c < 3; c++) { z->center[c] = 0; z->ind[0][c] = 0; z->ind[1][c] = 0; z->abss[c] = 0; } }
-            Z.LA[1].center[2] = rm.gravity;
+            Z.h.LA[1].center[2] = rm.gravity;
         }
         __syncthreads();
         phase_mark(PH_STAGE_A);
@@ -660,7 +682,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
             #pragma unroll 1
             for (int i = 0; i < NJ; i++) {                                                 // stage C forward
                 chain_joint<NT>(S, Z, T, i, (i + 1) & 1, i & 1);
-                force_joint<NT>(S, Z, T, tb, i, i & 1, Z.LA[i & 1]);
+                force_joint<NT>(S, Z, T, tb, i, i & 1, Z.h.LA[i & 1]);
             }
             #pragma unroll 1
             for (int i = NJ - 1; i >= 0; i--) backward_joint<NT>(S, Z, T, i);             // stage C backward
@@ -692,7 +714,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
             while (fk_next < NJ) { fk_joint<NT>(S, Z, T, tb, rec0, fk_next++); PIECE(pc_fk); }
         }
         else {
-            PZ<3>& LA = Z.LA[1];   // group 1's private linear_acc, initialised with gravity in stage A
+            PZ<3>& LA = Z.h.LA[1];   // group 1's private linear_acc, initialised with gravity in stage A
             #pragma unroll 1
             for (int i = 0; i < NJ; i++) {
                 group_wait<NT>(S, &sig_state, i);          // state of joint i-1 (the initial state for i = 0)
@@ -716,7 +738,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
             #pragma unroll 1
             for (int i = NJ - 1; i >= 0; i--) {
                 group_wait<NT>(S, &sig_u, NJ - i);
-                export_torque<NT>(S, tb, rec0 + i, Z.u[i]);
+                export_torque<NT>(S, tb, rec0 + i, Z.c.u[i]);
             }
         }
 #ifdef ARMOUR_PHASE_TIMING
@@ -727,7 +749,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
         // ---- stage M: disturbance, reduce(), torque radius (KPR/armour_main.cu:135-205) -------------
         if (GROUPS == 2 && tb.mode == 0) __syncthreads();   // group 1's exports are visible to thread 0
         if (group == 0 && tb.mode == 0) {
-            if (GROUPS == 1) for (int i = 0; i < NF; i++) export_torque<NT>(S, tb, rec0 + i, Z.u[i]);
+            if (GROUPS == 1) for (int i = 0; i < NF; i++) export_torque<NT>(S, tb, rec0 + i, Z.c.u[i]);
             if (threadIdx.x == 0) {
                 const size_t base = rec0;
                 // rho = sqrt(sum_i [-r_i, r_i]^2): only the upper end is used; everything rounded up
@@ -744,6 +766,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
                 }
             }
         }
+        if (threadIdx.x == 0) next_work = (int)gridDim.x + atomicAdd(tb.err + 1, 1);
         __syncthreads();
     }
     (void)zero3;
@@ -798,29 +821,47 @@ __global__ void __launch_bounds__(NT) pz_binary_kernel(int op, FlatPZ a, FlatPZ 
 // ---- host-side launch helpers -----------------------------------------------------------------
 cudaError_t upload_robot_model(const RobotModel& rm) { return cudaMemcpyToSymbol(c_robot, &rm, sizeof(RobotModel)); }
 
-size_t reach_smem_bytes(int scap, int tcap) { return Scratch::smem_bytes(scap, tcap); }
 size_t reach_gmem_bytes(int ncap) { return Scratch::gmem_bytes(ncap); }
 
-// kernel variants: (threads per group, CTAs per SM the register allocation is bounded for, thread groups per CTA)
+// kernel variants: (threads per group, CTAs per SM the register allocation is bounded for, thread groups per CTA,
+// per-joint descriptors in global memory).  One plan: 2 groups x 256 threads, 1 CTA per SM.  Sweeps: one group of 32 / 64 /
+// 128 threads per interval and as many CTAs per SM as shared memory and registers allow.
 typedef void (*ReachKernel)(Tables, char*, size_t, int, int, int, int, int);
-static ReachKernel pick_reach_kernel(int nt, int minb, int groups) {
-    if (groups == 2) return reach_build_kernel<256, 1, 2>;
-    if (nt == 128) return minb >= 8 ? reach_build_kernel<128, 8, 1> : minb >= 6 ? reach_build_kernel<128, 6, 1> : minb >= 4 ? reach_build_kernel<128, 4, 1> : reach_build_kernel<128, 2, 1>;
-    if (nt == 512) return reach_build_kernel<512, 1, 1>;
-    return minb >= 2 ? reach_build_kernel<256, 2, 1> : reach_build_kernel<256, 1, 1>;
+struct ReachVariant { ReachKernel k; int threads; int nwarps_per_group; int groups; bool cold_global; };
+static ReachVariant pick_reach_kernel(int nt, int minb, int groups) {
+    if (groups == 2) return {reach_build_kernel<256, 1, 2, false>, 512, 8, 2, false};
+    if (nt == 32) {
+        if (minb >= 24) return {reach_build_kernel<32, 24, 1, true>, 32, 1, 1, true};
+        if (minb >= 16) return {reach_build_kernel<32, 16, 1, true>, 32, 1, 1, true};
+        return {reach_build_kernel<32, 12, 1, true>, 32, 1, 1, true};
+    }
+    if (nt == 64) {
+        if (minb >= 12) return {reach_build_kernel<64, 12, 1, true>, 64, 2, 1, true};
+        return {reach_build_kernel<64, 8, 1, true>, 64, 2, 1, true};
+    }
+    if (nt == 128) {
+        if (minb >= 6) return {reach_build_kernel<128, 6, 1, true>, 128, 4, 1, true};
+        if (minb >= 4) return {reach_build_kernel<128, 4, 1, false>, 128, 4, 1, false};
+        return {reach_build_kernel<128, 2, 1, false>, 128, 4, 1, false};
+    }
+    if (nt == 512) return {reach_build_kernel<512, 1, 1, false>, 512, 16, 1, false};
+    if (minb >= 2) return {reach_build_kernel<256, 2, 1, false>, 256, 8, 1, false};
+    return {reach_build_kernel<256, 1, 1, false>, 256, 8, 1, false};
 }
-static int reach_threads(int nt, int groups) { return groups == 2 ? 512 : nt == 128 ? 128 : nt == 512 ? 512 : 256; }
+static size_t variant_smem(const ReachVariant& v, int scap, int tcap) {
+    return (v.cold_global ? 0 : ((sizeof(ColdSlots) + 15) & ~(size_t)15)) + (size_t)v.groups * Scratch::smem_bytes(scap, tcap, v.nwarps_per_group);
+}
 cudaError_t launch_reach_build(const Tables& tb, char* arena, size_t arena_stride, int mcap, int ncap, int scap, int tcap, int n_work, int grid, int nt, int minb, int groups, cudaStream_t stream) {
-    const size_t smem = reach_smem_bytes(scap, tcap) * (groups == 2 ? 2 : 1);
-    ReachKernel k = pick_reach_kernel(nt, minb, groups);
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const ReachVariant v = pick_reach_kernel(nt, minb, groups);
+    const size_t smem = variant_smem(v, scap, tcap);
+    cudaError_t e = cudaFuncSetAttribute(v.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<grid, reach_threads(nt, groups), smem, stream>>>(tb, arena, arena_stride, mcap, ncap, scap, tcap, n_work);
+    v.k<<<grid, v.threads, smem, stream>>>(tb, arena, arena_stride, mcap, ncap, scap, tcap, n_work);
     return cudaGetLastError();
 }
 
 cudaError_t launch_pz_binary(int op, const FlatPZ& a, const FlatPZ& b, const FlatPZ& r, FlatOut* out, char* gmem, int ncap, int scap, int tcap, double thr, int* err, cudaStream_t stream) {
-    const size_t smem = reach_smem_bytes(scap, tcap);
+    const size_t smem = Scratch::smem_bytes(scap, tcap, 8);
     cudaError_t e = cudaFuncSetAttribute(pz_binary_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     pz_binary_kernel<256><<<1, 256, smem, stream>>>(op, a, b, r, out, gmem, ncap, scap, tcap, thr, err);
@@ -846,13 +887,12 @@ void read_phase_cycles(unsigned long long* cycles, unsigned long long* calls, bo
 // resident CTAs per SM for a variant; 0 when it does not fit (e.g. two groups with large sort buffers)
 int reach_max_ctas_per_sm(int nt, int minb, int groups, int scap, int tcap) {
     int n = 0;
-    const size_t smem = reach_smem_bytes(scap, tcap) * (groups == 2 ? 2 : 1);
-    ReachKernel k = pick_reach_kernel(nt, minb, groups);
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, reach_threads(nt, groups), smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const ReachVariant v = pick_reach_kernel(nt, minb, groups);
+    const size_t smem = variant_smem(v, scap, tcap);
+    if (cudaFuncSetAttribute(v.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v.k, v.threads, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
 
 }  // namespace armour
 
-#include "reach_tasks.cuh"

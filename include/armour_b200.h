@@ -56,12 +56,16 @@ typedef struct armour_config {
     int max_monomials;          /* capacity of one PZ's monomial list; default 1024 (0 = default)  */
     int max_entries;            /* capacity of one sort (candidate monomials of one op); default 8192, at most 65535 (0 = default).
                                  * Operations up to 2048 candidates sort in shared memory, larger ones in global memory. */
-    int threads_per_cta;        /* 128, 256 or 512; 0 = default (256; 128 for a batch)    */
+    int threads_per_cta;        /* threads working on one time interval: 32, 64, 128, 256 or 512; 0 = default (one plan: two groups of
+                                 * 256; a batch: the measured sweep shape) */
     int device;                 /* CUDA device ordinal; -1 = current device              */
     int batch;                  /* problems one handle builds per armour_build_batch call; default 1 */
     int pin_user_buffers;       /* 1: armour_eval_g_jac page-locks the caller's g / values arrays (cudaHostRegister) and the
                                  * kernel writes into them directly, no staging copy.  The arrays must stay allocated until
                                  * armour_release_host_buffers / armour_destroy.  Default 0 (staging through pinned buffers). */
+    int export_trajectory_tables; /* the joint trajectory PZs (cos q, sin q, R, R_t, qd_des, qda_des, qdda_des; armour_get_pz tables
+                                 * 0..6) are only read by tests and the PZsparse facade: 1 = write them during the build, -1 = never,
+                                 * 0 = default (only for single-problem handles, cfg.batch == 1) */
 } armour_config;
 
 void armour_default_config(armour_config* cfg);

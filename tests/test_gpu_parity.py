@@ -268,17 +268,3 @@ def test_pinned_user_buffers_give_identical_results(gpu_lib):
     assert b.L.armour_release_host_buffers(b.h) == 0
     b.eval_g_jac(DEBUG_K, g, J)   # re-registers transparently
     assert np.array_equal(a.eval_g(DEBUG_K), g)
-
-
-@pytest.mark.gpu
-def test_task_scheduled_kernel_matches_oracle():
-    """The opt-in task-scheduled variant of the reach kernel (csrc/reach_tasks.cuh, ARMOUR_TUNE_TASKS=4: four thread groups
-    picking ready tasks from the interval's dependency graph) produces the same tables as the default kernel's oracle."""
-    import os, subprocess, sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, ARMOUR_TUNE_TASKS="4", ARMOUR_TUNE_TASK_SCAP="1536", ARMOUR_TUNE_TASK_TCAP="256")
-    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "tune_tasks.py"), "one"], env=env, capture_output=True, text=True, timeout=300)
-    res = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
-    assert res, out.stderr[-500:]
-    assert "mismatching tables 0 " in res[0], res[0]
-    assert float(res[0].split("diff|")[1]) < 1e-9
