@@ -26,7 +26,7 @@ EXPORTS = [
     "armour_eval_grad_f", "armour_eval_g", "armour_eval_jac_g", "armour_eval_g_jac", "armour_jac_structure", "armour_release_host_buffers", "armour_check_feasible",
     "armour_get_torque_radius", "armour_get_link_generators", "armour_get_link_sliced_center", "armour_get_hyperplanes",
     "armour_get_taylor_remainders", "armour_get_pz", "armour_pz_binary", "armour_last_build_ms", "armour_last_eval_ms",
-    "armour_kernel_launches", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_upload_x", "armour_standin_solve", "armour_debug_phase_cycles", "armour_measure_fp64_peak",
+    "armour_kernel_launches", "armour_set_kernel_timing", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_upload_x", "armour_standin_solve", "armour_debug_phase_cycles", "armour_measure_fp64_peak",
 ]
 
 
@@ -137,6 +137,8 @@ class Planner:
         cfg.export_trajectory_tables = int(export_trajectory_tables)
         self.T = T
         self.batch = batch
+        self.pin_user_buffers = bool(pin_user_buffers)
+        self._own = None
         self.k_range = np.array([cfg.k_range[i] for i in range(7)])
         self.n_obs = 0
         self.h = C.c_void_p()
@@ -267,11 +269,29 @@ class Planner:
         return v.reshape(self.m, 7)
 
     def eval_g_jac(self, x, g=None, values=None):
+        """Fused eval_g + eval_jac_g.  Under pin_user_buffers the library page-locks the arrays it is handed and keeps them
+        registered: when the caller passes none, results land in buffers this object owns for its lifetime (never in
+        temporaries that the garbage collector could free while still registered) and copies are returned."""
         m = self.m
+        own = g is None or values is None
+        if own and self.pin_user_buffers:
+            if self._own is None or self._own[0].size != m:
+                if self._own is not None:
+                    self._ck(self.L.armour_release_host_buffers(self.h))
+                self._own = (np.zeros(m), np.zeros(m * 7))
+            self._ck(self.L.armour_eval_g_jac(self.h, _dp(_vec(x, 7)), _dp(self._own[0]), _dp(self._own[1])))
+            if g is not None:
+                g[:] = self._own[0]
+            if values is not None:
+                values[:] = self._own[1]
+            return (self._own[0].copy() if g is None else g), (self._own[1].copy() if values is None else values).reshape(m, 7)
         g = np.zeros(m) if g is None else g
         values = np.zeros(m * 7) if values is None else values
         self._ck(self.L.armour_eval_g_jac(self.h, _dp(_vec(x, 7)), _dp(g), _dp(values)))
         return g, values.reshape(m, 7)
+
+    def set_kernel_timing(self, enabled):
+        self._ck(self.L.armour_set_kernel_timing(self.h, C.c_int(1 if enabled else 0)))
 
     def jac_structure(self):
         m = self.m

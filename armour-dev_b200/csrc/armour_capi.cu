@@ -127,6 +127,13 @@ struct armour_handle {
     int mode = 0;   // 0 ARMOUR, 1 ARMTD comparison planner
     double *d_state = nullptr, *d_obs = nullptr, *d_x = nullptr, *d_g = nullptr, *d_jac = nullptr, *d_link_center = nullptr;
     int* d_err = nullptr;
+    unsigned* d_done = nullptr;                    // blocks-finished counter of constraint_eval_kernel
+    volatile unsigned long long* h_done = nullptr; // completion word the kernel's last block writes (pinned, mapped)
+    unsigned long long* d_done_flag = nullptr;     // device alias of h_done
+    unsigned long long eval_seq = 0;
+    bool eval_timed = false;                       // events of the last evaluation are pending in ev[3], ev[4]
+    bool time_kernels = true;                      // record CUDA events around the per-iteration kernel (armour_set_kernel_timing)
+    int ucap = DEFAULT_UCAP, lcap = DEFAULT_LCAP;  // k-only table capacities (grown on overflow)
     // pinned host buffers
     double *h_state = nullptr, *h_obs = nullptr, *h_x = nullptr, *h_g = nullptr, *h_jac = nullptr, *h_torque_radius = nullptr;
     int* h_err = nullptr;
@@ -169,11 +176,24 @@ int alloc_arena(armour_handle* h) {
     return ARMOUR_OK;
 }
 
+// k-only monomial tables of the torque / link PZs (read by every constraint evaluation); capacities are runtime and grow
+int alloc_konly_tables(armour_handle* h) {
+    Tables& tb = h->tb;
+    for (void* p : {(void*)tb.u_keys, (void*)tb.u_coef, (void*)tb.l_keys, (void*)tb.l_coef}) if (p) cudaFree(p);
+    tb.u_keys = nullptr; tb.u_coef = nullptr; tb.l_keys = nullptr; tb.l_coef = nullptr;
+    const size_t P = h->P, T = h->T;
+    tb.ucap = h->ucap; tb.lcap = h->lcap;
+    CU(dalloc(&tb.u_keys, P * T * NF * h->ucap)); CU(dalloc(&tb.u_coef, P * T * NF * h->ucap));
+    CU(dalloc(&tb.l_keys, P * T * NJ * h->lcap)); CU(dalloc(&tb.l_coef, P * T * NJ * 3 * h->lcap));
+    return ARMOUR_OK;
+}
+
 int run_build(armour_handle* h) {   // kernels only; inputs already on the device
     const int n_work = h->count * h->T;
     Tables tb = h->tb;
     tb.P = h->count; tb.n_obs = h->n_obs; tb.mode = h->mode; tb.jrs = h->d_jrs; tb.k_range_in = h->d_krange;
-    for (int attempt = 0; attempt < 4; attempt++) {
+    for (int attempt = 0; attempt < 6; attempt++) {
+        tb.u_keys = h->tb.u_keys; tb.u_coef = h->tb.u_coef; tb.l_keys = h->tb.l_keys; tb.l_coef = h->tb.l_coef; tb.ucap = h->tb.ucap; tb.lcap = h->tb.lcap;
         CU(cudaMemsetAsync(h->d_err, 0, 2 * sizeof(int), h->stream));   // error word, work counter
         CU(cudaEventRecord(h->ev[0], h->stream));
         CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, h->scap, h->tcap, n_work, std::min(h->grid, n_work), h->nt, h->minb, h->groups, h->stream));
@@ -189,41 +209,95 @@ int run_build(armour_handle* h) {   // kernels only; inputs already on the devic
         cudaEventElapsedTime(&h->build_ms, h->ev[0], h->ev[2]);
         const int err = *h->h_err;
         if (err == 0) { h->built = true; h->have_eval = false; h->mirror_valid = false; return ARMOUR_OK; }
-        if (err & (8 | 16)) return fail(ARMOUR_E_NUMERIC, "reach-set build: unexpected monomial structure (error word " + std::to_string(err) + ")");
-        if (err & 4) return fail(ARMOUR_E_CAPACITY, "k-only monomial table capacity exceeded (UCAP/LCAP)");
-        // monomial / entry capacity exceeded: grow and retry (documented in armour_b200.h)
+        if (err & 16) return fail(ARMOUR_E_NUMERIC, "reach-set build: a monomial degree outgrew its key field (more than 3 for k / cos / sin error symbols, more than 1 for the others; KPR/PZsparse.h:23-40)");
+        if (err & 8) return fail(ARMOUR_E_NUMERIC, "reach-set build: a link PZ has a pure link generator other than the three box generators");
+        if (err & 32) return fail(ARMOUR_E_CUDA, "reach-set build: a hand-off between the two thread groups of a CTA timed out (internal error)");
+        // a capacity was exceeded: grow what overflowed and retry (documented in armour_b200.h)
         if ((err & 1) && h->ncap >= 65534) return fail(ARMOUR_E_CAPACITY, "an operation has more than 65535 candidate monomials");
+        if (err & (4 | 64)) {
+            if (err & 4) h->ucap *= 2;
+            if (err & 64) h->lcap *= 2;
+            h->mirror_valid = false;
+            int rc = alloc_konly_tables(h);
+            if (rc != ARMOUR_OK) return rc;
+        }
         if (err & 1) h->ncap = std::min(h->ncap * 2, 65534);
         if (err & 2) h->mcap *= 2;
         if (h->ncap < 2 * h->mcap) h->ncap = std::min(2 * h->mcap, 65534);
-        int rc = alloc_arena(h);
-        if (rc != ARMOUR_OK) return rc;
+        if (err & (1 | 2)) {
+            int rc = alloc_arena(h);
+            if (rc != ARMOUR_OK) return rc;
+        }
     }
     return fail(ARMOUR_E_CAPACITY, "monomial capacities exceeded after retries");
 }
 
-// One launch per call.  to_host: the kernel writes g and the Jacobian straight into the handle's pinned host
-// buffers (zero-copy over PCIe, overlapped with the computation); otherwise into device buffers (device-resident timing).
-int run_eval(armour_handle* h, const double* x, bool to_host) {
+// One launch per call.  g / jac: where the kernel writes (device buffers, the handle's pinned host buffers, or page-locked
+// caller arrays through their device alias).  host_visible: the results are read by the host right after — the kernel's last
+// block then stores a sequence number into a mapped completion word after a system-wide fence, and the host spins on that
+// word instead of calling cudaStreamSynchronize (saves the driver's wake-up latency on the per-iteration path).
+int launch_eval(armour_handle* h, const double* x, double* g, double* jac, bool host_visible) {
     if (!h->built) return fail(ARMOUR_E_STATE, "eval before build");
     if (x) memcpy(h->h_x, x, sizeof(double) * NF);
     Tables tb = h->tb;
     tb.P = h->count; tb.n_obs = h->n_obs; tb.mode = h->mode; tb.jrs = h->d_jrs; tb.k_range_in = h->d_krange;
-    CU(cudaEventRecord(h->ev[3], h->stream));
-    CU(launch_constraint_eval(tb, h->sel, h->h_x, to_host ? h->h_g : h->d_g, to_host ? h->h_jac : h->d_jac, h->d_link_center, h->stream));
-    CU(cudaEventRecord(h->ev[4], h->stream));
+    const bool timed = h->time_kernels || !host_visible;   // events are recorded here, read lazily by armour_last_eval_ms
+    if (timed) CU(cudaEventRecord(h->ev[3], h->stream));
+    const unsigned long long seq = ++h->eval_seq;
+    CU(launch_constraint_eval(tb, h->sel, h->h_x, g, jac, h->d_link_center, h->d_done, host_visible ? h->d_done_flag : nullptr, seq, h->stream));
+    if (timed) CU(cudaEventRecord(h->ev[4], h->stream));
     h->launches += 1;
-    CU(cudaStreamSynchronize(h->stream));
-    cudaEventElapsedTime(&h->eval_ms, h->ev[3], h->ev[4]);
+    if (host_visible) {
+        // bounded spin (about 50 ms), then fall back to the stream so that a faulted kernel surfaces as an error, not a hang
+        bool done = false;
+        for (long spin = 0; spin < 20000000L; spin++) {
+            if (*h->h_done == seq) { done = true; break; }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        if (!done) {
+            CU(cudaStreamSynchronize(h->stream));
+            if (*h->h_done != seq) return fail(ARMOUR_E_CUDA, "constraint evaluation did not signal completion");
+        }
+    }
+    else CU(cudaStreamSynchronize(h->stream));
+    h->eval_timed = timed;
+    return ARMOUR_OK;
+}
+int run_eval(armour_handle* h, const double* x, bool to_host) {
+    int rc = launch_eval(h, x, to_host ? h->h_g : h->d_g, to_host ? h->h_jac : h->d_jac, to_host);
+    if (rc != ARMOUR_OK) return rc;
     if (x && to_host) { memcpy(h->last_x, x, sizeof(double) * NF); h->have_eval = true; }
     return ARMOUR_OK;
 }
 
-void* pinned_alias(armour_handle* h, void* host, size_t bytes) {   // device alias of a caller array, registering it on first sight
-    for (auto& p : h->pinned) if (p.host == host && p.bytes >= bytes) return p.dev;
-    for (size_t i = 0; i < h->pinned.size(); i++)
-        if (h->pinned[i].host == host) { cudaHostUnregister(host); h->pinned.erase(h->pinned.begin() + i); break; }
-    if (h->pinned.size() >= 8) { cudaHostUnregister((void*)h->pinned[0].host); h->pinned.erase(h->pinned.begin()); }
+// Device alias of a caller array under cfg.pin_user_buffers, registering it on first sight.  `keep` is an alias resolved
+// earlier in the same call: its entry is never the one evicted.  A cached entry is re-validated with the driver before use
+// (cudaHostGetDevicePointer fails once the registration is gone); what the driver cannot see is a caller that frees a
+// registered array WITHOUT armour_release_host_buffers and gets the same address back from the allocator — the header
+// states that contract.
+void* pinned_alias(armour_handle* h, void* host, size_t bytes, const void* keep = nullptr) {
+    for (size_t i = 0; i < h->pinned.size(); i++) {
+        auto& p = h->pinned[i];
+        if (p.host != host) continue;
+        void* dev = nullptr;
+        if (p.bytes >= bytes && cudaHostGetDevicePointer(&dev, host, 0) == cudaSuccess && dev == p.dev) {
+            if (i + 1 != h->pinned.size()) { auto e = p; h->pinned.erase(h->pinned.begin() + i); h->pinned.push_back(e); }   // most recently used last
+            return dev;
+        }
+        cudaGetLastError();
+        cudaHostUnregister(host); cudaGetLastError();
+        h->pinned.erase(h->pinned.begin() + i);
+        break;
+    }
+    if (h->pinned.size() >= 8) {   // evict the least recently used entry that this call does not depend on
+        size_t victim = 0;
+        while (victim < h->pinned.size() && h->pinned[victim].dev == keep) victim++;
+        if (victim == h->pinned.size()) return nullptr;
+        cudaHostUnregister((void*)h->pinned[victim].host); cudaGetLastError();
+        h->pinned.erase(h->pinned.begin() + victim);
+    }
     if (cudaHostRegister(host, bytes, cudaHostRegisterMapped) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     void* dev = nullptr;
     if (cudaHostGetDevicePointer(&dev, host, 0) != cudaSuccess) { cudaGetLastError(); cudaHostUnregister(host); return nullptr; }
@@ -237,6 +311,7 @@ int ensure_mirror(armour_handle* h) {
     const size_t T = h->T, p = h->sel;
     h->m_traj.resize(T * TRAJ_TABLES * NJ);
     h->m_un.resize(T * NF); h->m_ln.resize(T * NJ);
+    const size_t UCAP = h->tb.ucap, LCAP = h->tb.lcap;
     h->m_ukeys.resize(T * NF * UCAP); h->m_ucoef.resize(T * NF * UCAP); h->m_ucenter.resize(T * NF); h->m_uind.resize(T * NF); h->m_dist.resize(T * NF);
     h->m_lkeys.resize(T * NJ * LCAP); h->m_lcoef.resize(T * NJ * 3 * LCAP); h->m_lcenter.resize(T * NJ * 3); h->m_lind.resize(T * NJ * 3);
     const Tables& tb = h->tb;
@@ -283,6 +358,7 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     armour_config cfg = *cfg_in;
     if (cfg.num_time_steps <= 0 || (cfg.num_time_steps & 1)) return fail(ARMOUR_E_INVALID, "num_time_steps must be a positive even number");
     if (cfg.max_obstacles < 0) return fail(ARMOUR_E_INVALID, "max_obstacles < 0");
+    if (cfg.max_obstacles > eval_max_obstacles()) return fail(ARMOUR_E_INVALID, "max_obstacles above 64 (the constraint kernel stages one link's half-space slab in shared memory; the reference's MAX_OBSTACLE_NUM is 40)");
     if (cfg.max_monomials <= 0) cfg.max_monomials = 1024;
     if (cfg.max_entries <= 0) cfg.max_entries = 8192;
     if (cfg.batch <= 0) cfg.batch = 1;
@@ -310,6 +386,8 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     if (nt == 32) { h->scap = 512; h->tcap = 128; }
     if (const char* e = getenv("ARMOUR_TUNE_MINB")) h->minb = atoi(e);
     if (const char* e = getenv("ARMOUR_TUNE_MCAP")) h->mcap = std::max(64, atoi(e));
+    if (const char* e = getenv("ARMOUR_TUNE_UCAP")) h->ucap = std::max(1, atoi(e));   // tests force the grow-and-retry path with tiny tables
+    if (const char* e = getenv("ARMOUR_TUNE_LCAP")) h->lcap = std::max(1, atoi(e));
     if (const char* e = getenv("ARMOUR_TUNE_NCAP")) h->ncap = std::min(std::max(256, atoi(e)), 65534) & ~1;
     // one plan (latency): two thread groups per CTA; a batch (throughput): one group per CTA and several resident CTAs per SM
     h->groups_cfg = (cfg.batch > 1 || nt != 256) ? 1 : 2;
@@ -334,9 +412,10 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     const bool want_traj = cfg.export_trajectory_tables > 0 || (cfg.export_trajectory_tables == 0 && cfg.batch == 1);
     if (want_traj) CU(dalloc(&tb.traj, P * T * TRAJ_TABLES * NJ));
     CU(dalloc(&tb.cos_rem, P * NJ * T * 2)); CU(dalloc(&tb.sin_rem, P * NJ * T * 2));
-    CU(dalloc(&tb.u_n, P * T * NF)); CU(dalloc(&tb.u_keys, P * T * NF * UCAP)); CU(dalloc(&tb.u_coef, P * T * NF * UCAP));
+    CU(dalloc(&tb.u_n, P * T * NF));
     CU(dalloc(&tb.u_center, P * T * NF)); CU(dalloc(&tb.u_ind, P * T * NF)); CU(dalloc(&tb.dist_rad, P * T * NF)); CU(dalloc(&tb.torque_radius, P * T * NF));
-    CU(dalloc(&tb.l_n, P * T * NJ)); CU(dalloc(&tb.l_keys, P * T * NJ * LCAP)); CU(dalloc(&tb.l_coef, P * T * NJ * 3 * LCAP));
+    CU(dalloc(&tb.l_n, P * T * NJ));
+    { int rc = alloc_konly_tables(h); if (rc != ARMOUR_OK) return rc; }
     CU(dalloc(&tb.l_center, P * T * NJ * 3)); CU(dalloc(&tb.l_ind, P * T * NJ * 3)); CU(dalloc(&tb.gens, P * T * NJ * 18));
     CU(dalloc(&tb.A, P * T * NJ * O * COMB * 3)); CU(dalloc(&tb.d, P * T * NJ * O * COMB)); CU(dalloc(&tb.delta, P * T * NJ * O * COMB));
     CU(dalloc(&h->d_err, 2)); tb.err = h->d_err;
@@ -346,6 +425,10 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     CU(cudaMallocHost((void**)&h->h_x, sizeof(double) * NF)); CU(cudaMallocHost((void**)&h->h_g, sizeof(double) * mmax));
     CU(cudaMallocHost((void**)&h->h_jac, sizeof(double) * mmax * NF)); CU(cudaMallocHost((void**)&h->h_torque_radius, sizeof(double) * P * T * NF));
     CU(cudaMallocHost((void**)&h->h_err, sizeof(int)));
+    CU(dalloc(&h->d_done, 1)); CU(cudaMemset(h->d_done, 0, sizeof(unsigned)));
+    CU(cudaHostAlloc((void**)&h->h_done, sizeof(unsigned long long), cudaHostAllocMapped));
+    *h->h_done = 0;
+    CU(cudaHostGetDevicePointer((void**)&h->d_done_flag, (void*)h->h_done, 0));
     int rc = alloc_arena(h);
     if (rc != ARMOUR_OK) return rc;
     return ARMOUR_OK;
@@ -359,9 +442,9 @@ void armour_destroy(armour_handle* h) {
     cudaGetLastError();
     Tables& tb = h->tb;
     void* dev[] = {h->d_jrs, h->d_krange, h->d_state, h->d_obs, tb.traj, tb.cos_rem, tb.sin_rem, tb.u_n, tb.u_keys, tb.u_coef, tb.u_center, tb.u_ind, tb.dist_rad, tb.torque_radius,
-                   tb.l_n, tb.l_keys, tb.l_coef, tb.l_center, tb.l_ind, tb.gens, tb.A, tb.d, tb.delta, h->d_err, h->d_x, h->d_g, h->d_jac, h->d_link_center, h->arena, h->bin_buf};
+                   tb.l_n, tb.l_keys, tb.l_coef, tb.l_center, tb.l_ind, tb.gens, tb.A, tb.d, tb.delta, h->d_err, h->d_x, h->d_g, h->d_jac, h->d_link_center, h->arena, h->bin_buf, h->d_done};
     for (void* p : dev) if (p) cudaFree(p);
-    void* pinned[] = {h->h_jrs, h->h_krange, h->h_state, h->h_obs, h->h_x, h->h_g, h->h_jac, h->h_torque_radius, h->h_err};
+    void* pinned[] = {h->h_jrs, h->h_krange, h->h_state, h->h_obs, h->h_x, h->h_g, h->h_jac, h->h_torque_radius, h->h_err, (void*)h->h_done};
     for (void* p : pinned) if (p) cudaFreeHost(p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -483,17 +566,10 @@ int armour_eval_g_jac(armour_handle* h, const double* x, double* g, double* valu
     if (h->cfg.pin_user_buffers && g && values && h->built) {   // zero staging: the kernel writes the caller's arrays
         const int m = m_of(h);
         double* dg = (double*)pinned_alias(h, g, sizeof(double) * m);
-        double* dj = dg ? (double*)pinned_alias(h, values, sizeof(double) * (size_t)m * NF) : nullptr;
+        double* dj = dg ? (double*)pinned_alias(h, values, sizeof(double) * (size_t)m * NF, dg) : nullptr;
         if (dg && dj) {
-            memcpy(h->h_x, x, sizeof(double) * NF);
-            Tables tb = h->tb;
-            tb.P = h->count; tb.n_obs = h->n_obs; tb.mode = h->mode; tb.jrs = h->d_jrs; tb.k_range_in = h->d_krange;
-            CU(cudaEventRecord(h->ev[3], h->stream));
-            CU(launch_constraint_eval(tb, h->sel, h->h_x, dg, dj, h->d_link_center, h->stream));
-            CU(cudaEventRecord(h->ev[4], h->stream));
-            h->launches += 1;
-            CU(cudaStreamSynchronize(h->stream));
-            cudaEventElapsedTime(&h->eval_ms, h->ev[3], h->ev[4]);
+            int rc = launch_eval(h, x, dg, dj, true);
+            if (rc != ARMOUR_OK) return rc;
             h->have_eval = false;
             return ARMOUR_OK;
         }
@@ -619,6 +695,7 @@ int armour_get_pz(armour_handle* h, int which, int idx, int t, int* dims, uint64
     }
     if (idx >= NJ) return fail(ARMOUR_E_INVALID, "joint index out of range");
     const size_t rec = (size_t)t * NJ + idx;
+    const size_t UCAP = h->tb.ucap, LCAP = h->tb.lcap;
     if (which == 7) {
         const int n = h->m_ln[rec];
         if (dims) { dims[0] = 3; dims[1] = 1; }
@@ -650,6 +727,13 @@ int armour_pz_binary(armour_handle* h, int op,
                      int cap, int* dims, uint64_t* keys, double* coeffs, double* center, double* independent) {
     if (!h || !dims || !keys || !coeffs || !center || !independent || !a_center || !b_center || !a_independent || !b_independent) return fail(ARMOUR_E_INVALID, "null argument");
     if (op < 0 || op > 3 || a_n < 0 || b_n < 0) return fail(ARMOUR_E_INVALID, "bad op");
+    {   // shapes are validated before any operand array is read (each array holds rows * cols values per monomial)
+        const bool a11 = a_rows == 1 && a_cols == 1, a31 = a_rows == 3 && a_cols == 1, a33 = a_rows == 3 && a_cols == 3;
+        const bool b11 = b_rows == 1 && b_cols == 1, b31 = b_rows == 3 && b_cols == 1, b33 = b_rows == 3 && b_cols == 3;
+        const bool ok = op == 0 ? ((a33 && (b31 || b33)) || (a11 && b11)) : op == 3 ? (a31 && b31) : ((a31 && b31) || (a11 && b11));
+        if (!ok) return fail(ARMOUR_E_INVALID, "unsupported operand shapes for this operation");
+        if ((a_n > 0 && (!a_keys || !a_coeffs)) || (b_n > 0 && (!b_keys || !b_coeffs)) || cap < 0) return fail(ARMOUR_E_INVALID, "null operand arrays");
+    }
     CU(cudaSetDevice(h->device));
     const int da = a_rows * a_cols, db = b_rows * b_cols;
     const int rcap = std::max(cap, 1), ncap = h->ncap;
@@ -686,12 +770,13 @@ int armour_pz_binary(armour_handle* h, int op,
     char* d_gmem = base + off; off += reach_gmem_bytes(ncap);
     int* d_err = (int*)(base + off); const size_t err_off = off; off += 64;
     CU(cudaMemcpyAsync(base, host.data(), need, cudaMemcpyHostToDevice, h->stream));
-    CU(launch_pz_binary(op, fa, fb, fr, d_out, d_gmem, ncap, h->scap, h->tcap, h->cfg.simplify_threshold, d_err, h->stream));
+    CU(launch_pz_binary(op, fa, fb, fr, d_out, d_gmem, ncap, std::min(h->scap, 2048), std::min(h->tcap, 512), h->cfg.simplify_threshold, d_err, h->stream));
     h->launches += 1;
     CU(cudaMemcpyAsync(host.data(), base, need, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     const int err = *(int*)(host.data() + err_off);
     const FlatOut o = *(FlatOut*)(host.data() + out_off);
+    if (err & 16) return fail(ARMOUR_E_NUMERIC, "a monomial degree outgrew its key field (KPR/PZsparse.h:23-40)");
     if (err & 2) return fail(ARMOUR_E_CAPACITY, "result does not fit in cap");
     if (err) return fail(ARMOUR_E_CAPACITY, "candidate list exceeds max_entries");
     if (o.n < 0) return fail(ARMOUR_E_INVALID, "unsupported operand shapes");
@@ -729,7 +814,18 @@ int armour_last_build_ms(armour_handle* h, float* total_ms, float* reach_kernel_
 }
 int armour_last_eval_ms(armour_handle* h, float* kernel_ms) {
     if (!h || !kernel_ms) return fail(ARMOUR_E_INVALID, "null argument");
+    if (h->eval_timed) {
+        CU(cudaEventSynchronize(h->ev[4]));
+        cudaEventElapsedTime(&h->eval_ms, h->ev[3], h->ev[4]);
+        h->eval_timed = false;
+    }
     *kernel_ms = h->eval_ms;
+    return ARMOUR_OK;
+}
+int armour_set_kernel_timing(armour_handle* h, int enabled) {
+    if (!h) return fail(ARMOUR_E_INVALID, "null argument");
+    h->time_kernels = enabled != 0;
+    if (!h->time_kernels) { h->eval_ms = -1.0f; h->eval_timed = false; }
     return ARMOUR_OK;
 }
 int armour_kernel_launches(armour_handle* h, uint64_t* launches) {

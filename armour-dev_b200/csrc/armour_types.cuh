@@ -7,8 +7,8 @@ namespace armour {
 constexpr int NJ = 7;       // NUM_JOINTS   (KPR/KinovaWithoutGripperInfo.h:10)
 constexpr int NF = 7;       // NUM_FACTORS  (:14)
 constexpr int COMB = 36;    // pairs of the 9 buffered generators (KPR/CollisionChecking.h:6-7)
-constexpr int UCAP = 128;   // k-only monomials kept per torque PZ after reduce()
-constexpr int LCAP = 64;    // k-only monomials kept per link PZ after reduce_link_PZ()
+constexpr int DEFAULT_UCAP = 128;   // k-only monomials kept per torque PZ after reduce(); runtime (Tables::ucap), grown on overflow
+constexpr int DEFAULT_LCAP = 64;    // k-only monomials kept per link PZ after reduce_link_PZ(); runtime (Tables::lcap)
 constexpr int SMALL_CAP = 4;
 
 // Robot constants (KPR/KinovaWithoutGripperInfo.h:10-112) after host-side preparation.
@@ -40,6 +40,7 @@ enum { TRAJ_COS = 0, TRAJ_SIN = 1, TRAJ_R = 2, TRAJ_RT = 3, TRAJ_QD = 4, TRAJ_QD
 
 struct Tables {
     int T, P, n_obs;
+    int ucap, lcap;            // capacities of the k-only monomial tables below
     double k_range[NF];
     double mass_unc, inertia_unc, thr;
     // inputs
@@ -54,16 +55,16 @@ struct Tables {
     double* sin_rem;
     // torque PZs after reduce(): k-only monomials
     int* u_n;                  // [P][T][NF]
-    unsigned long long* u_keys;   // [P][T][NF][UCAP]
-    double* u_coef;            // [P][T][NF][UCAP]
+    unsigned long long* u_keys;   // [P][T][NF][ucap]
+    double* u_coef;            // [P][T][NF][ucap]
     double* u_center;          // [P][T][NF]
     double* u_ind;             // [P][T][NF] radius after reduce()
     double* dist_rad;          // [P][T][NF] radius of u_nom_int - u_nom
     double* torque_radius;     // [P][T][NF]
     // link PZs after reduce_link_PZ()
     int* l_n;                  // [P][T][NJ]
-    unsigned long long* l_keys;   // [P][T][NJ][LCAP]
-    double* l_coef;            // [P][T][NJ][3][LCAP]
+    unsigned long long* l_keys;   // [P][T][NJ][lcap]
+    double* l_coef;            // [P][T][NJ][3][lcap]
     double* l_center;          // [P][T][NJ][3]
     double* l_ind;             // [P][T][NJ][3]
     double* gens;              // [P][T][NJ][18] 3x6 column-major

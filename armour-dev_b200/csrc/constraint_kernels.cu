@@ -16,44 +16,56 @@ __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a,
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 
 // pair (a, b), a < b, of the 9 buffered generators in the reference's enumeration order
-// (KPR/CollisionChecking.cu:26-39)
-__device__ __forceinline__ void pair_of(int p, int& a, int& b) {
-    int rem = p;
-    a = 0;
-    int row = 8;
-    while (rem >= row) { rem -= row; a++; row--; }
-    b = a + 1 + rem;
-}
+// (KPR/CollisionChecking.cu:26-39): (0,1) (0,2) ... (0,8) (1,2) ... (7,8)
+__constant__ unsigned char c_pair_a[COMB] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 6, 6, 7};
+__constant__ unsigned char c_pair_b[COMB] = {1, 2, 3, 4, 5, 6, 7, 8, 2, 3, 4, 5, 6, 7, 8, 3, 4, 5, 6, 7, 8, 4, 5, 6, 7, 8, 5, 6, 7, 8, 6, 7, 8, 7, 8, 8};
 
-// one thread per (problem, t, link, obs, pair)
-__global__ void hyperplane_kernel(Tables tb) {
-    const size_t total = (size_t)tb.P * tb.T * NJ * tb.n_obs * COMB;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int p = (int)(idx % COMB);
-        size_t r = idx / COMB;
-        const int o = (int)(r % tb.n_obs); r /= tb.n_obs;
-        const int link = (int)(r % NJ); r /= NJ;
-        const int t = (int)(r % tb.T);
-        const int prob = (int)(r / tb.T);
-        const double* ob = tb.obstacles + ((size_t)prob * tb.n_obs + o) * 12;
-        const double* lg = tb.gens + (((size_t)prob * tb.T + t) * NJ + link) * 18;
+// One block per (problem, t, link): the link's 3x6 generator block is staged once in shared memory, every thread owns one
+// (obstacle, pair) plane at a time.  All index arithmetic is 32-bit (the round-1 kernel decomposed a 64-bit flat index with
+// five 64-bit divisions per thread); results of a block are one contiguous run of A, d and delta.
+constexpr int HYPER_NT = 288;   // 8 obstacles x 36 pairs per pass
+__global__ void __launch_bounds__(HYPER_NT) hyperplane_kernel(Tables tb) {
+    __shared__ double lg[18];
+    const int n_obs = tb.n_obs;
+    const size_t rec = blockIdx.x;                      // (prob * T + t) * NJ + link
+    const int prob = (int)(rec / ((size_t)tb.T * NJ));
+    if (threadIdx.x < 18) lg[threadIdx.x] = tb.gens[rec * 18 + threadIdx.x];
+    __syncthreads();
+    const int p = threadIdx.x % COMB, o0 = threadIdx.x / COMB;
+    const int ia = c_pair_a[p], ib = c_pair_b[p];
+    for (int o = o0; o < n_obs; o += HYPER_NT / COMB) {
+        const double* ob = tb.obstacles + ((size_t)prob * n_obs + o) * 12;
         // buffered generators: 3 obstacle generators then the link's 3x6 block (bufferObstaclesKernel)
-        auto gen = [&](int g, int a) -> double { return g < 3 ? ob[(g + 1) * 3 + a] : lg[(g - 3) * 3 + a]; };
-        int ia, ib;
-        pair_of(p, ia, ib);
+        double G[9][3];
+#pragma unroll
+        for (int g = 0; g < 3; g++)
+#pragma unroll
+            for (int a = 0; a < 3; a++) G[g][a] = ob[(g + 1) * 3 + a];
+#pragma unroll
+        for (int g = 0; g < 6; g++)
+#pragma unroll
+            for (int a = 0; a < 3; a++) G[3 + g][a] = lg[g * 3 + a];
         double ga[3], gb[3];
-        for (int a = 0; a < 3; a++) { ga[a] = gen(ia, a); gb[a] = gen(ib, a); }
+#pragma unroll
+        for (int a = 0; a < 3; a++) { ga[a] = 0; gb[a] = 0; }
+#pragma unroll
+        for (int g = 0; g < 9; g++) {   // register-resident selection (no dynamically indexed local array)
+            if (g == ia) { ga[0] = G[g][0]; ga[1] = G[g][1]; ga[2] = G[g][2]; }
+            if (g == ib) { gb[0] = G[g][0]; gb[1] = G[g][1]; gb[2] = G[g][2]; }
+        }
         double cr[3];
         cr[0] = dadd(dmul(ga[1], gb[2]), -dmul(ga[2], gb[1]));
         cr[1] = dadd(dmul(ga[2], gb[0]), -dmul(ga[0], gb[2]));
         cr[2] = dadd(dmul(ga[0], gb[1]), -dmul(ga[1], gb[0]));
         const double nrm = __dsqrt_rn(dadd(dadd(dmul(cr[0], cr[0]), dmul(cr[1], cr[1])), dmul(cr[2], cr[2])));
         double C[3] = {0, 0, 0};
-        if (nrm > 0) for (int a = 0; a < 3; a++) C[a] = __ddiv_rn(cr[a], nrm);
+        if (nrm > 0) { C[0] = __ddiv_rn(cr[0], nrm); C[1] = __ddiv_rn(cr[1], nrm); C[2] = __ddiv_rn(cr[2], nrm); }
+        const size_t idx = (rec * n_obs + o) * COMB + p;
         tb.A[idx * 3 + 0] = C[0]; tb.A[idx * 3 + 1] = C[1]; tb.A[idx * 3 + 2] = C[2];
         tb.d[idx] = dadd(dadd(dmul(C[0], ob[0]), dmul(C[1], ob[1])), dmul(C[2], ob[2]));
         double dl = 0.0;
-        for (int j = 0; j < 9; j++) dl = dadd(dl, fabs(dadd(dadd(dmul(C[0], gen(j, 0)), dmul(C[1], gen(j, 1))), dmul(C[2], gen(j, 2)))));
+#pragma unroll
+        for (int j = 0; j < 9; j++) dl = dadd(dl, fabs(dadd(dadd(dmul(C[0], G[j][0]), dmul(C[1], G[j][1])), dmul(C[2], G[j][2]))));
         tb.delta[idx] = dl;
     }
 }
@@ -189,149 +201,249 @@ __device__ __forceinline__ double slice_term(double coef, u64 key, const double*
     return r;
 }
 
-constexpr int EVAL_NT = 256;
-constexpr int EVAL_MAX_OBS = 64;
-struct XArg { double x[NF]; };   // k passed by value: no host-to-device copy on the per-iteration path
-// grid: P_sel * (T * NJ + 1) blocks for the selected problem: block (t, j) handles torque row (t, j), link j
-// at interval t against every obstacle; the extra block handles the 28 limit rows.
-// g / jac may point to device memory or to pinned host memory (UVA): results of one block are staged in shared
-// memory and written out in contiguous runs, so that over PCIe they leave as full-width posted writes while the
-// rest of the grid is still computing (no separate device-to-host copy after the kernel).
-__global__ void __launch_bounds__(EVAL_NT) constraint_eval_kernel(Tables tb, int prob, XArg xarg, double* __restrict__ g, double* __restrict__ jac,
-                                                                  double* __restrict__ link_center_out) {
-    __shared__ double x[NF];
-    __shared__ double sg[EVAL_MAX_OBS], sjac[EVAL_MAX_OBS * NF];
-    __shared__ double terms[24][LCAP];      // link: 3 values + 21 gradients per monomial; torque rows reuse [0..7][UCAP/...]
-    __shared__ double uterms[8][UCAP];
+// ---- fused eval_g + eval_jac_g --------------------------------------------------------------------------------------
+// One block per (t, link) plus one for the 28 limit rows; every block of the benchmark configurations is resident at once
+// (7 blocks per SM x 148 SMs >= 7 T + 1 at T = 128, up to 20 obstacles).  The block's slab of the half-space table
+// (n_obs x 36 planes x 40 B, contiguous in A, d and delta) is fetched by three bulk asynchronous copies (TMA, completion on an
+// mbarrier) issued before anything else, so the table streams in while the block slices its two polynomial zonotopes at k.
+constexpr int EVAL_NT = 128;
+constexpr int EVAL_MAX_OBS = 64;      // shared-memory slab of the half-space table: 64 x 1440 B = 90 KB
+constexpr int EVAL_UCHUNK = 16;       // torque monomials staged per pass (x 8 outputs)
+constexpr int EVAL_LCHUNK = 5;        // link monomials staged per pass (x 24 outputs)
+struct XArg { double x[NF]; };        // k passed by value: no host-to-device copy on the per-iteration path
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+
+// dynamic shared memory of constraint_eval_kernel: the table slab, then a staging area used first for slice terms and then
+// for the block's output rows
+__host__ __device__ inline size_t eval_smem_bytes(int n_obs) {
+    const size_t slab = (size_t)n_obs * COMB * 40;
+    const size_t terms = (size_t)(8 * EVAL_UCHUNK + 24 * EVAL_LCHUNK) * 8;
+    const size_t rows = (size_t)n_obs * 8 * 8;
+    return slab + (terms > rows ? terms : rows);
+}
+
+// grid: T * NJ + 1 blocks for the selected problem: block (t, j) handles torque row (t, j) and link j at interval t against
+// every obstacle; the extra block handles the 28 limit rows.  g / jac may point to device memory or to pinned host memory
+// (UVA): the rows of one block are staged in shared memory and written out as contiguous runs, so over PCIe they leave as
+// full-width posted writes while the rest of the grid is still computing (no device-to-host copy after the kernel).
+// done_counter / done_flag: when done_flag != nullptr the last block to finish stores `seq` there (mapped pinned host memory)
+// after a system-wide fence — the host polls that word instead of synchronising the stream.
+__global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, int prob, XArg xarg, double* __restrict__ g, double* __restrict__ jac,
+                                                                     double* __restrict__ link_center_out, unsigned* done_counter,
+                                                                     volatile unsigned long long* done_flag, unsigned long long seq) {
+    extern __shared__ __align__(128) unsigned char eval_smem[];
+    __shared__ __align__(8) unsigned long long mbar_storage;
     __shared__ double lc[3], ldk[NF][3];
     const int T = tb.T, n_obs = tb.n_obs;
     const int tid = threadIdx.x;
-    if (tid < NF) x[tid] = xarg.x[tid];
-    __syncthreads();
     const int blk = blockIdx.x;
+    double x[NF];
+#pragma unroll
+    for (int i = 0; i < NF; i++) x[i] = xarg.x[i];
     const size_t off_obs = tb.mode == 0 ? (size_t)NF * T : 0, off_lim = off_obs + (size_t)NJ * T * n_obs;
+    const int n_planes = n_obs * COMB;
+    double* sA = reinterpret_cast<double*>(eval_smem);
+    double* sd = sA + (size_t)n_planes * 3;
+    double* sdl = sd + n_planes;
+    double* stage = sdl + n_planes;              // slice terms, later the block's output rows
     if (blk == T * NJ) {   // limit rows (KPR/NLPclass.cu:319-320, 393-394)
         if (tb.mode == 1) {   // KPA/NLPclass.cu:275-276
             if (tid < NF) {
                 const double* st = tb.state + (size_t)prob * 21;
                 double ext[4], gr[4];
-                armtd_state_extremum(st[tid], st[7 + tid], tb.k_range_in[(size_t)prob * NF + tid] * x[tid], ext, gr);
+                armtd_state_extremum(st[tid], st[7 + tid], tb.k_range_in[(size_t)prob * NF + tid] * xarg.x[tid], ext, gr);
                 for (int r = 0; r < 4; r++) {
                     const size_t row = off_lim + r * NF + tid;
                     g[row] = ext[r];
                     for (int j = 0; j < NF; j++) jac[row * NF + j] = (j == tid) ? gr[r] : 0.0;
                 }
             }
-            return;
         }
-        if (tid < 2 * NF) {
+        else if (tid < 2 * NF) {
             const int i = tid % NF;
             const bool velocity = tid >= NF;
             const double* st = tb.state + (size_t)prob * 21;
             const double kr = tb.k_range[i];
             double mn, mx, gmn, gmx;
-            joint_extremum(st[i], st[7 + i], st[14 + i], kr * x[i], velocity, &mn, &mx, &gmn, &gmx);
+            joint_extremum(st[i], st[7 + i], st[14 + i], kr * xarg.x[i], velocity, &mn, &mx, &gmn, &gmx);
             const size_t r0 = off_lim + (velocity ? 2 * NF : 0) + i, r1 = r0 + NF;
             g[r0] = mn; g[r1] = mx;   // DURATION == 1
             for (int j = 0; j < NF; j++) { jac[r0 * NF + j] = (i == j) ? gmn * kr : 0.0; jac[r1 * NF + j] = (i == j) ? gmx * kr : 0.0; }
         }
-        return;
     }
-    const int t = blk / NJ, j = blk - t * NJ;
-    const size_t rec = ((size_t)prob * T + t) * NJ + j;
-    // ---- torque row ------------------------------------------------------------------------------
-    const int un = tb.mode == 0 ? tb.u_n[rec] : 0;
-    for (int e = tid; e < un * 8; e += EVAL_NT) {
-        const int m = e >> 3, w = e & 7;
-        uterms[w][m] = slice_term(tb.u_coef[rec * UCAP + m], tb.u_keys[rec * UCAP + m], x, w == 0 ? -1 : w - 1);
-    }
-    // ---- link slice ------------------------------------------------------------------------------
-    const int ln = tb.l_n[rec];
-    for (int e = tid; e < ln * 24; e += EVAL_NT) {
-        const int m = e / 24, w = e - m * 24;
-        const int c = w % 3, which = w / 3;   // which 0: value, 1..7: d/dk_{which-1}
-        terms[w][m] = slice_term(tb.l_coef[(rec * 3 + c) * LCAP + m], tb.l_keys[rec * LCAP + m], x, which - 1);
-    }
-    __syncthreads();
-    if (tid < 8 && tb.mode == 0) {   // sequential sums in key order, like the reference's loop over the monomial list
-        double s = (tid == 0) ? tb.u_center[rec] : 0.0;
-        for (int m = 0; m < un; m++) s = s + uterms[tid][m];
-        const size_t row = (size_t)t * NF + j;
-        if (tid == 0) {
-            const double r = tb.u_ind[rec];
-            g[row] = ((s - r) + (s + r)) * 0.5;   // getCenter(Interval(c - r, c + r))
+    else {
+        const int t = blk / NJ, j = blk - t * NJ;
+        const size_t rec = ((size_t)prob * T + t) * NJ + j;
+        const unsigned mbar = smem_u32(&mbar_storage);
+        // ---- table slab: three bulk copies in flight from the first instruction on -----------------------------
+        if (tid == 0 && n_obs > 0) {
+            mbar_init(mbar, 1);
+            const size_t base = rec * n_obs * COMB;
+            mbar_expect_tx(mbar, (unsigned)n_planes * 40u);
+            bulk_g2s(smem_u32(sA), tb.A + base * 3, (unsigned)n_planes * 24u, mbar);
+            bulk_g2s(smem_u32(sd), tb.d + base, (unsigned)n_planes * 8u, mbar);
+            bulk_g2s(smem_u32(sdl), tb.delta + base, (unsigned)n_planes * 8u, mbar);
         }
-        else jac[row * NF + (tid - 1)] = s;
-    }
-    else if (tid >= 32 && tid < 32 + 24) {
-        const int w = tid - 32, c = w % 3, which = w / 3;
-        double s = (which == 0) ? tb.l_center[rec * 3 + c] : 0.0;
-        for (int m = 0; m < ln; m++) s = s + terms[w][m];
-        if (which == 0) {
-            const double r = tb.l_ind[rec * 3 + c];
-            const double v = ((s - r) + (s + r)) * 0.5;
-            lc[c] = v;
-            if (link_center_out) link_center_out[((size_t)t * NJ + j) * 3 + c] = v;
-        }
-        else ldk[which - 1][c] = s;
-    }
-    __syncthreads();
-    // ---- obstacle rows: one warp per obstacle (checkCollisionKernel) ---------------------------------
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int o = warp; o < n_obs; o += EVAL_NT / 32) {
-        const size_t base = (rec * n_obs + o) * COMB;
-        double best = -100000000.0;
-        int best_e = 0x7fffffff;   // order index 2*pair + (neg ? 1 : 0): the reference scans pos_0, neg_0, pos_1, ... and keeps the first maximum
-        for (int p = lane; p < COMB; p += 32) {
-            const double a0 = tb.A[(base + p) * 3], a1 = tb.A[(base + p) * 3 + 1], a2 = tb.A[(base + p) * 3 + 2];
-            double pos = -100000000.0, neg = -100000000.0;
-            if (__dsqrt_rn(dadd(dadd(dmul(a0, a0), dmul(a1, a1)), dmul(a2, a2))) > 0) {
-                const double dot = dadd(dadd(dmul(a0, lc[0]), dmul(a1, lc[1])), dmul(a2, lc[2]));
-                const double dd = tb.d[base + p], dl = tb.delta[base + p];
-                pos = dadd(dot, -dadd(dd, dl));
-                neg = dadd(-dot, -dadd(-dd, dl));
+        // ---- slices (PZsparse::slice, KPR/PZsparse.cu:404-555): terms in parallel, sums sequential in key order ----
+        const int un = tb.mode == 0 ? tb.u_n[rec] : 0;
+        const int ln = tb.l_n[rec];
+        const int UCAP = tb.ucap, LCAP = tb.lcap;
+        double* uterm = stage;                             // [8][EVAL_UCHUNK]
+        double* lterm = stage + 8 * EVAL_UCHUNK;           // [24][EVAL_LCHUNK]
+        // threads 0..7: torque value + 7 derivatives; threads 32..55: link value (3) + derivatives (21)
+        double acc = 0.0;
+        const bool sum_u = tid < 8, sum_l = tid >= 32 && tid < 56;
+        const int lw = tid - 32;
+        if (sum_u && tid == 0 && tb.mode == 0) acc = tb.u_center[rec];
+        if (sum_l && lw < 3) acc = tb.l_center[rec * 3 + lw];
+        const int u_passes = (un + EVAL_UCHUNK - 1) / EVAL_UCHUNK, l_passes = (ln + EVAL_LCHUNK - 1) / EVAL_LCHUNK;
+        const int passes = u_passes > l_passes ? u_passes : l_passes;
+        for (int ps = 0; ps < passes; ps++) {
+            const int ub = ps * EVAL_UCHUNK, uc = min(EVAL_UCHUNK, un - ub);
+            const int lb = ps * EVAL_LCHUNK, lcn = min(EVAL_LCHUNK, ln - lb);
+            // 8 * 16 torque terms on threads 0..127, 24 * 5 link terms on threads 0..119: two terms per thread and pass
+            if (tid < uc * 8) {
+                const int m = tid >> 3, w = tid & 7;
+                uterm[w * EVAL_UCHUNK + m] = slice_term(tb.u_coef[rec * UCAP + ub + m], tb.u_keys[rec * UCAP + ub + m], x, w - 1);
             }
-            if (pos > best) { best = pos; best_e = 2 * p; }
-            if (neg > best) { best = neg; best_e = 2 * p + 1; }
+            if (tid < lcn * 24) {
+                const int m = tid / 24, w = tid - m * 24;
+                const int c = w % 3, which = w / 3;   // which 0: value, 1..7: d/dk_{which-1}
+                lterm[w * EVAL_LCHUNK + m] = slice_term(tb.l_coef[(rec * 3 + c) * LCAP + lb + m], tb.l_keys[rec * LCAP + lb + m], x, which - 1);
+            }
+            __syncthreads();
+            if (sum_u) for (int m = 0; m < uc; m++) acc = acc + uterm[tid * EVAL_UCHUNK + m];
+            if (sum_l) for (int m = 0; m < lcn; m++) acc = acc + lterm[lw * EVAL_LCHUNK + m];
+            __syncthreads();
         }
-        // lanes whose candidates never beat the sentinel keep best_e = INT_MAX; the reference's thread 0 then
-        // reports max_id 0 / pos, i.e. order index 0
+        if (sum_u && tb.mode == 0) {
+            const size_t row = (size_t)t * NF + j;
+            if (tid == 0) {
+                const double r = tb.u_ind[rec];
+                g[row] = ((acc - r) + (acc + r)) * 0.5;   // getCenter(Interval(c - r, c + r))
+            }
+            else jac[row * NF + (tid - 1)] = acc;
+        }
+        if (sum_l) {
+            const int c = lw % 3, which = lw / 3;
+            if (which == 0) {
+                const double r = tb.l_ind[rec * 3 + c];
+                const double v = ((acc - r) + (acc + r)) * 0.5;
+                lc[c] = v;
+                if (link_center_out) link_center_out[((size_t)t * NJ + j) * 3 + c] = v;
+            }
+            else ldk[which - 1][c] = acc;
+        }
+        __syncthreads();
+        // ---- obstacle rows (checkCollisionKernel, KPR/CollisionChecking.cu:230-299): four lanes per obstacle, nine planes
+        // each; the reference scans pos_0, neg_0, pos_1, ... and keeps the FIRST maximum, i.e. the maximum value with the
+        // smallest order index 2 * plane + (neg ? 1 : 0) — a max-then-min reduction, independent of the reduction order.
+        if (n_obs > 0) {
+            mbar_wait(mbar, 0);
+            double* sg = stage;                  // [n_obs]
+            double* sjac = stage + n_obs;        // [n_obs][7]
+            const double c0 = lc[0], c1 = lc[1], c2 = lc[2];
+            const int q = tid & 3;
+            for (int o = tid >> 2; o < ((n_obs + 31) & ~31); o += EVAL_NT / 4) {   // whole warps stay in the loop for the shuffles
+                double best = -100000000.0;
+                int best_e = 0x7fffffff;
+                if (o < n_obs) {
+                    const int p0 = o * COMB + q * 9;
+#pragma unroll 3
+                    for (int i = 0; i < 9; i++) {
+                        const double a0 = sA[(p0 + i) * 3], a1 = sA[(p0 + i) * 3 + 1], a2 = sA[(p0 + i) * 3 + 2];
+                        double pos = -100000000.0, neg = -100000000.0;
+                        if (dadd(dadd(dmul(a0, a0), dmul(a1, a1)), dmul(a2, a2)) > 0) {   // A.norm() > 0  <=>  squared norm > 0
+                            const double dot = dadd(dadd(dmul(a0, c0), dmul(a1, c1)), dmul(a2, c2));
+                            const double dd = sd[p0 + i], dl = sdl[p0 + i];
+                            pos = dadd(dot, -dadd(dd, dl));
+                            neg = dadd(-dot, -dadd(-dd, dl));
+                        }
+                        if (pos > best) { best = pos; best_e = 2 * (q * 9 + i); }
+                        if (neg > best) { best = neg; best_e = 2 * (q * 9 + i) + 1; }
+                    }
+                }
 #pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, sft);
-            const int oe = __shfl_xor_sync(0xffffffffu, best_e, sft);
-            if (ob > best || (ob == best && oe < best_e)) { best = ob; best_e = oe; }
-        }
-        if (best_e == 0x7fffffff) best_e = 0;
-        if (lane == 0) sg[o] = -best;
-        if (lane < NF) {
-            const int p = best_e >> 1;
-            const bool neg = best_e & 1;
-            const double a0 = tb.A[(base + p) * 3], a1 = tb.A[(base + p) * 3 + 1], a2 = tb.A[(base + p) * 3 + 2];
-            const double dot = dadd(dadd(dmul(a0, ldk[lane][0]), dmul(a1, ldk[lane][1])), dmul(a2, ldk[lane][2]));
-            sjac[o * NF + lane] = neg ? dot : -dot;
+                for (int sft = 1; sft <= 2; sft <<= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, sft);
+                    const int oe = __shfl_xor_sync(0xffffffffu, best_e, sft);
+                    if (ob > best || (ob == best && oe < best_e)) { best = ob; best_e = oe; }
+                }
+                // no candidate beat the sentinel: the reference's thread 0 reports max_id 0 / pos, i.e. order index 0
+                if (best_e == 0x7fffffff) best_e = 0;
+                if (o < n_obs) {
+                    if (q == 0) sg[o] = -best;
+                    const int p = o * COMB + (best_e >> 1);
+                    const bool neg = best_e & 1;
+                    const double a0 = sA[p * 3], a1 = sA[p * 3 + 1], a2 = sA[p * 3 + 2];
+                    for (int k = q; k < NF; k += 4) {
+                        const double dot = dadd(dadd(dmul(a0, ldk[k][0]), dmul(a1, ldk[k][1])), dmul(a2, ldk[k][2]));
+                        sjac[o * NF + k] = neg ? dot : -dot;
+                    }
+                }
+            }
+            __syncthreads();
+            // rows (j*T + t)*n_obs + [0, n_obs) are contiguous in g and in jac: coalesced write-out
+            const size_t row0 = off_obs + ((size_t)j * T + t) * n_obs;
+            for (int e = tid; e < n_obs; e += EVAL_NT) g[row0 + e] = sg[e];
+            for (int e = tid; e < n_obs * NF; e += EVAL_NT) jac[row0 * NF + e] = sjac[e];
         }
     }
-    __syncthreads();
-    // rows (j*T + t)*n_obs + [0, n_obs) are contiguous in g and in jac: coalesced write-out
-    const size_t row0 = off_obs + ((size_t)j * T + t) * n_obs;
-    for (int e = tid; e < n_obs; e += EVAL_NT) g[row0 + e] = sg[e];
-    for (int e = tid; e < n_obs * NF; e += EVAL_NT) jac[row0 * NF + e] = sjac[e];
+    // ---- completion word for the polling host (see above) ----------------------------------------------------------
+    if (done_flag != nullptr) {
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned prev = atomicAdd(done_counter, 1u);
+            if (prev == gridDim.x - 1) {
+                *done_counter = 0;               // ready for the next launch (stream order)
+                __threadfence_system();
+                *done_flag = seq;
+            }
+        }
+    }
 }
 
 cudaError_t launch_hyperplanes(const Tables& tb, cudaStream_t stream) {
-    const size_t total = (size_t)tb.P * tb.T * NJ * tb.n_obs * COMB;
-    if (total == 0) return cudaSuccess;
-    const int nt = 288;
-    const int grid = (int)((total + nt - 1) / nt);
-    hyperplane_kernel<<<grid, nt, 0, stream>>>(tb);
+    const size_t blocks = (size_t)tb.P * tb.T * NJ;
+    if (blocks == 0 || tb.n_obs == 0) return cudaSuccess;
+    hyperplane_kernel<<<(unsigned)blocks, HYPER_NT, 0, stream>>>(tb);
     return cudaGetLastError();
 }
-cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* x_host, double* g, double* jac, double* link_center, cudaStream_t stream) {
+int eval_max_obstacles() { return EVAL_MAX_OBS; }
+cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* x_host, double* g, double* jac, double* link_center, unsigned* done_counter,
+                                   unsigned long long* done_flag, unsigned long long seq, cudaStream_t stream) {
     if (tb.n_obs > EVAL_MAX_OBS) return cudaErrorInvalidValue;
     XArg xa;
     for (int i = 0; i < NF; i++) xa.x[i] = x_host[i];
-    constraint_eval_kernel<<<tb.T * NJ + 1, EVAL_NT, 0, stream>>>(tb, prob, xa, g, jac, link_center);
+    const size_t smem = eval_smem_bytes(tb.n_obs);
+    if (smem > 48 * 1024) {   // more than 32 obstacles: opt in to a large dynamic shared-memory slab (off the benchmark path)
+        cudaError_t e = cudaFuncSetAttribute(constraint_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes(EVAL_MAX_OBS));
+        if (e != cudaSuccess) return e;
+    }
+    constraint_eval_kernel<<<tb.T * NJ + 1, EVAL_NT, smem, stream>>>(tb, prob, xa, g, jac, link_center, done_counter, done_flag, seq);
     return cudaGetLastError();
 }
 

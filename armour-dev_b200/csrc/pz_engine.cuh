@@ -44,7 +44,27 @@ static constexpr u64 KEY_K_ONLY = 1ull << 14;         // key < this  <=> depends
 static constexpr u64 KEY_K_LINKS_ONLY = 1ull << 35;   // (PZsparse.h:40)
 static constexpr u64 KEY_K_MASK = KEY_K_ONLY - 1;
 
-enum { ERR_NONE = 0, ERR_ENTRY_CAP = 1, ERR_MONO_CAP = 2, ERR_TABLE_CAP = 4, ERR_LINK_GEN = 8, ERR_DEGREE = 16 };
+enum { ERR_NONE = 0, ERR_ENTRY_CAP = 1, ERR_MONO_CAP = 2, ERR_TABLE_CAP = 4, ERR_LINK_GEN = 8, ERR_DEGREE = 16, ERR_SYNC = 32, ERR_LTABLE_CAP = 64 };
+
+// Degree-overflow guard for key addition.  The reference adds keys without checking ("do not have to check carry",
+// KPR/PZsparse.cu:938-940): a degree that outgrows its field (3 for the 2-bit fields, 1 for the 1-bit ones) silently corrupts
+// the neighbouring variable.  The carries INTO each bit of a + b are (a + b) ^ a ^ b; a carry into the first bit of a field (or
+// out of bit 62) is exactly an overflow of the field below it, the carry inside a 2-bit field (1 + 1 = 2) is legitimate.
+__host__ __device__ constexpr u64 field_start_mask() {
+    u64 m = 0;
+    for (int j = 1; j < 7; j++) m |= 1ull << (2 * j);            // k_1 .. k_6
+    for (int b = 14; b <= 35; b++) m |= 1ull << b;               // qde, qdae, qddae (1 bit each) and cosqe_0
+    for (int j = 1; j < 7; j++) m |= 1ull << (35 + 2 * j);       // cosqe_1 .. cosqe_6
+    for (int j = 0; j < 7; j++) m |= 1ull << (49 + 2 * j);       // sinqe_0 .. sinqe_6
+    m |= 1ull << 63;                                             // out of sinqe_6
+    return m;
+}
+static constexpr u64 KEY_FIELD_STARTS = field_start_mask();
+__device__ __forceinline__ u64 key_add_checked(u64 a, u64 b, u64& bad) {
+    const u64 s = a + b;
+    bad |= (s ^ a ^ b) & KEY_FIELD_STARTS;
+    return s;
+}
 
 template <int D>
 struct PZ {
@@ -623,13 +643,14 @@ __device__ __forceinline__ int fill_product_keys(Scratch& S, const u64* ka, int 
         for (int g = gtid<NT>(); g < N; g += NT) { key[g] = na ? ka[g] : kb[g]; idx[g] = (u16)g; }
         return N;
     }
+    u64 bad = 0;   // degree-overflow guard (key_add_checked)
     if (nb >= na) {   // runs: i = 0..na-1 (width nb), then B's own list (nb), then A's own list (na <= nb, last)
         W = nb; magicW = magic_b;
         const FastDiv fd(magic_b);
         #pragma unroll 1
         for (int g = gtid<NT>(); g < na * nb; g += NT) {
             const int i = fd.div(g), j = g - i * nb;
-            key[g] = ka[i] + kb[j];   // degrees add; no carry by construction (KPR/PZsparse.cu:938-940)
+            key[g] = key_add_checked(ka[i], kb[j], bad);   // degrees add (KPR/PZsparse.cu:938-940); an overflowing field sets ERR_DEGREE
             idx[g] = (u16)(na + nb + g);
         }
         const int o1 = na * nb;
@@ -645,7 +666,7 @@ __device__ __forceinline__ int fill_product_keys(Scratch& S, const u64* ka, int 
         #pragma unroll 1
         for (int g = gtid<NT>(); g < na * nb; g += NT) {
             const int j = fd.div(g), i = g - j * na;
-            key[g] = ka[i] + kb[j];
+            key[g] = key_add_checked(ka[i], kb[j], bad);
             idx[g] = (u16)(na + nb + i * nb + j);
         }
         const int o0 = na * nb;
@@ -655,6 +676,7 @@ __device__ __forceinline__ int fill_product_keys(Scratch& S, const u64* ka, int 
         #pragma unroll 1
         for (int j = gtid<NT>(); j < nb; j += NT) { key[o1 + j] = kb[j]; idx[o1 + j] = (u16)(na + j); }
     }
+    if (bad) set_err(S, ERR_DEGREE);
     return N;
 }
 

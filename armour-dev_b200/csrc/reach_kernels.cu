@@ -276,7 +276,8 @@ __device__ __noinline__ void export_link(Scratch& S, const Tables& tb, size_t re
     for (int g = g0; g < g1; g++) cnt += flag[g];
     int total;
     int off = block_scan_sum<NT, 3>(S, cnt, red, total);
-    if (total > LCAP) { if (gtid<NT>() == 0) set_err(S, ERR_TABLE_CAP); total = 0; }
+    const int LCAP = tb.lcap;
+    if (total > LCAP) { if (gtid<NT>() == 0) set_err(S, ERR_LTABLE_CAP); total = 0; }
     else {
         u64* ok = tb.l_keys + rec * LCAP;
         double* oc = tb.l_coef + rec * 3 * LCAP;
@@ -316,6 +317,7 @@ __device__ __noinline__ void export_torque(Scratch& S, const Tables& tb, size_t 
     for (int g = g0; g < g1; g++) cnt += flag[g];
     int total;
     int off = block_scan_sum<NT, 1>(S, cnt, red, total);
+    const int UCAP = tb.ucap;
     if (total > UCAP) { if (gtid<NT>() == 0) set_err(S, ERR_TABLE_CAP); total = 0; }
     else {
         u64* ok = tb.u_keys + rec * UCAP;
@@ -383,7 +385,6 @@ __device__ __noinline__ char* carve(PZ<D>& z, char* p, int cap) {
 // Monotonic counters in shared memory.  The producing group signals after an operation (whose closing group
 // barrier has made every thread's writes visible to its thread 0); the consuming group's thread 0 polls, then the
 // group barrier releases the rest.  The poll is bounded: a lost signal becomes an error word, never a hang.
-enum { ERR_SYNC = 32 };
 template <int NT>
 __device__ __forceinline__ void group_signal(volatile int* flag, int value) {
     if (gtid<NT>() == 0) { __threadfence_block(); *flag = value; }

@@ -39,7 +39,8 @@ extern "C" {
 #define ARMOUR_OK 0
 #define ARMOUR_E_INVALID (-1)  /* bad argument (null pointer, n_obs out of range, odd T ...) */
 #define ARMOUR_E_CUDA (-2)     /* CUDA runtime error or no usable device; see armour_last_error() */
-#define ARMOUR_E_CAPACITY (-3) /* a monomial list outgrew the configured capacities even after the automatic retry */
+#define ARMOUR_E_CAPACITY (-3) /* a monomial list outgrew the configured capacities even after the automatic retries (every
+                                * capacity — monomials per PZ, candidates per operation, k-only table rows — doubles and the build re-runs) */
 #define ARMOUR_E_STATE (-4)    /* call order violated (e.g. eval before build) */
 #define ARMOUR_E_NUMERIC (-5)  /* monomial degree overflow or more than 3 pure link generators */
 
@@ -52,7 +53,7 @@ typedef struct armour_config {
     double mass_uncertainty;    /* default 0.03                     (KinovaWithoutGripperInfo.h:41) */
     double inertia_uncertainty; /* default 0.03                     (KinovaWithoutGripperInfo.h:61) */
     double simplify_threshold;  /* SIMPLIFY_THRESHOLD, default 5e-4                     (Parameters.h:10) */
-    int max_obstacles;          /* MAX_OBSTACLE_NUM, default 40                         (Parameters.h:26) */
+    int max_obstacles;          /* MAX_OBSTACLE_NUM, default 40, at most 64             (Parameters.h:26) */
     int max_monomials;          /* capacity of one PZ's monomial list; default 1024 (0 = default)  */
     int max_entries;            /* capacity of one sort (candidate monomials of one op); default 8192, at most 65535 (0 = default).
                                  * Operations up to 2048 candidates sort in shared memory, larger ones in global memory. */
@@ -61,8 +62,10 @@ typedef struct armour_config {
     int device;                 /* CUDA device ordinal; -1 = current device              */
     int batch;                  /* problems one handle builds per armour_build_batch call; default 1 */
     int pin_user_buffers;       /* 1: armour_eval_g_jac page-locks the caller's g / values arrays (cudaHostRegister) and the
-                                 * kernel writes into them directly, no staging copy.  The arrays must stay allocated until
-                                 * armour_release_host_buffers / armour_destroy.  Default 0 (staging through pinned buffers). */
+                                 * kernel writes into them directly, no staging copy.  CONTRACT: the arrays must stay allocated
+                                 * until armour_release_host_buffers / armour_destroy — a registered array that is freed and whose
+                                 * address the allocator hands out again cannot be detected.  Pass the same arrays every call (Ipopt
+                                 * does); at most 8 distinct arrays are kept registered.  Default 0 (staging through pinned buffers). */
     int export_trajectory_tables; /* the joint trajectory PZs (cos q, sin q, R, R_t, qd_des, qda_des, qdda_des; armour_get_pz tables
                                  * 0..6) are only read by tests and the PZsparse facade: 1 = write them during the build, -1 = never,
                                  * 0 = default (only for single-problem handles, cfg.batch == 1) */
@@ -139,7 +142,9 @@ int armour_get_pz(armour_handle* h, int which, int idx, int t, int* dims, uint64
 
 /* ---- stand-alone PZsparse arithmetic on the device (PZsparse facade; primitive parity tests) --------- */
 /* op: 0 a*b, 1 a+b, 2 a-b, 3 cross(a,b) for 3x1 operands.  Shapes supported: (3x3)*(3x1), (3x3)*(3x3),
- * (1x1)*(1x1); + and - for 1x1 and 3x1.  Returns the monomial count or a negative error (-needed if > cap). */
+ * (1x1)*(1x1); + and - for 1x1 and 3x1; any other shape is rejected with ARMOUR_E_INVALID before anything is read.
+ * Returns the monomial count (>= 0) or a negative ARMOUR_E_* code: ARMOUR_E_CAPACITY when the result has more than `cap`
+ * monomials or the candidate list exceeds cfg.max_entries, ARMOUR_E_NUMERIC when a monomial degree outgrows its key field. */
 int armour_pz_binary(armour_handle* h, int op,
                      int a_rows, int a_cols, int a_n, const uint64_t* a_keys, const double* a_coeffs, const double* a_center, const double* a_independent,
                      int b_rows, int b_cols, int b_n, const uint64_t* b_keys, const double* b_coeffs, const double* b_center, const double* b_independent,
@@ -154,6 +159,9 @@ int armour_standin_solve(armour_handle* h, const double* q_des, double t_plan, d
 /* device time of the last build / eval in milliseconds (CUDA events on the handle's stream) */
 int armour_last_build_ms(armour_handle* h, float* total_ms, float* reach_kernel_ms, float* hyperplane_kernel_ms);
 int armour_last_eval_ms(armour_handle* h, float* kernel_ms);
+/* The per-iteration path records two CUDA events per call for armour_last_eval_ms (about 2 us of host time); 0 switches them
+ * off for host-buffer evaluations (armour_last_eval_ms then reports -1), 1 (default) back on. */
+int armour_set_kernel_timing(armour_handle* h, int enabled);
 /* kernels launched by this handle since creation */
 int armour_kernel_launches(armour_handle* h, uint64_t* launches);
 /* build with inputs already resident on the device (armour_build without the host<->device copies);

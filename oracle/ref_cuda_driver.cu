@@ -9,6 +9,7 @@
 // tests/test_reference_pin.py to pin constraints and Jacobians of the device path against the reference itself.
 #include "NLPclass.h"
 
+#include <chrono>
 #include <cstdint>
 
 namespace {
@@ -21,6 +22,7 @@ struct RefCudaPlan {
     std::vector<Eigen::Matrix<double, 3, 3 + 3>> link_gens;
     Eigen::MatrixXd torque_radius;
     Eigen::VectorXd q_des;
+    double build_ms = 0.0;   // the reference's own "Time taken by generating reachable sets" span (KPR/armour_main.cu:89-226)
     ~RefCudaPlan() { delete nlp; delete O; delete kd; delete traj; }
 };
 }  // namespace
@@ -35,7 +37,8 @@ void* refcuda_build(const double* q0_in, const double* qd0_in, const double* qdd
     p->obstacles.assign(obstacles, obstacles + (size_t)num_obstacles * (MAX_OBSTACLE_GENERATOR_NUM + 1) * 3);
     omp_set_num_threads(num_threads > 0 ? num_threads : 1);
     try {
-        p->O = new Obstacles(p->obstacles.data(), num_obstacles);
+        p->O = new Obstacles(p->obstacles.data(), num_obstacles);   // KPR/armour_main.cu:87, before the reference starts its timer (:89)
+        const auto t_start = std::chrono::high_resolution_clock::now();
         p->traj = new BezierCurve(q0, qd0, qdd0);
         int s = 0;
 #pragma omp parallel for private(s) schedule(dynamic, 1)
@@ -66,6 +69,7 @@ void* refcuda_build(const double* q0_in, const double* qd0_in, const double* qdd
             for (int i = 0; i < NUM_FACTORS; i++) p->torque_radius(i, t) += friction[i];
         }
         p->O->initializeHyperPlane(p->link_gens.data());
+        p->build_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t_start).count();   // :224-226
         p->nlp = new armtd_NLP();
         p->nlp->set_parameters(p->q_des, t_plan, p->traj, p->kd, &p->torque_radius, p->O);
     } catch (...) {
@@ -76,6 +80,10 @@ void* refcuda_build(const double* q0_in, const double* qd0_in, const double* qdd
     return p;
 }
 void refcuda_destroy(void* h) { delete (RefCudaPlan*)h; }
+int refcuda_num_time_steps() { return NUM_TIME_STEPS; }
+double refcuda_k_range(int i) { return k_range[i]; }
+double refcuda_mass_uncertainty() { return mass_uncertainty; }
+double refcuda_last_build_ms(void* h) { return ((RefCudaPlan*)h)->build_ms; }
 
 int refcuda_get_nlp_info(void* h, int* n, int* m, int* nnz_jac_g, int* nnz_h_lag) {
     Ipopt::TNLP::IndexStyleEnum style;

@@ -40,7 +40,7 @@ for r in csv.reader(io.StringIO(src)):
         for i, c in stall_cols: stall[c] += int(r[i] or 0)
 ts, ti = sum(v[0] for v in agg.values()), sum(v[1] for v in agg.values())
 with open(os.path.join(P, "%s_batch_hot_lines.txt" % out), "w") as f:
-    f.write("reach_build_kernel<128,4,1> (sweep shape): warp-stall samples and executed warp instructions per source line (ncu --set full, source page)\n")
+    f.write("reach_build_kernel (" + tag + "): warp-stall samples and executed warp instructions per source line (ncu --set full, source page)\n")
     tot = sum(stall.values())
     f.write("stall reasons: " + ", ".join("%s %.1f%%" % (k[6:], 100.0 * v / tot) for k, v in stall.most_common(8)) + "\n")
     f.write("static SASS instructions %d, executed warp instructions %d\n" % (sum(v[2] for v in agg.values()), ti))

@@ -323,12 +323,20 @@ def reference_available():
     return os.path.exists(REF_LIB_PATH)
 
 
+def ref_variant_path(base, variant=None):
+    """oracle/_ref/<base>[_<variant>].so.  Variants (oracle/Makefile): "T512u5" = NUM_TIME_STEPS 512 and 5 % mass / inertia
+    uncertainty (BASELINE.json configs[3]), "k24" = k_range pi/24 (KPR/debug_script.m:35), "nofma" (CUDA build only) = the
+    reference's device code without FMA contraction."""
+    return os.path.join(ORACLE_DIR, "_ref", base + ("_" + variant if variant else "") + ".so")
+
+
 class Reference:
     """The reference's own reach-set build (KPR/armour_main.cu:94-205 call sequence) through oracle/ref_driver.cpp.
-    T, k_range and the thresholds are the reference's compile-time values (T = 128, pi/48, 5e-4)."""
+    T, k_range and the thresholds are the reference's compile-time values (T = 128, pi/48, 5e-4; other values through the
+    temporarily patched variant builds, see ref_variant_path)."""
 
-    def __init__(self, num_threads=None):
-        self.L = C.CDLL(REF_LIB_PATH)
+    def __init__(self, num_threads=None, variant=None):
+        self.L = C.CDLL(ref_variant_path("libref", variant))
         self.L.ref_build.restype = C.c_void_p
         self.L.ref_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         self.L.ref_destroy.argtypes = [C.c_void_p]
@@ -398,11 +406,18 @@ class ReferenceCuda:
     """The reference's complete path, its own CUDA kernels and TNLP callbacks included (oracle/ref_cuda_driver.cu over
     KPR/*.cu built by nvcc).  Needs a GPU.  Method names follow armtd_NLP."""
 
-    def __init__(self, num_threads=None):
-        self.L = C.CDLL(REF_CUDA_LIB_PATH)
+    def __init__(self, num_threads=None, variant=None):
+        self.L = C.CDLL(ref_variant_path("libref_cuda", variant))
         self.L.refcuda_build.restype = C.c_void_p
         self.L.refcuda_build.argtypes = [C.c_void_p] * 4 + [C.c_double, C.c_void_p, C.c_int, C.c_int]
         self.L.refcuda_destroy.argtypes = [C.c_void_p]
+        self.L.refcuda_k_range.restype = C.c_double
+        self.L.refcuda_mass_uncertainty.restype = C.c_double
+        self.L.refcuda_last_build_ms.restype = C.c_double
+        self.L.refcuda_last_build_ms.argtypes = [C.c_void_p]
+        self.T = self.L.refcuda_num_time_steps()
+        self.k_range = np.array([self.L.refcuda_k_range(i) for i in range(NF)])
+        self.mass_uncertainty = self.L.refcuda_mass_uncertainty()
         self.num_threads = num_threads or len(os.sched_getaffinity(0))
         self.h = None
 
@@ -459,9 +474,13 @@ class ReferenceCuda:
         return bool(self.L.refcuda_check_feasible(self.h, _dp(_vec(x, 7)), self.m, _dp(g)))
 
     def link_sliced_center(self):
-        out = np.zeros(128 * NJ * 3)
+        out = np.zeros(self.T * NJ * 3)
         self.L.refcuda_get_link_sliced_center(self.h, _dp(out))
-        return out.reshape(128, NJ, 3)
+        return out.reshape(self.T, NJ, 3)
+
+    def last_build_ms(self):
+        """The reference's own timed span (KPR/armour_main.cu:89-226): starts after the Obstacles constructor."""
+        return self.L.refcuda_last_build_ms(self.h)
 
 
 REF_ARMTD_LIB_PATH = os.path.join(ORACLE_DIR, "_ref", "libref_armtd_cuda.so")

@@ -73,3 +73,15 @@ def make_jrs_tables(qd0, k_range, T):
                 r = float(np.abs(v - c - g * ks[:, None]).max())
                 jrs[base, i, s], jrs[base + 1, i, s], jrs[base + 2, i, s] = c, g, r
     return jrs
+
+
+def saved_worlds():
+    """The reference's 100 saved random worlds (kinova_src/saved_worlds/random/scene_*.csv), packed by
+    tests/golden/make_saved_worlds.py: list of (name, start q, goal q, obstacles[n_obs * 12])."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "worlds_saved_random.npz"))
+    out, off = [], 0
+    for name, q, g, n in zip(d["names"], d["start"], d["goal"], d["n_obs"]):
+        out.append((str(name), q.copy(), g.copy(), d["obstacles"][off:off + n].ravel().copy()))
+        off += n
+    return out

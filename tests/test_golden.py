@@ -9,7 +9,7 @@ import pytest
 import _oracle
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith("controller_"))   # controller fixtures: tests/test_controller.py
+FIXTURES = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith(("controller_", "worlds_")))   # controller fixtures: tests/test_controller.py
 
 
 def k_only(backend, T):

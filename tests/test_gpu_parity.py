@@ -7,6 +7,7 @@ Tolerances are the ones BASELINE.json's north_star states:
     interval enclosures must additionally contain the oracle's (>=, <= on the end points)
   * constraint values and Jacobians: 1e-8
 """
+import os
 import zlib
 
 import numpy as np
@@ -17,6 +18,7 @@ import armour_b200 as ab
 from problems import DEBUG_K, DEBUG_Q0, DEBUG_QD0, DEBUG_QDD0, EXAMPLE_OBS, EXAMPLE_Q0, make_problem
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 REL = 1e-9      # reach sets
 CTOL = 1e-8     # constraints, Jacobians
@@ -268,3 +270,101 @@ def test_pinned_user_buffers_give_identical_results(gpu_lib):
     assert b.L.armour_release_host_buffers(b.h) == 0
     b.eval_g_jac(DEBUG_K, g, J)   # re-registers transparently
     assert np.array_equal(a.eval_g(DEBUG_K), g)
+
+
+# ---- guards (round 2) --------------------------------------------------------------------------------------------------
+def _scalar_pz(keys, coeffs):
+    keys = np.array(keys, dtype=np.uint64)
+    return dict(rows=1, cols=1, keys=keys, coeffs=np.array(coeffs, dtype=float).reshape(-1, 1), center=np.array([0.5]), independent=np.array([0.0]))
+
+
+def test_degree_overflow_is_reported(gpu_lib):
+    """The reference adds monomial keys without checking for a carry (KPR/PZsparse.cu:938-940); a degree that outgrows its
+    field would silently corrupt the neighbouring variable.  The device checks every key addition: k_0^2 * k_0^2 (degree 4 in a
+    2-bit field) and qde_0 * qde_0 (degree 2 in a 1-bit field) must fail with ARMOUR_E_NUMERIC; k_0^2 * k_0 and a product that
+    fills every field to its maximum must pass."""
+    p = ab.Planner(T=2)
+    k0sq, k0, qde0 = 2, 1, 1 << 14
+    for ka, kb in ((k0sq, k0sq), (qde0, qde0), (3 << 12, 1 << 12), (1 << 34, 1 << 34), (2 << 61, 2 << 61), (3 << 47, 1 << 47)):
+        with pytest.raises(ab.ArmourError) as e:
+            p.pz_binary("mul", _scalar_pz([ka], [1.0]), _scalar_pz([kb], [1.0]))
+        assert e.value.code == -5, (ka, kb, e.value.code)
+    r = p.pz_binary("mul", _scalar_pz([k0sq], [1.0]), _scalar_pz([k0], [1.0]))
+    assert list(r["keys"]) == [k0, k0sq, 3]
+    full_a = sum(2 << (2 * j) for j in range(7)) | sum(2 << (35 + 2 * j) for j in range(7)) | sum(2 << (49 + 2 * j) for j in range(7))
+    full_b = sum(1 << (2 * j) for j in range(7)) | sum(1 << b for b in range(14, 35)) | sum(1 << (35 + 2 * j) for j in range(7)) | sum(1 << (49 + 2 * j) for j in range(7))
+    r = p.pz_binary("mul", _scalar_pz([full_a], [1.0]), _scalar_pz([full_b], [1.0]))
+    assert int(r["keys"][-1]) == full_a + full_b == (1 << 63) - 1
+    p.close()
+
+
+def test_pz_binary_rejects_unsupported_shapes(gpu_lib):
+    p = ab.Planner(T=2)
+    rng = np.random.default_rng(3)
+    for op, sa, sb in (("mul", (3, 1), (3, 1)), ("mul", (4, 4), (4, 1)), ("add", (3, 3), (3, 3)), ("cross", (1, 1), (3, 1)), ("mul", (1, 1), (3, 1))):
+        with pytest.raises(ab.ArmourError) as e:
+            p.pz_binary(op, random_pz(rng, sa[0], sa[1], 3), random_pz(rng, sb[0], sb[1], 3))
+        assert e.value.code == -1
+    p.close()
+
+
+def test_more_than_64_obstacles_is_rejected_at_create(gpu_lib):
+    with pytest.raises(ab.ArmourError) as e:
+        ab.Planner(T=8, max_obstacles=65)
+    assert e.value.code == -1
+    p = ab.Planner(T=8, max_obstacles=64)      # the limit itself works end to end
+    q0, qd0, qdd0, _, obs = make_problem(77, 64)
+    p.build(q0, qd0, qdd0, obs)
+    o = _oracle.Oracle(T=8)
+    o.build(q0, qd0, qdd0, obs)
+    g, J = p.eval_g_jac(DEBUG_K)
+    assert np.abs(g - o.eval_g(DEBUG_K)).max() <= 1e-8 and np.abs(J - o.eval_jac_g(DEBUG_K)).max() <= 1e-8
+    p.close()
+
+
+def test_k_only_table_capacity_grows_and_retries(gpu_lib):
+    """UCAP / LCAP (k-only monomials kept per torque / link PZ) are runtime capacities: a build that overflows them doubles
+    them and re-runs instead of failing.  Forced here by starting from 2-entry tables in a child process."""
+    import os, subprocess, sys
+    code = ("import sys; sys.path[:0] = [%r, %r]\n"
+            "import numpy as np, armour_b200 as ab\nfrom problems import make_problem, DEBUG_K\n"
+            "q0, qd0, qdd0, _, obs = make_problem(21, 4)\n"
+            "p = ab.Planner(T=16); p.build(q0, qd0, qdd0, obs)\n"
+            "g, J = p.eval_g_jac(DEBUG_K); print('SUM %%.17g %%.17g %%d' %% (g.sum(), np.abs(J).sum(), max(len(p.get_pz('u_nom', j, 8)['keys']) for j in range(7))))\n"
+            % (os.path.join(ROOT, "armour-dev_b200"), os.path.join(ROOT, "tests")))
+    outs = []
+    for env in (dict(os.environ), dict(os.environ, ARMOUR_TUNE_UCAP="2", ARMOUR_TUNE_LCAP="2")):
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-800:]
+        outs.append([l for l in r.stdout.splitlines() if l.startswith("SUM")][0])
+    assert outs[0] == outs[1], outs
+    assert int(outs[0].split()[-1]) > 2
+
+
+def test_pinned_buffers_default_arrays_are_owned_by_the_planner(gpu_lib):
+    """with pin_user_buffers the caller's arrays stay page-locked; temporaries allocated per call would be freed
+    while registered and their addresses reused.  The wrapper now owns persistent buffers for the default-array path: many
+    calls with interleaved allocations keep returning the right numbers."""
+    q0, qd0, qdd0, _, obs = make_problem(43, 9)
+    a = ab.Planner(T=16)
+    b = ab.Planner(T=16, pin_user_buffers=True)
+    a.build(q0, qd0, qdd0, obs)
+    b.build(q0, qd0, qdd0, obs)
+    rng = np.random.default_rng(2)
+    junk = []
+    for it in range(30):
+        x = rng.uniform(-1, 1, 7)
+        ga, Ja = a.eval_g_jac(x)
+        gb, Jb = b.eval_g_jac(x)
+        assert np.array_equal(ga, gb) and np.array_equal(Ja, Jb), it
+        junk.append(np.zeros(rng.integers(1000, 200000)))      # churn the allocator between calls
+        if it % 3 == 0:
+            junk = junk[-2:]
+    # more than 8 distinct caller arrays: entries are evicted, never the one resolved in the same call
+    for it in range(12):
+        g, J = np.zeros(b.m), np.zeros(b.m * 7)
+        b.eval_g_jac(DEBUG_K, g, J)
+        assert np.array_equal(g, a.eval_g(DEBUG_K)) and np.array_equal(J.reshape(-1, 7), a.eval_jac_g(DEBUG_K))
+        assert b.L.armour_release_host_buffers(b.h) == 0 if it % 5 == 4 else True
+        junk.append((g, J))        # keep them alive: the contract for caller-provided arrays
+    a.close(); b.close()
