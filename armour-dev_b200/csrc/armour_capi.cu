@@ -6,9 +6,11 @@
 #include "armour_launch.h"
 #include "../host/standin_solver.hpp"
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdint>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -131,8 +133,15 @@ struct armour_handle {
     volatile unsigned long long* h_done = nullptr; // completion word the kernel's last block writes (pinned, mapped)
     unsigned long long* d_done_flag = nullptr;     // device alias of h_done
     unsigned long long eval_seq = 0;
+    // cuStreamWriteValue64, resolved through the runtime (no link-time dependency on libcuda): writes the completion word
+    // after the constraint kernel in stream order, so the kernel needs no system-wide fences of its own
+    int (*write_value64)(cudaStream_t, unsigned long long, unsigned long long, unsigned) = nullptr;
+    int host_write = 0;                            // how results reach host memory, see launch_eval
+    double eval_host_us = 0.0;                     // wall-clock time spent inside the last evaluation call
+    double *a_g = nullptr, *a_jac = nullptr;       // device aliases of the pinned staging buffers h_g / h_jac
+    int eval_bps_host = 0;                         // resident blocks per SM of the constraint kernel when it writes to host memory (waves overlap compute and PCIe)
     bool eval_timed = false;                       // events of the last evaluation are pending in ev[3], ev[4]
-    bool time_kernels = true;                      // record CUDA events around the per-iteration kernel (armour_set_kernel_timing)
+    bool time_kernels = false;                     // record CUDA events around the per-iteration kernel (armour_set_kernel_timing)
     int ucap = DEFAULT_UCAP, lcap = DEFAULT_LCAP;  // k-only table capacities (grown on overflow)
     // pinned host buffers
     double *h_state = nullptr, *h_obs = nullptr, *h_x = nullptr, *h_g = nullptr, *h_jac = nullptr, *h_torque_radius = nullptr;
@@ -232,41 +241,69 @@ int run_build(armour_handle* h) {   // kernels only; inputs already on the devic
     return fail(ARMOUR_E_CAPACITY, "monomial capacities exceeded after retries");
 }
 
-// One launch per call.  g / jac: where the kernel writes (device buffers, the handle's pinned host buffers, or page-locked
-// caller arrays through their device alias).  host_visible: the results are read by the host right after — the kernel's last
-// block then stores a sequence number into a mapped completion word after a system-wide fence, and the host spins on that
-// word instead of calling cudaStreamSynchronize (saves the driver's wake-up latency on the per-iteration path).
-int launch_eval(armour_handle* h, const double* x, double* g, double* jac, bool host_visible) {
+// One fused eval_g + eval_jac_g launch.
+//   hg / hj == nullptr: device-resident evaluation into d_g / d_jac (bench.py's `value` timing).
+//   otherwise hg / hj are PAGE-LOCKED host destinations (the handle's staging buffers or registered caller arrays) and
+//   ag / aj their device aliases.  How the 1.2 MB of results cross PCIe is h->host_write:
+//     0  the kernel stores g and the Jacobian straight into host memory (zero-copy)                        [default]
+//     1  the kernel writes device buffers, two copy-engine transfers follow in stream order
+//     2  g (8 m bytes) zero-copy from the kernel, the Jacobian (56 m bytes) by one copy-engine transfer
+//   Measured on the B200 box (T = 128, 20 obstacles, in-library wall clock per call, profiles/r2_eval_latency.md):
+//   0: 42.8 us, 1: 54.1 us, 2: 48.7 us — a stand-alone copy-engine transfer of 1.2 MB is ~20 % faster than SM stores
+//   (22 vs 26 us), but each copy adds ~3 us of start-up in stream order and nothing overlaps the kernel.
+//   Completion: a 64-bit sequence number written to a mapped word in stream order (cuStreamWriteValue64; when the driver
+//   entry point is missing, by the kernel's last block after a system-wide fence); the host spins on that word instead of
+//   calling cudaStreamSynchronize, which saves the driver's wake-up latency on the per-iteration path.
+int launch_eval(armour_handle* h, const double* x, double* hg, double* hj, double* ag, double* aj) {
     if (!h->built) return fail(ARMOUR_E_STATE, "eval before build");
+    const auto t_begin = std::chrono::steady_clock::now();
     if (x) memcpy(h->h_x, x, sizeof(double) * NF);
     Tables tb = h->tb;
     tb.P = h->count; tb.n_obs = h->n_obs; tb.mode = h->mode; tb.jrs = h->d_jrs; tb.k_range_in = h->d_krange;
+    const bool host_visible = hg != nullptr;
+    const int mode = host_visible ? h->host_write : -1;
     const bool timed = h->time_kernels || !host_visible;   // events are recorded here, read lazily by armour_last_eval_ms
     if (timed) CU(cudaEventRecord(h->ev[3], h->stream));
     const unsigned long long seq = ++h->eval_seq;
-    CU(launch_constraint_eval(tb, h->sel, h->h_x, g, jac, h->d_link_center, h->d_done, host_visible ? h->d_done_flag : nullptr, seq, h->stream));
-    if (timed) CU(cudaEventRecord(h->ev[4], h->stream));
+    const bool flag_in_kernel = host_visible && !h->write_value64 && mode == 0;
+    double* kg = !host_visible ? h->d_g : (mode == 1 ? h->d_g : ag);
+    double* kj = !host_visible ? h->d_jac : (mode == 0 ? aj : h->d_jac);
+    CU(launch_constraint_eval(tb, h->sel, h->h_x, kg, kj, h->d_link_center, h->d_done, flag_in_kernel ? h->d_done_flag : nullptr, seq, host_visible ? h->eval_bps_host : 0, h->stream));
     h->launches += 1;
     if (host_visible) {
-        // bounded spin (about 50 ms), then fall back to the stream so that a faulted kernel surfaces as an error, not a hang
+        const size_t m = (size_t)m_of(h);
+        if (mode == 1) CU(cudaMemcpyAsync(hg, h->d_g, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+        if (mode >= 1) CU(cudaMemcpyAsync(hj, h->d_jac, sizeof(double) * m * NF, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (timed) CU(cudaEventRecord(h->ev[4], h->stream));
+    if (host_visible) {
+        bool polled = false;
+        if (h->write_value64) {
+            if (h->write_value64(h->stream, (unsigned long long)(uintptr_t)h->d_done_flag, seq, 0) != 0) return fail(ARMOUR_E_CUDA, "cuStreamWriteValue64 failed");
+            polled = true;
+        }
+        else if (flag_in_kernel) polled = true;
         bool done = false;
-        for (long spin = 0; spin < 20000000L; spin++) {
-            if (*h->h_done == seq) { done = true; break; }
+        if (polled) {   // bounded spin (about 50 ms), then fall back to the stream so that a faulted kernel surfaces as an error, not a hang
+            for (long spin = 0; spin < 20000000L; spin++) {
+                if (*h->h_done == seq) { done = true; break; }
 #if defined(__x86_64__)
-            __builtin_ia32_pause();
+                __builtin_ia32_pause();
 #endif
+            }
         }
         if (!done) {
             CU(cudaStreamSynchronize(h->stream));
-            if (*h->h_done != seq) return fail(ARMOUR_E_CUDA, "constraint evaluation did not signal completion");
+            if (polled && *h->h_done != seq) return fail(ARMOUR_E_CUDA, "constraint evaluation did not signal completion");
         }
     }
     else CU(cudaStreamSynchronize(h->stream));
     h->eval_timed = timed;
+    h->eval_host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count();
     return ARMOUR_OK;
 }
 int run_eval(armour_handle* h, const double* x, bool to_host) {
-    int rc = launch_eval(h, x, to_host ? h->h_g : h->d_g, to_host ? h->h_jac : h->d_jac, to_host);
+    int rc = to_host ? launch_eval(h, x, h->h_g, h->h_jac, h->a_g, h->a_jac) : launch_eval(h, x, nullptr, nullptr, nullptr, nullptr);
     if (rc != ARMOUR_OK) return rc;
     if (x && to_host) { memcpy(h->last_x, x, sizeof(double) * NF); h->have_eval = true; }
     return ARMOUR_OK;
@@ -386,6 +423,16 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     if (nt == 32) { h->scap = 512; h->tcap = 128; }
     if (const char* e = getenv("ARMOUR_TUNE_MINB")) h->minb = atoi(e);
     if (const char* e = getenv("ARMOUR_TUNE_MCAP")) h->mcap = std::max(64, atoi(e));
+    if (const char* e = getenv("ARMOUR_TUNE_EVAL_BPS")) h->eval_bps_host = atoi(e);
+    if (const char* e = getenv("ARMOUR_TUNE_HOST_WRITE")) h->host_write = std::min(2, std::max(0, atoi(e)));
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        const char* off = getenv("ARMOUR_TUNE_FLAG_IN_KERNEL");
+        if (!(off && atoi(off)) && cudaGetDriverEntryPoint("cuStreamWriteValue64", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess && fn)
+            h->write_value64 = (int (*)(cudaStream_t, unsigned long long, unsigned long long, unsigned))fn;
+        cudaGetLastError();
+    }
     if (const char* e = getenv("ARMOUR_TUNE_UCAP")) h->ucap = std::max(1, atoi(e));   // tests force the grow-and-retry path with tiny tables
     if (const char* e = getenv("ARMOUR_TUNE_LCAP")) h->lcap = std::max(1, atoi(e));
     if (const char* e = getenv("ARMOUR_TUNE_NCAP")) h->ncap = std::min(std::max(256, atoi(e)), 65534) & ~1;
@@ -425,6 +472,7 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     CU(cudaMallocHost((void**)&h->h_x, sizeof(double) * NF)); CU(cudaMallocHost((void**)&h->h_g, sizeof(double) * mmax));
     CU(cudaMallocHost((void**)&h->h_jac, sizeof(double) * mmax * NF)); CU(cudaMallocHost((void**)&h->h_torque_radius, sizeof(double) * P * T * NF));
     CU(cudaMallocHost((void**)&h->h_err, sizeof(int)));
+    CU(cudaHostGetDevicePointer((void**)&h->a_g, h->h_g, 0)); CU(cudaHostGetDevicePointer((void**)&h->a_jac, h->h_jac, 0));
     CU(dalloc(&h->d_done, 1)); CU(cudaMemset(h->d_done, 0, sizeof(unsigned)));
     CU(cudaHostAlloc((void**)&h->h_done, sizeof(unsigned long long), cudaHostAllocMapped));
     *h->h_done = 0;
@@ -568,7 +616,7 @@ int armour_eval_g_jac(armour_handle* h, const double* x, double* g, double* valu
         double* dg = (double*)pinned_alias(h, g, sizeof(double) * m);
         double* dj = dg ? (double*)pinned_alias(h, values, sizeof(double) * (size_t)m * NF, dg) : nullptr;
         if (dg && dj) {
-            int rc = launch_eval(h, x, dg, dj, true);
+            int rc = launch_eval(h, x, g, values, dg, dj);
             if (rc != ARMOUR_OK) return rc;
             h->have_eval = false;
             return ARMOUR_OK;
@@ -820,6 +868,11 @@ int armour_last_eval_ms(armour_handle* h, float* kernel_ms) {
         h->eval_timed = false;
     }
     *kernel_ms = h->eval_ms;
+    return ARMOUR_OK;
+}
+int armour_last_eval_host_us(armour_handle* h, double* microseconds) {
+    if (!h || !microseconds) return fail(ARMOUR_E_INVALID, "null argument");
+    *microseconds = h->eval_host_us;
     return ARMOUR_OK;
 }
 int armour_set_kernel_timing(armour_handle* h, int enabled) {

@@ -6,6 +6,7 @@
 //                           link PZs at k, checkCollisionKernel (KPR/CollisionChecking.cu:230-299) for all
 //                           seven links, and the joint position / velocity limit rows
 //                           (KPR/Trajectory.cu:256-540), one launch per Ipopt iteration.
+#include <algorithm>
 #include "armour_types.cuh"
 
 namespace armour {
@@ -20,54 +21,46 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __constant__ unsigned char c_pair_a[COMB] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 6, 6, 7};
 __constant__ unsigned char c_pair_b[COMB] = {1, 2, 3, 4, 5, 6, 7, 8, 2, 3, 4, 5, 6, 7, 8, 3, 4, 5, 6, 7, 8, 4, 5, 6, 7, 8, 5, 6, 7, 8, 6, 7, 8, 7, 8, 8};
 
-// One block per (problem, t, link): the link's 3x6 generator block is staged once in shared memory, every thread owns one
-// (obstacle, pair) plane at a time.  All index arithmetic is 32-bit (the round-1 kernel decomposed a 64-bit flat index with
-// five 64-bit divisions per thread); results of a block are one contiguous run of A, d and delta.
-constexpr int HYPER_NT = 288;   // 8 obstacles x 36 pairs per pass
+// One block per (problem, t, link, group of 8 obstacles), one thread per (obstacle, pair) plane: no loops, no 64-bit index
+// arithmetic (the round-1 kernel decomposed a flat 64-bit index with five 64-bit divisions per thread).  The nine buffered
+// generators of each obstacle of the group — its own three and the link's 3x6 block (bufferObstaclesKernel) — are staged in
+// shared memory and read from there (broadcast loads), which keeps the kernel at 40 registers.
+constexpr int HYPER_OBS = 8;
+constexpr int HYPER_NT = HYPER_OBS * COMB;   // 288
 __global__ void __launch_bounds__(HYPER_NT) hyperplane_kernel(Tables tb) {
-    __shared__ double lg[18];
+    __shared__ double G[HYPER_OBS][9][3];
+    __shared__ double cen[HYPER_OBS][3];
     const int n_obs = tb.n_obs;
     const size_t rec = blockIdx.x;                      // (prob * T + t) * NJ + link
     const int prob = (int)(rec / ((size_t)tb.T * NJ));
-    if (threadIdx.x < 18) lg[threadIdx.x] = tb.gens[rec * 18 + threadIdx.x];
-    __syncthreads();
-    const int p = threadIdx.x % COMB, o0 = threadIdx.x / COMB;
-    const int ia = c_pair_a[p], ib = c_pair_b[p];
-    for (int o = o0; o < n_obs; o += HYPER_NT / COMB) {
-        const double* ob = tb.obstacles + ((size_t)prob * n_obs + o) * 12;
-        // buffered generators: 3 obstacle generators then the link's 3x6 block (bufferObstaclesKernel)
-        double G[9][3];
-#pragma unroll
-        for (int g = 0; g < 3; g++)
-#pragma unroll
-            for (int a = 0; a < 3; a++) G[g][a] = ob[(g + 1) * 3 + a];
-#pragma unroll
-        for (int g = 0; g < 6; g++)
-#pragma unroll
-            for (int a = 0; a < 3; a++) G[3 + g][a] = lg[g * 3 + a];
-        double ga[3], gb[3];
-#pragma unroll
-        for (int a = 0; a < 3; a++) { ga[a] = 0; gb[a] = 0; }
-#pragma unroll
-        for (int g = 0; g < 9; g++) {   // register-resident selection (no dynamically indexed local array)
-            if (g == ia) { ga[0] = G[g][0]; ga[1] = G[g][1]; ga[2] = G[g][2]; }
-            if (g == ib) { gb[0] = G[g][0]; gb[1] = G[g][1]; gb[2] = G[g][2]; }
-        }
-        double cr[3];
-        cr[0] = dadd(dmul(ga[1], gb[2]), -dmul(ga[2], gb[1]));
-        cr[1] = dadd(dmul(ga[2], gb[0]), -dmul(ga[0], gb[2]));
-        cr[2] = dadd(dmul(ga[0], gb[1]), -dmul(ga[1], gb[0]));
-        const double nrm = __dsqrt_rn(dadd(dadd(dmul(cr[0], cr[0]), dmul(cr[1], cr[1])), dmul(cr[2], cr[2])));
-        double C[3] = {0, 0, 0};
-        if (nrm > 0) { C[0] = __ddiv_rn(cr[0], nrm); C[1] = __ddiv_rn(cr[1], nrm); C[2] = __ddiv_rn(cr[2], nrm); }
-        const size_t idx = (rec * n_obs + o) * COMB + p;
-        tb.A[idx * 3 + 0] = C[0]; tb.A[idx * 3 + 1] = C[1]; tb.A[idx * 3 + 2] = C[2];
-        tb.d[idx] = dadd(dadd(dmul(C[0], ob[0]), dmul(C[1], ob[1])), dmul(C[2], ob[2]));
-        double dl = 0.0;
-#pragma unroll
-        for (int j = 0; j < 9; j++) dl = dadd(dl, fabs(dadd(dadd(dmul(C[0], G[j][0]), dmul(C[1], G[j][1])), dmul(C[2], G[j][2]))));
-        tb.delta[idx] = dl;
+    const int o_base = blockIdx.y * HYPER_OBS;
+    const int n_here = min(HYPER_OBS, n_obs - o_base);
+    for (int e = threadIdx.x; e < n_here * 30; e += HYPER_NT) {
+        const int ol = e / 30, r = e - ol * 30;
+        const double* ob = tb.obstacles + ((size_t)prob * n_obs + o_base + ol) * 12;
+        if (r < 3) cen[ol][r] = ob[r];
+        else if (r < 12) G[ol][(r - 3) / 3][(r - 3) % 3] = ob[r];
+        else G[ol][3 + (r - 12) / 3][(r - 12) % 3] = tb.gens[rec * 18 + (r - 12)];
     }
+    __syncthreads();
+    const int p = threadIdx.x % COMB, ol = threadIdx.x / COMB;
+    if (ol >= n_here) return;
+    const int ia = c_pair_a[p], ib = c_pair_b[p];
+    const double ga0 = G[ol][ia][0], ga1 = G[ol][ia][1], ga2 = G[ol][ia][2];
+    const double gb0 = G[ol][ib][0], gb1 = G[ol][ib][1], gb2 = G[ol][ib][2];
+    const double cr0 = dadd(dmul(ga1, gb2), -dmul(ga2, gb1));
+    const double cr1 = dadd(dmul(ga2, gb0), -dmul(ga0, gb2));
+    const double cr2 = dadd(dmul(ga0, gb1), -dmul(ga1, gb0));
+    const double nrm = __dsqrt_rn(dadd(dadd(dmul(cr0, cr0), dmul(cr1, cr1)), dmul(cr2, cr2)));
+    double C0 = 0, C1 = 0, C2 = 0;
+    if (nrm > 0) { C0 = __ddiv_rn(cr0, nrm); C1 = __ddiv_rn(cr1, nrm); C2 = __ddiv_rn(cr2, nrm); }
+    const size_t idx = (rec * n_obs + o_base + ol) * COMB + p;
+    tb.A[idx * 3 + 0] = C0; tb.A[idx * 3 + 1] = C1; tb.A[idx * 3 + 2] = C2;
+    tb.d[idx] = dadd(dadd(dmul(C0, cen[ol][0]), dmul(C1, cen[ol][1])), dmul(C2, cen[ol][2]));
+    double dl = 0.0;
+#pragma unroll
+    for (int j = 0; j < 9; j++) dl = dadd(dl, fabs(dadd(dadd(dmul(C0, G[ol][j][0]), dmul(C1, G[ol][j][1])), dmul(C2, G[ol][j][2]))));
+    tb.delta[idx] = dl;
 }
 
 // ---- Bezier curve pieces used by the limit rows (KPR/Trajectory.cu:542-599) -----------------------
@@ -375,7 +368,9 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
                     for (int i = 0; i < 9; i++) {
                         const double a0 = sA[(p0 + i) * 3], a1 = sA[(p0 + i) * 3 + 1], a2 = sA[(p0 + i) * 3 + 2];
                         double pos = -100000000.0, neg = -100000000.0;
-                        if (dadd(dadd(dmul(a0, a0), dmul(a1, a1)), dmul(a2, a2)) > 0) {   // A.norm() > 0  <=>  squared norm > 0
+                        // A.norm() > 0 (KPR/CollisionChecking.cu:252): the rows of this table are unit vectors or exactly zero
+                        // (hyperplane_kernel), for which "norm > 0" is "some component is not +-0" — three bit tests, no arithmetic
+                        if (((__double_as_longlong(a0) | __double_as_longlong(a1) | __double_as_longlong(a2)) << 1) != 0) {
                             const double dot = dadd(dadd(dmul(a0, c0), dmul(a1, c1)), dmul(a2, c2));
                             const double dd = sd[p0 + i], dl = sdl[p0 + i];
                             pos = dadd(dot, -dadd(dd, dl));
@@ -427,21 +422,31 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
 }
 
 cudaError_t launch_hyperplanes(const Tables& tb, cudaStream_t stream) {
-    const size_t blocks = (size_t)tb.P * tb.T * NJ;
-    if (blocks == 0 || tb.n_obs == 0) return cudaSuccess;
-    hyperplane_kernel<<<(unsigned)blocks, HYPER_NT, 0, stream>>>(tb);
+    const size_t recs = (size_t)tb.P * tb.T * NJ;
+    if (recs == 0 || tb.n_obs == 0) return cudaSuccess;
+    hyperplane_kernel<<<dim3((unsigned)recs, (tb.n_obs + HYPER_OBS - 1) / HYPER_OBS), HYPER_NT, 0, stream>>>(tb);
     return cudaGetLastError();
 }
 int eval_max_obstacles() { return EVAL_MAX_OBS; }
+// blocks_per_sm > 0 caps the resident blocks per SM by padding the dynamic shared-memory request.  With every block resident
+// at once (the default, best for device-resident results) all blocks finish together; when the results go to host memory
+// over PCIe it pays to run the grid in a few waves, so that the first rows are on the wire while later blocks still compute.
 cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* x_host, double* g, double* jac, double* link_center, unsigned* done_counter,
-                                   unsigned long long* done_flag, unsigned long long seq, cudaStream_t stream) {
+                                   unsigned long long* done_flag, unsigned long long seq, int blocks_per_sm, cudaStream_t stream) {
     if (tb.n_obs > EVAL_MAX_OBS) return cudaErrorInvalidValue;
     XArg xa;
     for (int i = 0; i < NF; i++) xa.x[i] = x_host[i];
-    const size_t smem = eval_smem_bytes(tb.n_obs);
-    if (smem > 48 * 1024) {   // more than 32 obstacles: opt in to a large dynamic shared-memory slab (off the benchmark path)
-        cudaError_t e = cudaFuncSetAttribute(constraint_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes(EVAL_MAX_OBS));
-        if (e != cudaSuccess) return e;
+    size_t smem = eval_smem_bytes(tb.n_obs);
+    if (blocks_per_sm > 0) smem = std::max(smem, std::min((size_t)(227 * 1024) / blocks_per_sm - 1280, eval_smem_bytes(EVAL_MAX_OBS)));
+    if (smem > 48 * 1024) {   // opt in to a large dynamic shared-memory request, once per device
+        static bool opted_in[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !opted_in[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(constraint_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes(EVAL_MAX_OBS));
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) opted_in[dev] = true;
+        }
     }
     constraint_eval_kernel<<<tb.T * NJ + 1, EVAL_NT, smem, stream>>>(tb, prob, xa, g, jac, link_center, done_counter, done_flag, seq);
     return cudaGetLastError();

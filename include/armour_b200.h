@@ -159,9 +159,12 @@ int armour_standin_solve(armour_handle* h, const double* q_des, double t_plan, d
 /* device time of the last build / eval in milliseconds (CUDA events on the handle's stream) */
 int armour_last_build_ms(armour_handle* h, float* total_ms, float* reach_kernel_ms, float* hyperplane_kernel_ms);
 int armour_last_eval_ms(armour_handle* h, float* kernel_ms);
-/* The per-iteration path records two CUDA events per call for armour_last_eval_ms (about 2 us of host time); 0 switches them
- * off for host-buffer evaluations (armour_last_eval_ms then reports -1), 1 (default) back on. */
+/* Host-buffer evaluations (armour_eval_g / _jac_g / _g_jac) record CUDA events for armour_last_eval_ms only when asked to:
+ * two event records cost about 4 us per call on the per-iteration path.  enabled = 1 turns them on, 0 (default) off
+ * (armour_last_eval_ms then reports -1 after a host-buffer evaluation; armour_eval_resident is always timed). */
 int armour_set_kernel_timing(armour_handle* h, int enabled);
+/* wall-clock microseconds spent inside the last evaluation call (launch, PCIe transfer, completion wait) */
+int armour_last_eval_host_us(armour_handle* h, double* microseconds);
 /* kernels launched by this handle since creation */
 int armour_kernel_launches(armour_handle* h, uint64_t* launches);
 /* build with inputs already resident on the device (armour_build without the host<->device copies);

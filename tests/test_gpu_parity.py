@@ -206,12 +206,17 @@ def test_build_is_deterministic(gpu_lib):
 
 
 # ---- primitive-level parity: PZsparse arithmetic on random operands -------------------------------------------
-def random_pz(rng, rows, cols, n, nvars=6):
+def random_pz(rng, rows, cols, n, nvars=6, one_bit=range(7, 28)):
+    """Random monomials of degree 1 in up to nvars - 1 of the 42 variables.  one_bit: which of the 21 one-bit error symbols
+    (variable indices 7..27) may appear — the two operands of a product draw them from disjoint halves, because a product that
+    squares a one-bit symbol overflows its key field (the reference would silently carry into the neighbouring variable; the
+    device reports ARMOUR_E_NUMERIC, see test_degree_overflow_is_reported)."""
     dim = rows * cols
     keys = set()
+    allowed = np.array([v for v in range(42) if v < 7 or v >= 28 or v in one_bit])
     while len(keys) < n:
         k = 0
-        for v in rng.choice(42, size=rng.integers(1, nvars), replace=False):
+        for v in rng.choice(allowed, size=rng.integers(1, nvars), replace=False):
             shift = 2 * v if v < 7 else (14 + (v - 7)) if v < 28 else 35 + 2 * (v - 28)
             k |= 1 << int(shift)
         keys.add(k)
@@ -232,8 +237,9 @@ def test_pz_primitives(op, shape_a, shape_b, na, nb, gpu_lib):
     rng = np.random.default_rng(zlib.crc32(repr((op, shape_a, shape_b, na, nb)).encode()))
     p = ab.Planner(T=2)
     for trial in range(3):
-        a = random_pz(rng, shape_a[0], shape_a[1], na)
-        b = random_pz(rng, shape_b[0], shape_b[1], nb)
+        prod = op in ("mul", "cross")
+        a = random_pz(rng, shape_a[0], shape_a[1], na, one_bit=range(7, 17) if prod else range(7, 28))
+        b = random_pz(rng, shape_b[0], shape_b[1], nb, one_bit=range(17, 28) if prod else range(7, 28))
         if op in ("add", "sub") and trial == 1 and na and nb:   # force shared keys so that merging and cancellation happen
             m = min(na, nb) // 2
             b["keys"][:m] = a["keys"][:m]
