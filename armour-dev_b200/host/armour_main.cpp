@@ -12,6 +12,8 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <memory>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -58,36 +60,66 @@ int main(int argc, char** argv) {
     const long duration1 = std::chrono::duration_cast<std::chrono::milliseconds>(stop1 - start1).count();
     std::cout << "        CUDA & C++: Time taken by generating reachable sets: " << duration1 << " milliseconds" << std::endl;
 
+    // KPR/armour_main.cu:228-230: the deadline formula is commented out in the reference; 10 s is what it passes to Ipopt
+    double time_for_optimization = 10;
+    time_for_optimization = std::max(time_for_optimization, 0.0);
+    std::cout << "        CUDA & C++: Time allocated for Ipopt: " << time_for_optimization * 1000.0 << " milliseconds" << std::endl;
+
     auto start2 = std::chrono::high_resolution_clock::now();
-    armtd_NLP nlp;
-    nlp.verbose = true;
-    nlp.set_time_steps(NUM_TIME_STEPS);
-    if (!nlp.set_parameters(q_des, t_plan, h)) { printf("        CUDA & C++: Error initializing the NLP!\n"); out1 << -1 << '\n'; out1.close(); armour_destroy(h); return 1; }
-    double k_opt[7] = {0};
+    // The NLP lives on the heap, like the reference's (`SmartPtr<armtd_NLP> mynlp = new armtd_NLP()`, KPR/armour_main.cu:238):
+    // Ipopt's SmartPtr deletes the object when the last reference goes away, so it must never point at a stack object.
+#ifdef ARMOUR_HAVE_IPOPT
+    Ipopt::SmartPtr<armtd_NLP> mynlp = new armtd_NLP();
+#else
+    std::unique_ptr<armtd_NLP> mynlp(new armtd_NLP());
+#endif
+    mynlp->verbose = true;
+    mynlp->set_time_steps(NUM_TIME_STEPS);
+    if (!mynlp->set_parameters(q_des, t_plan, h)) {
+        printf("        CUDA & C++: Error initializing Ipopt! Check previous error message!\n");
+        out1 << -1 << '\n'; out1.close(); armour_destroy(h); return 1;
+    }
+    bool report_solve_time = true;
 #ifdef ARMOUR_HAVE_IPOPT
     {
-        Ipopt::SmartPtr<armtd_NLP> mynlp = &nlp;   // options as KPR/armour_main.cu:256-261
-        Ipopt::SmartPtr<Ipopt::IpoptApplication> app = IpoptApplicationFactory();
+        Ipopt::SmartPtr<Ipopt::IpoptApplication> app = Ipopt::IpoptApplicationFactory();   // options: KPR/armour_main.cu:256-261
         app->Options()->SetNumericValue("tol", 1e-4);
-        app->Options()->SetNumericValue("max_wall_time", 10.0);
+        app->Options()->SetNumericValue("max_wall_time", time_for_optimization);
         app->Options()->SetIntegerValue("print_level", 0);
         app->Options()->SetStringValue("mu_strategy", "adaptive");
         app->Options()->SetStringValue("linear_solver", "ma97");
         app->Options()->SetStringValue("hessian_approximation", "limited-memory");
-        if (app->Initialize() != Ipopt::Solve_Succeeded) { printf("Error during initialization!"); out1 << -1 << '\n'; out1.close(); return 1; }
-        app->OptimizeTNLP(mynlp);
+        Ipopt::ApplicationReturnStatus status = app->Initialize();
+        if (status != Ipopt::Solve_Succeeded) {   // :276-281 (the reference then rethrows and aborts; here: a clean non-zero exit)
+            printf("Error during initialization!\n");
+            out1 << -1 << '\n'; out1.close(); armour_destroy(h); return 1;
+        }
+        status = app->OptimizeTNLP(mynlp);
+        // :295-317
+        if (status == Ipopt::Invalid_Option) {
+            std::cout << "        CUDA & C++: Cannot find HSL library! Need to put libcoinhsl.so in proper path!\n";
+            report_solve_time = false;
+        }
+        else if (status == Ipopt::Maximum_CpuTime_Exceeded) {
+            std::cout << "        CUDA & C++: Ipopt maximum CPU time exceeded!\n";
+            std::cout << (mynlp->feasible ? "        CUDA & C++: Found a feasible solution!\n" : "        CUDA & C++: Did not find a feasible solution!\n");
+        }
+        else std::cout << (mynlp->feasible ? "        CUDA & C++: Found an optimal solution!\n" : "        CUDA & C++: Problem infeasible!\n");
     }
 #else
     {
-        StandinResult r = standin_solve(nlp, k_opt);
+        double k_opt[7] = {0};
+        StandinResult r = standin_solve(*mynlp, k_opt);
         std::cout << "        CUDA & C++: stand-in solver (Ipopt not available at build time): " << r.iterations << " iterations, " << r.evaluations
                   << " constraint evaluations, max violation " << r.max_violation << std::endl;
+        std::cout << (mynlp->feasible ? "        CUDA & C++: Found an optimal solution!\n" : "        CUDA & C++: Problem infeasible!\n");
     }
 #endif
     auto stop2 = std::chrono::high_resolution_clock::now();
     const long duration2 = std::chrono::duration_cast<std::chrono::milliseconds>(stop2 - start2).count();
-    std::cout << (nlp.feasible ? "        CUDA & C++: Found an optimal solution!\n" : "        CUDA & C++: Problem infeasible!\n");
-    std::cout << "        CUDA & C++: Time taken by Ipopt: " << duration2 << " milliseconds" << std::endl;
+    if (report_solve_time) std::cout << "        CUDA & C++: Time taken by Ipopt: " << duration2 << " milliseconds" << std::endl;
+    armtd_NLP& nlp = *mynlp;
+    if (nlp.link_sliced_center.empty()) nlp.link_sliced_center.assign((size_t)NUM_TIME_STEPS * 7 * 3, 0.0);   // no solve happened (Invalid_Option)
 
     out1 << std::setprecision(10);
     if (nlp.feasible) for (int i = 0; i < 7; i++) out1 << nlp.solution[i] << '\n';

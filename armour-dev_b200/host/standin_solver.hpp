@@ -11,8 +11,10 @@
 
 struct StandinResult { int iterations = 0; int evaluations = 0; bool converged = false; double objective = 0; double max_violation = 0; };
 
-inline StandinResult standin_solve(armtd_NLP& nlp, double* x_out, int max_iter = 60) {
-    typedef armtd_NLP::Index Index;
+// NLP: anything with the Ipopt::TNLP callbacks (armtd_NLP directly, or an Ipopt::TNLP& through its virtual interface)
+template <class NLP>
+inline StandinResult standin_solve(NLP& nlp, double* x_out, int max_iter = 60) {
+    typedef Ipopt::Index Index;
     Index n, m, nnz, nh;
     Ipopt::TNLP::IndexStyleEnum st;
     nlp.get_nlp_info(n, m, nnz, nh, st);

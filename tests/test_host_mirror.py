@@ -43,42 +43,95 @@ def test_cpp_adapter_and_facade_match_ctypes_path(gpu_lib):
     assert int(val["iters"]) >= 1
 
 
-def test_armour_main_cli_file_protocol(gpu_lib):
-    """Text protocol of KPR/armour_main.cu:47-79 (input) and :324-397 (five output files)."""
-    exe = os.path.join(PKG, "armour_main")
-    assert os.path.exists(exe)
+def _write_armour_in(d, q0, qd0, qdd0, q_des, obs):
+    """written like uarmtd_planner.m:169-196 (%.10f)"""
+    obs = np.asarray(obs).reshape(-1, 12)
+    with open(os.path.join(d, "armour.in"), "w") as f:
+        for vec in (q0, qd0, qdd0, q_des):
+            f.write(" ".join("%.10f" % v for v in vec) + "\n")
+        f.write("%d\n" % len(obs))
+        for row in obs:
+            f.write(" ".join("%.10f" % v for v in row) + "\n")
+
+
+@pytest.mark.parametrize("binary", ["armour_main", "armour_main_ipopt_stub"])
+def test_armour_main_cli_file_protocol(binary, gpu_lib):
+    """Text protocol of KPR/armour_main.cu:47-79 (input) and :324-397 (five output files): EVERY value of every file is
+    compared with the in-memory path at the file's precision (10 significant digits; 6 for the constraint file), including
+    the 28 bound rows appended to the constraint file (:381-394).  Both builds of the CLI are exercised: the stand-in solver
+    branch and the ARMOUR_HAVE_IPOPT branch (SmartPtr ownership, options, return statuses) against the in-test Ipopt
+    stand-in of tests/ipopt_stub — the same Gauss-Newton iteration sits behind both, so k must agree too."""
+    exe = os.path.join(PKG, binary)
+    assert os.path.exists(exe), "run __graft_entry__.build()"
     T, n_obs = 128, 10
+    q0 = np.array([float("%.10f" % v) for v in EXAMPLE_Q0])      # what the executable reads back from the text file
+    q_des = np.array([float("%.10f" % v) for v in EXAMPLE_QDES])
+    obs = np.array([float("%.10f" % v) for v in EXAMPLE_OBS])
     with tempfile.TemporaryDirectory() as d:
-        with open(os.path.join(d, "armour.in"), "w") as f:   # written like uarmtd_planner.m:169-196 (%.10f)
-            for vec in (EXAMPLE_Q0, np.zeros(7), np.zeros(7), EXAMPLE_QDES):
-                f.write(" ".join("%.10f" % v for v in vec) + "\n")
-            f.write("%d\n" % n_obs)
-            for row in EXAMPLE_OBS.reshape(n_obs, 12):
-                f.write(" ".join("%.10f" % v for v in row) + "\n")
+        _write_armour_in(d, q0, np.zeros(7), np.zeros(7), q_des, obs)
         out = subprocess.run([exe, d], capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stdout + out.stderr
-        assert "Time taken by generating reachable sets" in out.stdout and "Time taken by Ipopt" in out.stdout
+        for line in ("Time taken by generating reachable sets", "Time allocated for Ipopt: 10000 milliseconds", "Time taken by Ipopt"):
+            assert line in out.stdout, out.stdout
+        assert ("Found an optimal solution!" in out.stdout) != ("Problem infeasible!" in out.stdout)
         m = 7 * T + 7 * T * n_obs + 28
+        # the in-memory path: same build, same solver
+        p = ab.Planner(T=T)
+        p.build(q0, np.zeros(7), np.zeros(7), obs)
+        k, feasible, _, _ = p.standin_solve(q_des, 0.5)
+        g = p.eval_g(k)
         main = open(os.path.join(d, "armour.out")).read().split()
-        assert len(main) in (2, 8)            # -1 or 7 k values, then the total milliseconds
-        if len(main) == 8:
-            assert all(-1.0 <= float(v) <= 1.0 for v in main[:7])
+        if feasible:
+            assert len(main) == 8 and "Found an optimal solution!" in out.stdout
+            assert np.allclose([float(v) for v in main[:7]], k, rtol=1e-9, atol=1e-12)
         else:
-            assert main[0] == "-1"
+            assert len(main) == 2 and main[0] == "-1" and "Problem infeasible!" in out.stdout
+        assert float(main[-1]) >= 0 and float(main[-1]) == int(float(main[-1]))     # total milliseconds
+        centers = np.loadtxt(os.path.join(d, "armour_joint_position_center.out"))
+        assert centers.shape == (T * 7, 3)
+        assert np.allclose(centers, p.link_sliced_center().reshape(T * 7, 3), rtol=1e-9, atol=1e-12)
+        gens = np.loadtxt(os.path.join(d, "armour_joint_position_radius.out"))
+        assert gens.shape == (T * 7 * 3, 6)
+        assert np.allclose(gens, p.link_generators().reshape(T * 7 * 3, 6), rtol=1e-9, atol=1e-15)
+        radius = np.loadtxt(os.path.join(d, "armour_control_input_radius.out"))
+        assert radius.shape == (T, 7) and np.allclose(radius, p.torque_radius(), rtol=1e-9)
         cons = np.loadtxt(os.path.join(d, "armour_constraints.out"))
         assert cons.shape == (m + 28,)
-        assert np.loadtxt(os.path.join(d, "armour_joint_position_center.out")).shape == (T * 7, 3)
-        assert np.loadtxt(os.path.join(d, "armour_joint_position_radius.out")).shape == (T * 7 * 3, 6)
-        radius = np.loadtxt(os.path.join(d, "armour_control_input_radius.out"))
-        assert radius.shape == (T, 7)
-        # the file boundary keeps 10 significant digits: compare with the in-memory path at that precision
-        p = ab.Planner(T=T)
-        p.build(EXAMPLE_Q0, np.zeros(7), np.zeros(7), EXAMPLE_OBS)
-        assert np.allclose(radius, p.torque_radius(), rtol=1e-9)
+        assert np.allclose(cons[:m], g, rtol=1e-5, atol=1e-12)
+        _, _, gl, gu = p.get_bounds_info()
+        pos = np.stack([gl[m - 28:m - 21], gu[m - 28:m - 21]], axis=1).ravel()      # lb, ub interleaved per joint (:382-386)
+        vel = np.stack([gl[m - 14:m - 7], gu[m - 14:m - 7]], axis=1).ravel()        # (:389-393)
+        assert np.allclose(cons[m:m + 14], pos, rtol=1e-5) and np.allclose(cons[m + 14:], vel, rtol=1e-5)
         # missing input file: -1 in armour.out and a non-zero exit code
         with tempfile.TemporaryDirectory() as d2:
             bad = subprocess.run([exe, d2], capture_output=True, text=True, timeout=60)
             assert bad.returncode != 0 and open(os.path.join(d2, "armour.out")).read().strip() == "-1"
+        # too many obstacles (KPR/armour_main.cu:66-72)
+        with tempfile.TemporaryDirectory() as d3:
+            _write_armour_in(d3, q0, np.zeros(7), np.zeros(7), q_des, np.zeros(41 * 12))
+            bad = subprocess.run([exe, d3], capture_output=True, text=True, timeout=60)
+            assert bad.returncode != 0 and open(os.path.join(d3, "armour.out")).read().strip() == "-1"
+
+
+def test_armour_main_ipopt_return_statuses(gpu_lib):
+    """KPR/armour_main.cu:276-281, 295-317: initialisation failure, missing HSL library (Invalid_Option) and a CPU-time-out
+    with a usable iterate, simulated by the in-test Ipopt stand-in (IPOPT_STUB_STATUS)."""
+    exe = os.path.join(PKG, "armour_main_ipopt_stub")
+    assert os.path.exists(exe)
+    with tempfile.TemporaryDirectory() as d:
+        _write_armour_in(d, EXAMPLE_Q0, np.zeros(7), np.zeros(7), EXAMPLE_QDES, EXAMPLE_OBS[:36])
+        run = lambda status: subprocess.run([exe, d], capture_output=True, text=True, timeout=300, env=dict(os.environ, IPOPT_STUB_STATUS=status, ARMOUR_NUM_TIME_STEPS="16"))
+        r = run("Maximum_CpuTime_Exceeded")
+        assert r.returncode == 0 and "Ipopt maximum CPU time exceeded!" in r.stdout and "Time taken by Ipopt" in r.stdout
+        assert ("Found a feasible solution!" in r.stdout) != ("Did not find a feasible solution!" in r.stdout)
+        main = open(os.path.join(d, "armour.out")).read().split()
+        assert len(main) == (8 if "Found a feasible solution!" in r.stdout else 2)
+        r = run("Invalid_Option")
+        assert r.returncode == 0 and "Cannot find HSL library!" in r.stdout and "Time taken by Ipopt" not in r.stdout
+        assert open(os.path.join(d, "armour.out")).read().split()[0] == "-1"
+        r = run("Initialize_Failure")
+        assert r.returncode != 0 and "Error during initialization!" in r.stdout
+        assert open(os.path.join(d, "armour.out")).read().strip() == "-1"
 
 
 def test_same_solver_same_k(gpu_lib):
