@@ -26,7 +26,7 @@ EXPORTS = [
     "armour_eval_grad_f", "armour_eval_g", "armour_eval_jac_g", "armour_eval_g_jac", "armour_jac_structure", "armour_release_host_buffers", "armour_check_feasible",
     "armour_get_torque_radius", "armour_get_link_generators", "armour_get_link_sliced_center", "armour_get_hyperplanes",
     "armour_get_taylor_remainders", "armour_get_pz", "armour_pz_binary", "armour_last_build_ms", "armour_last_eval_ms",
-    "armour_kernel_launches", "armour_set_kernel_timing", "armour_last_eval_host_us", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_upload_x", "armour_standin_solve", "armour_debug_phase_cycles", "armour_measure_fp64_peak",
+    "armour_kernel_launches", "armour_set_kernel_timing", "armour_last_eval_host_us", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_eval_resident_burst", "armour_upload_x", "armour_standin_solve", "armour_debug_phase_cycles", "armour_measure_fp64_peak",
 ]
 
 
@@ -289,6 +289,12 @@ class Planner:
         values = np.zeros(m * 7) if values is None else values
         self._ck(self.L.armour_eval_g_jac(self.h, _dp(_vec(x, 7)), _dp(g), _dp(values)))
         return g, values.reshape(m, 7)
+
+    def eval_resident_burst(self, x, launches=20):
+        """average device time (ms) of `launches` back-to-back device-resident evaluations"""
+        v = C.c_float()
+        self._ck(self.L.armour_eval_resident_burst(self.h, _dp(_vec(x, 7)), C.c_int(launches), C.byref(v)))
+        return v.value
 
     def last_eval_host_us(self):
         v = C.c_double()

@@ -149,6 +149,7 @@ struct armour_handle {
     // state
     int count = 0, n_obs = 0, sel = 0;
     bool built = false, have_eval = false;
+    int staged = 0;   // which results of the evaluation at last_x sit in the pinned staging buffers: bit 0 g, bit 1 Jacobian
     double last_x[NF];
     float build_ms = 0, reach_ms = 0, hyper_ms = 0, eval_ms = 0;
     uint64_t launches = 0;
@@ -254,13 +255,13 @@ int run_build(armour_handle* h) {   // kernels only; inputs already on the devic
 //   Completion: a 64-bit sequence number written to a mapped word in stream order (cuStreamWriteValue64; when the driver
 //   entry point is missing, by the kernel's last block after a system-wide fence); the host spins on that word instead of
 //   calling cudaStreamSynchronize, which saves the driver's wake-up latency on the per-iteration path.
-int launch_eval(armour_handle* h, const double* x, double* hg, double* hj, double* ag, double* aj) {
+int launch_eval(armour_handle* h, const double* x, double* hg, double* hj, double* ag, double* aj, int what = 3) {
     if (!h->built) return fail(ARMOUR_E_STATE, "eval before build");
     const auto t_begin = std::chrono::steady_clock::now();
     if (x) memcpy(h->h_x, x, sizeof(double) * NF);
     Tables tb = h->tb;
     tb.P = h->count; tb.n_obs = h->n_obs; tb.mode = h->mode; tb.jrs = h->d_jrs; tb.k_range_in = h->d_krange;
-    const bool host_visible = hg != nullptr;
+    const bool host_visible = hg != nullptr || hj != nullptr;
     const int mode = host_visible ? h->host_write : -1;
     const bool timed = h->time_kernels || !host_visible;   // events are recorded here, read lazily by armour_last_eval_ms
     if (timed) CU(cudaEventRecord(h->ev[3], h->stream));
@@ -268,12 +269,12 @@ int launch_eval(armour_handle* h, const double* x, double* hg, double* hj, doubl
     const bool flag_in_kernel = host_visible && !h->write_value64 && mode == 0;
     double* kg = !host_visible ? h->d_g : (mode == 1 ? h->d_g : ag);
     double* kj = !host_visible ? h->d_jac : (mode == 0 ? aj : h->d_jac);
-    CU(launch_constraint_eval(tb, h->sel, h->h_x, kg, kj, h->d_link_center, h->d_done, flag_in_kernel ? h->d_done_flag : nullptr, seq, host_visible ? h->eval_bps_host : 0, h->stream));
+    CU(launch_constraint_eval(tb, h->sel, h->h_x, kg, kj, h->d_link_center, what, h->d_done, flag_in_kernel ? h->d_done_flag : nullptr, seq, host_visible ? h->eval_bps_host : 0, h->stream));
     h->launches += 1;
     if (host_visible) {
         const size_t m = (size_t)m_of(h);
-        if (mode == 1) CU(cudaMemcpyAsync(hg, h->d_g, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
-        if (mode >= 1) CU(cudaMemcpyAsync(hj, h->d_jac, sizeof(double) * m * NF, cudaMemcpyDeviceToHost, h->stream));
+        if (mode == 1 && (what & 1)) CU(cudaMemcpyAsync(hg, h->d_g, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+        if (mode >= 1 && (what & 2)) CU(cudaMemcpyAsync(hj, h->d_jac, sizeof(double) * m * NF, cudaMemcpyDeviceToHost, h->stream));
     }
     if (timed) CU(cudaEventRecord(h->ev[4], h->stream));
     if (host_visible) {
@@ -305,7 +306,7 @@ int launch_eval(armour_handle* h, const double* x, double* hg, double* hj, doubl
 int run_eval(armour_handle* h, const double* x, bool to_host) {
     int rc = to_host ? launch_eval(h, x, h->h_g, h->h_jac, h->a_g, h->a_jac) : launch_eval(h, x, nullptr, nullptr, nullptr, nullptr);
     if (rc != ARMOUR_OK) return rc;
-    if (x && to_host) { memcpy(h->last_x, x, sizeof(double) * NF); h->have_eval = true; }
+    if (x && to_host) { memcpy(h->last_x, x, sizeof(double) * NF); h->have_eval = true; h->staged = 3; }
     return ARMOUR_OK;
 }
 
@@ -608,28 +609,42 @@ int armour_release_host_buffers(armour_handle* h) {
     cudaGetLastError();
     return ARMOUR_OK;
 }
-int armour_eval_g_jac(armour_handle* h, const double* x, double* g, double* values) {
-    if (!h || !x) return fail(ARMOUR_E_INVALID, "null argument");
-    CU(cudaSetDevice(h->device));
-    if (h->cfg.pin_user_buffers && g && values && h->built) {   // zero staging: the kernel writes the caller's arrays
-        const int m = m_of(h);
-        double* dg = (double*)pinned_alias(h, g, sizeof(double) * m);
-        double* dj = dg ? (double*)pinned_alias(h, values, sizeof(double) * (size_t)m * NF, dg) : nullptr;
-        if (dg && dj) {
-            int rc = launch_eval(h, x, g, values, dg, dj);
+// Ipopt asks for g and for the Jacobian in separate callbacks (eval_g at every trial point, eval_jac_g once per accepted
+// iterate), so each entry point computes what it is asked for: `what` bit 0 = g, bit 1 = Jacobian.  With cfg.pin_user_buffers
+// the kernel writes the caller's page-locked arrays directly; otherwise results pass through the handle's pinned staging
+// buffers, and a repeated request at the same x is served from there.
+static int eval_into(armour_handle* h, const double* x, double* g, double* values) {
+    const int what = (g ? 1 : 0) | (values ? 2 : 0);
+    if (!h->built) return fail(ARMOUR_E_STATE, "eval before build");
+    const int m = m_of(h);
+    if (h->cfg.pin_user_buffers) {   // zero staging: the kernel writes the caller's arrays
+        double* dg = g ? (double*)pinned_alias(h, g, sizeof(double) * m) : nullptr;
+        double* dj = values ? (double*)pinned_alias(h, values, sizeof(double) * (size_t)m * NF, dg) : nullptr;
+        if ((!g || dg) && (!values || dj)) {
+            int rc = launch_eval(h, x, g, values, dg, dj, what);
             if (rc != ARMOUR_OK) return rc;
-            h->have_eval = false;
+            h->have_eval = true; h->staged = 0;      // link_sliced_center is current, nothing is staged
+            memcpy(h->last_x, x, sizeof(double) * NF);
             return ARMOUR_OK;
         }
     }
-    if (!(h->have_eval && memcmp(h->last_x, x, sizeof(double) * NF) == 0)) {
-        int rc = run_eval(h, x, true);
+    const bool same_x = h->have_eval && memcmp(h->last_x, x, sizeof(double) * NF) == 0;
+    const int missing = same_x ? (what & ~h->staged) : what;
+    if (missing) {
+        int rc = launch_eval(h, x, (missing & 1) ? h->h_g : nullptr, (missing & 2) ? h->h_jac : nullptr, h->a_g, h->a_jac, missing);
         if (rc != ARMOUR_OK) return rc;
+        h->staged = same_x ? (h->staged | missing) : missing;
+        memcpy(h->last_x, x, sizeof(double) * NF);
+        h->have_eval = true;
     }
-    const int m = m_of(h);
     if (g) memcpy(g, h->h_g, sizeof(double) * m);
     if (values) memcpy(values, h->h_jac, sizeof(double) * (size_t)m * NF);
     return ARMOUR_OK;
+}
+int armour_eval_g_jac(armour_handle* h, const double* x, double* g, double* values) {
+    if (!h || !x || (!g && !values)) return fail(ARMOUR_E_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    return eval_into(h, x, g, values);
 }
 int armour_eval_g(armour_handle* h, const double* x, double* g) { if (!g) return fail(ARMOUR_E_INVALID, "null argument"); return armour_eval_g_jac(h, x, g, nullptr); }
 int armour_eval_jac_g(armour_handle* h, const double* x, double* values) { if (!values) return fail(ARMOUR_E_INVALID, "null argument"); return armour_eval_g_jac(h, x, nullptr, values); }
@@ -637,6 +652,26 @@ int armour_eval_resident(armour_handle* h, const double* x) {
     if (!h) return fail(ARMOUR_E_INVALID, "null argument");
     CU(cudaSetDevice(h->device));
     return run_eval(h, x, false);
+}
+int armour_eval_resident_burst(armour_handle* h, const double* x, int launches, float* ms_per_launch) {
+    if (!h || !ms_per_launch || launches < 1) return fail(ARMOUR_E_INVALID, "bad argument");
+    if (!h->built) return fail(ARMOUR_E_STATE, "eval before build");
+    CU(cudaSetDevice(h->device));
+    if (x) memcpy(h->h_x, x, sizeof(double) * NF);
+    Tables tb = h->tb;
+    tb.P = h->count; tb.n_obs = h->n_obs; tb.mode = h->mode; tb.jrs = h->d_jrs; tb.k_range_in = h->d_krange;
+    CU(launch_constraint_eval(tb, h->sel, h->h_x, h->d_g, h->d_jac, h->d_link_center, 3, h->d_done, nullptr, 0, 0, h->stream));   // warm
+    CU(cudaEventRecord(h->ev[3], h->stream));
+    for (int i = 0; i < launches; i++)
+        CU(launch_constraint_eval(tb, h->sel, h->h_x, h->d_g, h->d_jac, h->d_link_center, 3, h->d_done, nullptr, 0, 0, h->stream));
+    CU(cudaEventRecord(h->ev[4], h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->launches += launches + 1;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]);
+    *ms_per_launch = ms / launches;
+    h->eval_timed = false;
+    return ARMOUR_OK;
 }
 int armour_upload_x(armour_handle* h, const double* x) {
     if (!h || !x) return fail(ARMOUR_E_INVALID, "null argument");
@@ -846,7 +881,12 @@ int armour_standin_solve(armour_handle* h, const double* q_des, double t_plan, d
     armtd_NLP nlp;
     nlp.set_time_steps(h->T);
     if (!nlp.set_parameters(q_des, t_plan, h)) return fail(ARMOUR_E_STATE, "set_parameters failed");
+    // the solver's own g / Jacobian vectors live for the whole solve: page-lock them so that every callback is a direct write
+    const int saved_pin = h->cfg.pin_user_buffers;
+    h->cfg.pin_user_buffers = 1;
     StandinResult r = standin_solve(nlp, k_opt);
+    h->cfg.pin_user_buffers = saved_pin;
+    if (!saved_pin) armour_release_host_buffers(h);
     if (feasible) *feasible = nlp.feasible ? 1 : 0;
     if (iterations) *iterations = r.iterations;
     if (evaluations) *evaluations = r.evaluations;

@@ -244,7 +244,7 @@ __host__ __device__ inline size_t eval_smem_bytes(int n_obs) {
 // done_counter / done_flag: when done_flag != nullptr the last block to finish stores `seq` there (mapped pinned host memory)
 // after a system-wide fence — the host polls that word instead of synchronising the stream.
 __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, int prob, XArg xarg, double* __restrict__ g, double* __restrict__ jac,
-                                                                     double* __restrict__ link_center_out, unsigned* done_counter,
+                                                                     double* __restrict__ link_center_out, int what, unsigned* done_counter,
                                                                      volatile unsigned long long* done_flag, unsigned long long seq) {
     extern __shared__ __align__(128) unsigned char eval_smem[];
     __shared__ __align__(8) unsigned long long mbar_storage;
@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
     double* sd = sA + (size_t)n_planes * 3;
     double* sdl = sd + n_planes;
     double* stage = sdl + n_planes;              // slice terms, later the block's output rows
+    const bool want_g = what & 1, want_j = what & 2;   // Ipopt asks for g and for the Jacobian in separate callbacks: each launch computes what is asked for
     if (blk == T * NJ) {   // limit rows (KPR/NLPclass.cu:319-320, 393-394)
         if (tb.mode == 1) {   // KPA/NLPclass.cu:275-276
             if (tid < NF) {
@@ -269,8 +270,8 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
                 armtd_state_extremum(st[tid], st[7 + tid], tb.k_range_in[(size_t)prob * NF + tid] * xarg.x[tid], ext, gr);
                 for (int r = 0; r < 4; r++) {
                     const size_t row = off_lim + r * NF + tid;
-                    g[row] = ext[r];
-                    for (int j = 0; j < NF; j++) jac[row * NF + j] = (j == tid) ? gr[r] : 0.0;
+                    if (want_g) g[row] = ext[r];
+                    if (want_j) for (int j = 0; j < NF; j++) jac[row * NF + j] = (j == tid) ? gr[r] : 0.0;
                 }
             }
         }
@@ -282,8 +283,8 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
             double mn, mx, gmn, gmx;
             joint_extremum(st[i], st[7 + i], st[14 + i], kr * xarg.x[i], velocity, &mn, &mx, &gmn, &gmx);
             const size_t r0 = off_lim + (velocity ? 2 * NF : 0) + i, r1 = r0 + NF;
-            g[r0] = mn; g[r1] = mx;   // DURATION == 1
-            for (int j = 0; j < NF; j++) { jac[r0 * NF + j] = (i == j) ? gmn * kr : 0.0; jac[r1 * NF + j] = (i == j) ? gmx * kr : 0.0; }
+            if (want_g) { g[r0] = mn; g[r1] = mx; }   // DURATION == 1
+            if (want_j) for (int j = 0; j < NF; j++) { jac[r0 * NF + j] = (i == j) ? gmn * kr : 0.0; jac[r1 * NF + j] = (i == j) ? gmx * kr : 0.0; }
         }
     }
     else {
@@ -317,11 +318,11 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
             const int ub = ps * EVAL_UCHUNK, uc = min(EVAL_UCHUNK, un - ub);
             const int lb = ps * EVAL_LCHUNK, lcn = min(EVAL_LCHUNK, ln - lb);
             // 8 * 16 torque terms on threads 0..127, 24 * 5 link terms on threads 0..119: two terms per thread and pass
-            if (tid < uc * 8) {
+            if (tid < uc * 8 && (want_j || (tid & 7) == 0) && (want_g || (tid & 7) != 0)) {
                 const int m = tid >> 3, w = tid & 7;
                 uterm[w * EVAL_UCHUNK + m] = slice_term(tb.u_coef[rec * UCAP + ub + m], tb.u_keys[rec * UCAP + ub + m], x, w - 1);
             }
-            if (tid < lcn * 24) {
+            if (tid < lcn * 24 && (want_j || (tid % 24) < 3)) {   // the link centre (value) is needed for both g and the arg-max of the Jacobian rows
                 const int m = tid / 24, w = tid - m * 24;
                 const int c = w % 3, which = w / 3;   // which 0: value, 1..7: d/dk_{which-1}
                 lterm[w * EVAL_LCHUNK + m] = slice_term(tb.l_coef[(rec * 3 + c) * LCAP + lb + m], tb.l_keys[rec * LCAP + lb + m], x, which - 1);
@@ -335,9 +336,9 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
             const size_t row = (size_t)t * NF + j;
             if (tid == 0) {
                 const double r = tb.u_ind[rec];
-                g[row] = ((acc - r) + (acc + r)) * 0.5;   // getCenter(Interval(c - r, c + r))
+                if (want_g) g[row] = ((acc - r) + (acc + r)) * 0.5;   // getCenter(Interval(c - r, c + r))
             }
-            else jac[row * NF + (tid - 1)] = acc;
+            else if (want_j) jac[row * NF + (tid - 1)] = acc;
         }
         if (sum_l) {
             const int c = lw % 3, which = lw / 3;
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
                     const int p = o * COMB + (best_e >> 1);
                     const bool neg = best_e & 1;
                     const double a0 = sA[p * 3], a1 = sA[p * 3 + 1], a2 = sA[p * 3 + 2];
-                    for (int k = q; k < NF; k += 4) {
+                    if (want_j) for (int k = q; k < NF; k += 4) {
                         const double dot = dadd(dadd(dmul(a0, ldk[k][0]), dmul(a1, ldk[k][1])), dmul(a2, ldk[k][2]));
                         sjac[o * NF + k] = neg ? dot : -dot;
                     }
@@ -402,8 +403,8 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
             __syncthreads();
             // rows (j*T + t)*n_obs + [0, n_obs) are contiguous in g and in jac: coalesced write-out
             const size_t row0 = off_obs + ((size_t)j * T + t) * n_obs;
-            for (int e = tid; e < n_obs; e += EVAL_NT) g[row0 + e] = sg[e];
-            for (int e = tid; e < n_obs * NF; e += EVAL_NT) jac[row0 * NF + e] = sjac[e];
+            if (want_g) for (int e = tid; e < n_obs; e += EVAL_NT) g[row0 + e] = sg[e];
+            if (want_j) for (int e = tid; e < n_obs * NF; e += EVAL_NT) jac[row0 * NF + e] = sjac[e];
         }
     }
     // ---- completion word for the polling host (see above) ----------------------------------------------------------
@@ -431,7 +432,7 @@ int eval_max_obstacles() { return EVAL_MAX_OBS; }
 // blocks_per_sm > 0 caps the resident blocks per SM by padding the dynamic shared-memory request.  With every block resident
 // at once (the default, best for device-resident results) all blocks finish together; when the results go to host memory
 // over PCIe it pays to run the grid in a few waves, so that the first rows are on the wire while later blocks still compute.
-cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* x_host, double* g, double* jac, double* link_center, unsigned* done_counter,
+cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* x_host, double* g, double* jac, double* link_center, int what, unsigned* done_counter,
                                    unsigned long long* done_flag, unsigned long long seq, int blocks_per_sm, cudaStream_t stream) {
     if (tb.n_obs > EVAL_MAX_OBS) return cudaErrorInvalidValue;
     XArg xa;
@@ -448,7 +449,7 @@ cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* x_h
             if (dev >= 0 && dev < 64) opted_in[dev] = true;
         }
     }
-    constraint_eval_kernel<<<tb.T * NJ + 1, EVAL_NT, smem, stream>>>(tb, prob, xa, g, jac, link_center, done_counter, done_flag, seq);
+    constraint_eval_kernel<<<tb.T * NJ + 1, EVAL_NT, smem, stream>>>(tb, prob, xa, g, jac, link_center, what, done_counter, done_flag, seq);
     return cudaGetLastError();
 }
 

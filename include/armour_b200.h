@@ -109,8 +109,10 @@ int armour_get_starting_point(armour_handle* h, double* x);
 /* armtd_NLP::eval_f / eval_grad_f (:207-267); q_des and t_plan are set_parameters' arguments (:30-60) */
 int armour_eval_f(armour_handle* h, const double* q_des, double t_plan, const double* x, double* obj_value);
 int armour_eval_grad_f(armour_handle* h, const double* q_des, double t_plan, const double* x, double* grad_f);
-/* armtd_NLP::eval_g (:272-324) and eval_jac_g (:330-396).  One fused kernel evaluates both; the second
- * call at the same x is served from the handle's pinned result buffers. */
+/* armtd_NLP::eval_g (:272-324) and eval_jac_g (:330-396).  One kernel slices the torque and link PZs at k and tests every link
+ * against every obstacle; each call computes and transfers only what it is asked for (Ipopt calls eval_g at every trial point
+ * and eval_jac_g once per accepted iterate).  Without cfg.pin_user_buffers a repeated request at the same x is served from the
+ * handle's pinned result buffers.  armour_eval_g_jac asks for both in one launch. */
 int armour_eval_g(armour_handle* h, const double* x, double* g);
 int armour_eval_jac_g(armour_handle* h, const double* x, double* values);
 int armour_eval_g_jac(armour_handle* h, const double* x, double* g, double* values);
@@ -173,6 +175,9 @@ int armour_upload_problems(armour_handle* h, int count, const double* q0, const 
 int armour_build_resident(armour_handle* h);
 int armour_eval_resident(armour_handle* h, const double* x); /* x == NULL: reuse the x uploaded by armour_upload_x */
 int armour_upload_x(armour_handle* h, const double* x);
+/* `launches` device-resident evaluations back to back between two CUDA events: average kernel time without the ~6 us that
+ * a single launch bracketed by two events reads high (roofline measurement of bench.py) */
+int armour_eval_resident_burst(armour_handle* h, const double* x, int launches, float* ms_per_launch);
 /* profiling builds (-DARMOUR_PHASE_TIMING) only: cycles / calls per engine phase summed over CTAs; zeros otherwise.
  * phases: 0 fill, 1 sort level, 2 segment walk, 3 scan+compact, 4 element-wise, 5 stage A, 6 export, 7 other */
 int armour_debug_phase_cycles(uint64_t* cycles8, uint64_t* calls8, int reset);
