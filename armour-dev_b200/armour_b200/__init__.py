@@ -18,7 +18,7 @@ NF = 7
 COMB = 36
 
 TABLES = {"cos_q": 0, "sin_q": 1, "R": 2, "R_t": 3, "qd_des": 4, "qda_des": 5, "qdda_des": 6, "links": 7, "u_nom": 8, "u_nom_int": 9}
-PZ_OPS = {"mul": 0, "add": 1, "sub": 2, "cross": 3}
+PZ_OPS = {"mul": 0, "add": 1, "sub": 2, "cross": 3, "simplify": 4, "add_one_dim0": 7, "add_one_dim1": 8, "add_one_dim2": 9, "cross_const_first": 10, "cross_const_second": 11}
 
 EXPORTS = [
     "armour_default_config", "armour_create", "armour_destroy", "armour_last_error", "armour_build", "armour_build_batch",

@@ -809,11 +809,12 @@ int armour_pz_binary(armour_handle* h, int op,
                      int b_rows, int b_cols, int b_n, const uint64_t* b_keys, const double* b_coeffs, const double* b_center, const double* b_independent,
                      int cap, int* dims, uint64_t* keys, double* coeffs, double* center, double* independent) {
     if (!h || !dims || !keys || !coeffs || !center || !independent || !a_center || !b_center || !a_independent || !b_independent) return fail(ARMOUR_E_INVALID, "null argument");
-    if (op < 0 || op > 3 || a_n < 0 || b_n < 0) return fail(ARMOUR_E_INVALID, "bad op");
+    if (op < 0 || op > 11 || op == 5 || op == 6 || a_n < 0 || b_n < 0) return fail(ARMOUR_E_INVALID, "bad op");
     {   // shapes are validated before any operand array is read (each array holds rows * cols values per monomial)
         const bool a11 = a_rows == 1 && a_cols == 1, a31 = a_rows == 3 && a_cols == 1, a33 = a_rows == 3 && a_cols == 3;
         const bool b11 = b_rows == 1 && b_cols == 1, b31 = b_rows == 3 && b_cols == 1, b33 = b_rows == 3 && b_cols == 3;
-        const bool ok = op == 0 ? ((a33 && (b31 || b33)) || (a11 && b11)) : op == 3 ? (a31 && b31) : ((a31 && b31) || (a11 && b11));
+        const bool ok = op == 0 ? ((a33 && (b31 || b33)) || (a11 && b11)) : op == 3 ? (a31 && b31) : op == 4 ? (a11 || a31 || a33)
+                      : (op >= 7 && op <= 9) ? (a31 && b11) : (op == 10 || op == 11) ? (a31 && b31 && b_n == 0) : ((a31 && b31) || (a11 && b11));
         if (!ok) return fail(ARMOUR_E_INVALID, "unsupported operand shapes for this operation");
         if ((a_n > 0 && (!a_keys || !a_coeffs)) || (b_n > 0 && (!b_keys || !b_coeffs)) || cap < 0) return fail(ARMOUR_E_INVALID, "null operand arrays");
     }

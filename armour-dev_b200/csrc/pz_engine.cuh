@@ -875,6 +875,34 @@ __device__ __noinline__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA> A,
     if (N <= S.scap) pz_merge_impl<NT, DA, DB, DO, false>(S, dst, A, B, negb, N);
     else pz_merge_impl<NT, DA, DB, DO, true>(S, dst, A, B, negb, N);
 }
+// simplify() of an arbitrary monomial list (unsorted, repeated keys allowed): KPR/PZsparse.cu:284-350.  The engine's own
+// operations never need it (their operands are sorted and unique by construction); it backs PZsparse::simplify / stack of
+// the host facade.  A full merge sort from runs of width 1, ties on the list position (= stable), then the shared walk.
+template <int D>
+struct SimplifyEpi {
+    const PZ<D>& A;
+    __device__ __forceinline__ void operator()(int c, double& cen, double& r0, double& r1) const { cen = A.center[c]; r0 = A.ind[0][c]; r1 = A.ind[1][c]; }
+};
+template <int NT, int D, bool BIG>
+__device__ __forceinline__ void pz_simplify_impl(Scratch& S, PZ<D>& dst, const PZ<D>& A, int N) {
+    u64* key = Buf<BIG>::key(S, 0);
+    u16* idx = Buf<BIG>::idx(S, 0);
+    const u64* ka = A.keys;
+    #pragma unroll 1
+    for (int i = gtid<NT>(); i < N; i += NT) { key[i] = ka[i]; idx[i] = (u16)i; }
+    const View<D> va = view(A);
+    MergeOp<D, D, D> op{va, va, N, false, S.thr_sq, A.coef, A.coef, A.cap, A.cap};   // every origin index is below na = N: the second view is never read
+    gsync<NT>();
+    const int buf = merge_sort_runs<NT, BIG>(S, N, 1, FastDiv::magic(1));
+    reduce_emit<NT, D, BIG, MergeOp<D, D, D>, SimplifyEpi<D>>(S, buf, N, op, dst, SimplifyEpi<D>{A});
+}
+template <int NT, int D>
+__device__ __noinline__ void pz_simplify(Scratch& S, PZ<D>& dst, const PZ<D>& A) {
+    int N = A.n;
+    if (N > S.ncap || N > 65535) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
+    if (N <= S.scap) pz_simplify_impl<NT, D, false>(S, dst, A, N);
+    else pz_simplify_impl<NT, D, true>(S, dst, A, N);
+}
 template <int NT> __device__ __forceinline__ void pz_add3(Scratch& S, PZ<3>& dst, const PZ<3>& a, const PZ<3>& b) { pz_merge<NT, 3, 3, 3>(S, dst, view(a), view(b), false); }
 // dst = a with the scalar PZ s added into row `row`   (addOneDimPZ)
 template <int NT> __device__ __forceinline__ void pz_add_one_dim(Scratch& S, PZ<3>& dst, const PZ<3>& a, const PZ<1>& s, int row) {

@@ -815,6 +815,19 @@ __global__ void __launch_bounds__(NT) pz_binary_kernel(int op, FlatPZ a, FlatPZ 
         else if (a.dim == 1 && b.dim == 1) { load_flat<1>(a1, a); load_flat<1>(b1, b); __syncthreads(); pz_merge<NT, 1, 1, 1>(S, r1, view(a1), view(b1), op == 2); o.n = r1.n; o.dim = 1; store_flat<1>(r, r1); }
     }
     else if (op == 3 && a.dim == 3 && b.dim == 3) { load_flat<3>(a3, a); load_flat<3>(b3, b); __syncthreads(); pz_cross_pp<NT>(S, r3, a3, b3); o.n = r3.n; o.dim = 3; store_flat<3>(r, r3); }
+    else if (op == 4) {   // simplify
+        if (a.dim == 1) { load_flat<1>(a1, a); __syncthreads(); pz_simplify<NT, 1>(S, r1, a1); o.n = r1.n; o.dim = 1; store_flat<1>(r, r1); }
+        else if (a.dim == 3) { load_flat<3>(a3, a); __syncthreads(); pz_simplify<NT, 3>(S, r3, a3); o.n = r3.n; o.dim = 3; store_flat<3>(r, r3); }
+        else if (a.dim == 9) { load_flat<9>(a9, a); __syncthreads(); pz_simplify<NT, 9>(S, r9, a9); o.n = r9.n; o.dim = 9; store_flat<9>(r, r9); }
+    }
+    else if (op >= 7 && op <= 9 && a.dim == 3 && b.dim == 1) {   // addOneDimPZ(b, row, 0)
+        load_flat<3>(a3, a); load_flat<1>(b1, b); __syncthreads(); pz_add_one_dim<NT>(S, r3, a3, b1, op - 7); o.n = r3.n; o.dim = 3; store_flat<3>(r, r3);
+    }
+    else if ((op == 10 || op == 11) && a.dim == 3 && b.dim == 3) {   // cross(constant, a) / cross(a, constant): the constant is b's centre
+        load_flat<3>(a3, a); load_flat<3>(b3, b); __syncthreads();
+        const double kv[3] = {b3.center[0], b3.center[1], b3.center[2]};
+        pz_cross_const<NT>(S, r3, a3, kv, op == 10); o.n = r3.n; o.dim = 3; store_flat<3>(r, r3);
+    }
     __syncthreads();
     if (threadIdx.x == 0) { if (o.dim == 1) o.n = r1.n; else if (o.dim == 3) o.n = r3.n; else if (o.dim == 9) o.n = r9.n; *out = o; }
 }

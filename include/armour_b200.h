@@ -143,8 +143,11 @@ int armour_get_taylor_remainders(armour_handle* h, double* cos_rem, double* sin_
 int armour_get_pz(armour_handle* h, int which, int idx, int t, int* dims, uint64_t* keys, double* coeffs, double* center, double* independent);
 
 /* ---- stand-alone PZsparse arithmetic on the device (PZsparse facade; primitive parity tests) --------- */
-/* op: 0 a*b, 1 a+b, 2 a-b, 3 cross(a,b) for 3x1 operands.  Shapes supported: (3x3)*(3x1), (3x3)*(3x3),
- * (1x1)*(1x1); + and - for 1x1 and 3x1; any other shape is rejected with ARMOUR_E_INVALID before anything is read.
+/* op: 0 a*b, 1 a+b, 2 a-b, 3 cross(a,b) for 3x1 operands, 4 simplify(a) (any monomial list: unsorted, repeated keys; b is ignored,
+ * pass a 1x1 with b_n = 0), 7/8/9 a.addOneDimPZ(b, row 0/1/2, 0) for a 3x1 and b 1x1, 10 cross(c, a) and 11 cross(a, c) with the
+ * constant 3-vector c = b_center (b 3x1, b_n = 0).  (5 and 6 — reduce, transpose — are pure data movement and live in the host
+ * facade.)  Shapes supported: (3x3)*(3x1), (3x3)*(3x3), (1x1)*(1x1); + and - for 1x1 and 3x1; simplify for 1x1, 3x1, 3x3;
+ * any other shape is rejected with ARMOUR_E_INVALID before anything is read.
  * Returns the monomial count (>= 0) or a negative ARMOUR_E_* code: ARMOUR_E_CAPACITY when the result has more than `cap`
  * monomials or the candidate list exceeds cfg.max_entries, ARMOUR_E_NUMERIC when a monomial degree outgrows its key field. */
 int armour_pz_binary(armour_handle* h, int op,

@@ -1088,6 +1088,9 @@ int oracle_pz_binary(int op, double threshold,
         else if (op == 1) r = a + b;
         else if (op == 2) r = a - b;
         else if (op == 3) r = cross(a, b);
+        else if (op >= 7 && op <= 9) { r = a; r.addOneDimPZ(b, op - 7, 0); }          // KPR/PZsparse.cu:1068-1085
+        else if (op == 10) r = cross(b.center, a);                                       // :1118-1132, the constant is b's centre
+        else if (op == 11) r = cross(a, b.center);                                       // :1153-1167
         else return -1;
     }
     return pz_to_flat(r, cap, dims, keys, coeffs, center, indep);

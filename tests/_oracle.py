@@ -223,7 +223,8 @@ class Oracle:
         return out.reshape(cap, 8)[: min(n, cap)]
 
 
-PZ_OPS = {"mul": 0, "add": 1, "sub": 2, "cross": 3, "simplify": 4, "reduce": 5, "transpose": 6}
+PZ_OPS = {"mul": 0, "add": 1, "sub": 2, "cross": 3, "simplify": 4, "reduce": 5, "transpose": 6, "add_one_dim0": 7, "add_one_dim1": 8, "add_one_dim2": 9,
+          "cross_const_first": 10, "cross_const_second": 11}
 
 
 def pz_binary(op, a, b=None, threshold=5e-4, cap=1 << 16):

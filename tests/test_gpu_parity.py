@@ -374,3 +374,58 @@ def test_pinned_buffers_default_arrays_are_owned_by_the_planner(gpu_lib):
         assert b.L.armour_release_host_buffers(b.h) == 0 if it % 5 == 4 else True
         junk.append((g, J))        # keep them alive: the contract for caller-provided arrays
     a.close(); b.close()
+
+
+# ---- the rest of the PZsparse public surface that runs on the device (round 2) ------------------------------------------
+def _shuffled_with_repeats(rng, z, repeats):
+    """an un-simplified monomial list: z's monomials in random order with `repeats` of them split into two parts"""
+    keys, co = list(z["keys"]), [c.copy() for c in z["coeffs"]]
+    for i in rng.choice(len(keys), size=min(repeats, len(keys)), replace=False):
+        part = co[i] * rng.uniform(0.2, 0.8)
+        co[i] = co[i] - part
+        keys.append(keys[i]); co.append(part)
+    order = rng.permutation(len(keys))
+    return dict(z, keys=np.array(keys, dtype=np.uint64)[order], coeffs=np.array(co)[order])
+
+
+@pytest.mark.parametrize("shape,n", [((1, 1), 40), ((3, 1), 300), ((3, 3), 25), ((3, 1), 0), ((3, 1), 2500)])
+def test_pz_simplify_primitive(shape, n, gpu_lib):
+    """PZsparse::simplify (KPR/PZsparse.cu:284-350) of an arbitrary list: unsorted, repeated keys, coefficients straddling
+    the threshold.  The 2500-monomial case sorts in global memory (more candidates than the shared sort buffers hold)."""
+    rng = np.random.default_rng(zlib.crc32(repr((shape, n)).encode()))
+    p = ab.Planner(T=2)
+    dummy = dict(rows=1, cols=1, keys=np.zeros(0, dtype=np.uint64), coeffs=np.zeros((0, 1)), center=np.zeros(1), independent=np.zeros(1))
+    for trial in range(2):
+        z = _shuffled_with_repeats(rng, random_pz(rng, shape[0], shape[1], n), n // 3)
+        ref = _oracle.pz_binary("simplify", z, None)
+        dev = p.pz_binary("simplify", z, dummy)
+        assert_pz_equal(ref, dev, "simplify %s n=%d trial %d" % (shape, n, trial))
+    p.close()
+
+
+@pytest.mark.parametrize("row", [0, 1, 2])
+def test_pz_add_one_dim_primitive(row, gpu_lib):
+    rng = np.random.default_rng(40 + row)
+    p = ab.Planner(T=2)
+    for na, nb in ((120, 30), (0, 9), (50, 0)):
+        a, b = random_pz(rng, 3, 1, na), random_pz(rng, 1, 1, nb)
+        if na and nb:
+            b["keys"][: nb // 2] = a["keys"][: nb // 2]        # shared keys: the scalar's terms merge into row `row`
+            order = np.argsort(b["keys"], kind="stable")
+            order = order[np.concatenate([[True], np.diff(b["keys"][order]) != 0])]
+            b["keys"], b["coeffs"] = b["keys"][order], b["coeffs"][order]
+        op = "add_one_dim%d" % row
+        assert_pz_equal(_oracle.pz_binary(op, a, b), p.pz_binary(op, a, b), "%s na=%d nb=%d" % (op, na, nb))
+    p.close()
+
+
+@pytest.mark.parametrize("op", ["cross_const_first", "cross_const_second"])
+def test_pz_cross_with_constant_primitive(op, gpu_lib):
+    """cross(Eigen vector, PZ) and cross(PZ, Eigen vector) (KPR/PZsparse.cu:1118-1132, 1153-1167)"""
+    rng = np.random.default_rng(zlib.crc32(op.encode()))
+    p = ab.Planner(T=2)
+    for n in (0, 7, 350):
+        a = random_pz(rng, 3, 1, n)
+        c = dict(rows=3, cols=1, keys=np.zeros(0, dtype=np.uint64), coeffs=np.zeros((0, 3)), center=rng.standard_normal(3) * [1.0, 1e-3, 0.2], independent=np.zeros(3))
+        assert_pz_equal(_oracle.pz_binary(op, a, c), p.pz_binary(op, a, c), "%s n=%d" % (op, n))
+    p.close()
