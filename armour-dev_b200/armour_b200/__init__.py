@@ -26,7 +26,7 @@ EXPORTS = [
     "armour_eval_grad_f", "armour_eval_g", "armour_eval_jac_g", "armour_eval_g_jac", "armour_jac_structure", "armour_release_host_buffers", "armour_check_feasible",
     "armour_get_torque_radius", "armour_get_link_generators", "armour_get_link_sliced_center", "armour_get_hyperplanes",
     "armour_get_taylor_remainders", "armour_get_pz", "armour_pz_binary", "armour_last_build_ms", "armour_last_eval_ms",
-    "armour_kernel_launches", "armour_set_kernel_timing", "armour_last_eval_host_us", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_eval_resident_burst", "armour_upload_x", "armour_standin_solve", "armour_debug_phase_cycles", "armour_measure_fp64_peak",
+    "armour_kernel_launches", "armour_set_kernel_timing", "armour_last_eval_host_us", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_eval_resident_burst", "armour_upload_x", "armour_standin_solve", "armour_debug_phase_cycles", "armour_debug_canaries_verified", "armour_measure_fp64_peak",
 ]
 
 

@@ -7,6 +7,7 @@
 #include "../host/standin_solver.hpp"
 
 #include <chrono>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nanoseconds unless a profiler is attached
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -198,20 +199,23 @@ int alloc_konly_tables(armour_handle* h) {
     return ARMOUR_OK;
 }
 
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
+
 int run_build(armour_handle* h) {   // kernels only; inputs already on the device
+    NvtxRange range("armour_build: reach sets + half-space tables");
     const int n_work = h->count * h->T;
     Tables tb = h->tb;
     tb.P = h->count; tb.n_obs = h->n_obs; tb.mode = h->mode; tb.jrs = h->d_jrs; tb.k_range_in = h->d_krange;
     for (int attempt = 0; attempt < 6; attempt++) {
         tb.u_keys = h->tb.u_keys; tb.u_coef = h->tb.u_coef; tb.l_keys = h->tb.l_keys; tb.l_coef = h->tb.l_coef; tb.ucap = h->tb.ucap; tb.lcap = h->tb.lcap;
-        CU(cudaMemsetAsync(h->d_err, 0, 2 * sizeof(int), h->stream));   // error word, work counter
+        CU(cudaMemsetAsync(h->d_err, 0, 3 * sizeof(int), h->stream));   // error word, work counter, guard words verified
         CU(cudaEventRecord(h->ev[0], h->stream));
         CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, h->scap, h->tcap, n_work, std::min(h->grid, n_work), h->nt, h->minb, h->groups, h->stream));
         CU(cudaEventRecord(h->ev[1], h->stream));
         CU(launch_hyperplanes(tb, h->stream));
         CU(cudaEventRecord(h->ev[2], h->stream));
         h->launches += (h->n_obs > 0) ? 2 : 1;
-        CU(cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->h_err, h->d_err, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaMemcpyAsync(h->h_torque_radius, h->tb.torque_radius, sizeof(double) * (size_t)h->count * h->T * NF, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
         cudaEventElapsedTime(&h->reach_ms, h->ev[0], h->ev[1]);
@@ -221,6 +225,7 @@ int run_build(armour_handle* h) {   // kernels only; inputs already on the devic
         if (err == 0) { h->built = true; h->have_eval = false; h->mirror_valid = false; return ARMOUR_OK; }
         if (err & 16) return fail(ARMOUR_E_NUMERIC, "reach-set build: a monomial degree outgrew its key field (more than 3 for k / cos / sin error symbols, more than 1 for the others; KPR/PZsparse.h:23-40)");
         if (err & 8) return fail(ARMOUR_E_NUMERIC, "reach-set build: a link PZ has a pure link generator other than the three box generators");
+        if (err & 128) return fail(ARMOUR_E_CUDA, "reach-set build: an arena guard word was overwritten (debug build, ARMOUR_ARENA_CANARY)");
         if (err & 32) return fail(ARMOUR_E_CUDA, "reach-set build: a hand-off between the two thread groups of a CTA timed out (internal error)");
         // a capacity was exceeded: grow what overflowed and retry (documented in armour_b200.h)
         if ((err & 1) && h->ncap >= 65534) return fail(ARMOUR_E_CAPACITY, "an operation has more than 65535 candidate monomials");
@@ -257,6 +262,7 @@ int run_build(armour_handle* h) {   // kernels only; inputs already on the devic
 //   calling cudaStreamSynchronize, which saves the driver's wake-up latency on the per-iteration path.
 int launch_eval(armour_handle* h, const double* x, double* hg, double* hj, double* ag, double* aj, int what = 3) {
     if (!h->built) return fail(ARMOUR_E_STATE, "eval before build");
+    NvtxRange range("armour_eval: constraints + Jacobian");
     const auto t_begin = std::chrono::steady_clock::now();
     if (x) memcpy(h->h_x, x, sizeof(double) * NF);
     Tables tb = h->tb;
@@ -466,13 +472,13 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     { int rc = alloc_konly_tables(h); if (rc != ARMOUR_OK) return rc; }
     CU(dalloc(&tb.l_center, P * T * NJ * 3)); CU(dalloc(&tb.l_ind, P * T * NJ * 3)); CU(dalloc(&tb.gens, P * T * NJ * 18));
     CU(dalloc(&tb.A, P * T * NJ * O * COMB * 3)); CU(dalloc(&tb.d, P * T * NJ * O * COMB)); CU(dalloc(&tb.delta, P * T * NJ * O * COMB));
-    CU(dalloc(&h->d_err, 2)); tb.err = h->d_err;
+    CU(dalloc(&h->d_err, 3)); tb.err = h->d_err;
     const size_t mmax = NF * T + NJ * T * O + NF * 4;
     CU(dalloc(&h->d_x, NF)); CU(dalloc(&h->d_g, mmax)); CU(dalloc(&h->d_jac, mmax * NF)); CU(dalloc(&h->d_link_center, T * NJ * 3));
     CU(cudaMallocHost((void**)&h->h_state, sizeof(double) * P * 21)); CU(cudaMallocHost((void**)&h->h_obs, sizeof(double) * P * O * 12));
     CU(cudaMallocHost((void**)&h->h_x, sizeof(double) * NF)); CU(cudaMallocHost((void**)&h->h_g, sizeof(double) * mmax));
     CU(cudaMallocHost((void**)&h->h_jac, sizeof(double) * mmax * NF)); CU(cudaMallocHost((void**)&h->h_torque_radius, sizeof(double) * P * T * NF));
-    CU(cudaMallocHost((void**)&h->h_err, sizeof(int)));
+    CU(cudaMallocHost((void**)&h->h_err, 3 * sizeof(int)));
     CU(cudaHostGetDevicePointer((void**)&h->a_g, h->h_g, 0)); CU(cudaHostGetDevicePointer((void**)&h->a_jac, h->h_jac, 0));
     CU(dalloc(&h->d_done, 1)); CU(cudaMemset(h->d_done, 0, sizeof(unsigned)));
     CU(cudaHostAlloc((void**)&h->h_done, sizeof(unsigned long long), cudaHostAllocMapped));
@@ -909,6 +915,11 @@ int armour_last_eval_ms(armour_handle* h, float* kernel_ms) {
         h->eval_timed = false;
     }
     *kernel_ms = h->eval_ms;
+    return ARMOUR_OK;
+}
+int armour_debug_canaries_verified(armour_handle* h, int* count) {
+    if (!h || !count) return fail(ARMOUR_E_INVALID, "null argument");
+    *count = h->h_err ? h->h_err[2] : 0;
     return ARMOUR_OK;
 }
 int armour_last_eval_host_us(armour_handle* h, double* microseconds) {

@@ -73,7 +73,7 @@ struct Tables {
     double* d;                 // [P][T][NJ][n_obs][COMB]
     double* delta;
     // per-problem Bezier constants needed by the limit rows of the constraint kernel are recomputed there
-    int* err;                  // [2] error word, work counter of the persistent reach kernel
+    int* err;                  // [3] error word, work counter of the persistent reach kernel, guard words verified (debug build)
 };
 
 }  // namespace armour

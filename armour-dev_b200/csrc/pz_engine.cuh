@@ -44,7 +44,7 @@ static constexpr u64 KEY_K_ONLY = 1ull << 14;         // key < this  <=> depends
 static constexpr u64 KEY_K_LINKS_ONLY = 1ull << 35;   // (PZsparse.h:40)
 static constexpr u64 KEY_K_MASK = KEY_K_ONLY - 1;
 
-enum { ERR_NONE = 0, ERR_ENTRY_CAP = 1, ERR_MONO_CAP = 2, ERR_TABLE_CAP = 4, ERR_LINK_GEN = 8, ERR_DEGREE = 16, ERR_SYNC = 32, ERR_LTABLE_CAP = 64 };
+enum { ERR_NONE = 0, ERR_ENTRY_CAP = 1, ERR_MONO_CAP = 2, ERR_TABLE_CAP = 4, ERR_LINK_GEN = 8, ERR_DEGREE = 16, ERR_SYNC = 32, ERR_LTABLE_CAP = 64, ERR_CANARY = 128 };
 
 // Degree-overflow guard for key addition.  The reference adds keys without checking ("do not have to check carry",
 // KPR/PZsparse.cu:938-940): a degree that outgrows its field (3 for the 2-bit fields, 1 for the 1-bit ones) silently corrupts

@@ -359,9 +359,22 @@ struct Slots {
 };
 constexpr int N_BIG3 = 8 + 10 + 3 + 5 * NJ;   // W/WD/WA/LA x 2, two temporary sets, Fv/Nv/FKT, C1/C2/F/N/LINK per joint
 
+// Debug builds (-DARMOUR_ARENA_CANARY, `make canary`): every PZ slot of the arena is followed by a guard word that the kernel
+// checks after its last interval; a write past a slot's capacity — which the capacity checks of the engine are there to
+// prevent — sets ERR_CANARY.  (compute-sanitizer is closed on this GPU pool: profiles/r2_sanitizer_refusal.txt.)
+#ifdef ARMOUR_ARENA_CANARY
+constexpr u64 CANARY_WORD = 0xA5C3F00DDEADBEEFull;
+constexpr int CANARY_MAX = 192;
+__shared__ u64* g_canary[CANARY_MAX];
+__shared__ int g_ncanary;
+#define CANARY_BYTES 16
+#else
+#define CANARY_BYTES 0
+#endif
 __host__ __device__ constexpr size_t cold_arena_bytes() { return (sizeof(ColdSlots) + 255) & ~(size_t)255; }
 size_t arena_bytes(int mcap, int ncap, int groups) {
     size_t b = cold_arena_bytes();                                // per-joint descriptors (narrow sweep shapes)
+    b += (size_t)CANARY_BYTES * 160;                              // guard words of the debug build (one per slot)
     b += (size_t)N_BIG3 * mcap * (8 + 3 * 8);                    // big 3-vectors
     b += (size_t)NJ * SMALL_CAP * (8 + 3 * 8);                    // link0
     b += (size_t)mcap * (8 + 9 * 8);                              // FK_R
@@ -377,6 +390,10 @@ __device__ __noinline__ char* carve(PZ<D>& z, char* p, int cap) {
     z.cap = cap; z.n = 0; z.divM = FastDiv::magic(0);
     z.keys = (u64*)p; p += (size_t)cap * 8;
     z.coef = (double*)p; p += (size_t)cap * 8 * D;
+#ifdef ARMOUR_ARENA_CANARY
+    if (g_ncanary < CANARY_MAX) { g_canary[g_ncanary++] = (u64*)p; *(u64*)p = CANARY_WORD; }
+    p += CANARY_BYTES;
+#endif
     for (int c = 0; c < D; c++) { z.center[c] = 0; z.ind[0][c] = 0; z.ind[1][c] = 0; z.abss[c] = 0; }
     return p;
 }
@@ -586,6 +603,9 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
                                 : *reinterpret_cast<ColdSlots*>(smem_raw);
     Slots Z{ZH, ZC};
     if (threadIdx.x == 0) {
+#ifdef ARMOUR_ARENA_CANARY
+        g_ncanary = 0;
+#endif
         char* g = arena + (size_t)blockIdx.x * arena_stride + cold_arena_bytes();
         for (int k = 0; k < 2; k++) { g = carve<3>(Z.h.W[k], g, mcap); g = carve<3>(Z.h.WD[k], g, mcap); g = carve<3>(Z.h.WA[k], g, mcap); g = carve<3>(Z.h.LA[k], g, mcap); }
         for (int k = 0; k < GROUPS; k++) for (int t = 0; t < 5; t++) g = carve<3>(TT[k][t], g, mcap);
@@ -770,6 +790,14 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
         if (threadIdx.x == 0) next_work = (int)gridDim.x + atomicAdd(tb.err + 1, 1);
         __syncthreads();
     }
+#ifdef ARMOUR_ARENA_CANARY
+    if (threadIdx.x == 0) {
+        bool ok = g_ncanary > 100 && g_ncanary < CANARY_MAX;
+        for (int i = 0; i < g_ncanary && i < CANARY_MAX; i++) ok = ok && (*g_canary[i] == CANARY_WORD);
+        if (!ok) atomicOr(tb.err, ERR_CANARY);
+        else atomicAdd(tb.err + 2, g_ncanary);   // guard words verified (read back by the canary test)
+    }
+#endif
     (void)zero3;
 }
 

@@ -184,6 +184,9 @@ int armour_eval_resident_burst(armour_handle* h, const double* x, int launches, 
 /* profiling builds (-DARMOUR_PHASE_TIMING) only: cycles / calls per engine phase summed over CTAs; zeros otherwise.
  * phases: 0 fill, 1 sort level, 2 segment walk, 3 scan+compact, 4 element-wise, 5 stage A, 6 export, 7 other */
 int armour_debug_phase_cycles(uint64_t* cycles8, uint64_t* calls8, int reset);
+/* debug builds (-DARMOUR_ARENA_CANARY, `make canary`) only: guard words behind the arena's PZ slots that the last build
+ * found intact, summed over CTAs (0 in the product build); an overwritten guard word fails the build with ARMOUR_E_CUDA */
+int armour_debug_canaries_verified(armour_handle* h, int* count);
 /* fp64 FMA micro-benchmark (TFLOP/s) used as the fp64 roofline denominator */
 int armour_measure_fp64_peak(int device, double* tflops);
 

@@ -429,3 +429,30 @@ def test_pz_cross_with_constant_primitive(op, gpu_lib):
         c = dict(rows=3, cols=1, keys=np.zeros(0, dtype=np.uint64), coeffs=np.zeros((0, 3)), center=rng.standard_normal(3) * [1.0, 1e-3, 0.2], independent=np.zeros(3))
         assert_pz_equal(_oracle.pz_binary(op, a, c), p.pz_binary(op, a, c), "%s n=%d" % (op, n))
     p.close()
+
+
+def test_arena_guard_words_stay_intact(gpu_lib):
+    """compute-sanitizer is closed on this GPU pool (profiles/r2_sanitizer_refusal.txt), so memory safety of the per-CTA arena
+    is checked by a debug build of the library (`make canary`): a guard word behind every PZ slot, verified by the kernel after
+    its last interval.  Runs a single plan (two thread groups) and a batch (sweep shape) with deliberately small monomial
+    capacities, so that the grow-and-retry path — the place where an off-by-one would write past a slot — is exercised too."""
+    import subprocess, sys
+    lib = os.path.join(ROOT, "armour-dev_b200", "libarmour_b200_canary.so")
+    assert os.path.exists(lib), "run __graft_entry__.build()"
+    code = ("import sys, ctypes as C; sys.path[:0] = [%r, %r]\n"
+            "import numpy as np, armour_b200 as ab\nab.LIB_PATH = %r\nfrom problems import make_problem, DEBUG_K\n"
+            "def verified(p):\n    v = C.c_int(); assert p.L.armour_debug_canaries_verified(p.h, C.byref(v)) == 0; return v.value\n"
+            "q0, qd0, qdd0, _, obs = make_problem(21, 4)\n"
+            "for mono in (0, 96):\n"
+            "    p = ab.Planner(T=16, max_monomials=mono); p.build(q0, qd0, qdd0, obs); g, J = p.eval_g_jac(DEBUG_K)\n"
+            "    print('SINGLE %%d %%.17g' %% (verified(p), g.sum())); p.close()\n"
+            "bp = [make_problem(70 + b, 4) for b in range(3)]\n"
+            "pb = ab.Planner(T=16, batch=3, max_monomials=96)\n"
+            "pb.build_batch(np.concatenate([q[0] for q in bp]), np.concatenate([q[1] for q in bp]), np.concatenate([q[2] for q in bp]), np.concatenate([q[4] for q in bp]), 4)\n"
+            "print('BATCH %%d' %% verified(pb))\n" % (os.path.join(ROOT, "armour-dev_b200"), os.path.join(ROOT, "tests"), lib))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr[-800:]
+    single = [l.split() for l in r.stdout.splitlines() if l.startswith("SINGLE")]
+    assert len(single) == 2 and all(int(s[1]) >= 16 * 100 for s in single), r.stdout      # > 100 guard words per CTA, 16 CTAs
+    assert single[0][2] == single[1][2]                                                  # the retried build gives the same numbers
+    assert int([l.split()[1] for l in r.stdout.splitlines() if l.startswith("BATCH")][0]) >= 100
