@@ -414,6 +414,7 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ARMOUR_E_CUDA, "no CUDA device: this library has no CPU fallback");
     armour_handle* h = new armour_handle();
     h->cfg = cfg;
+    bool no_structured_env = false;
     if (cfg.device >= 0) { if (cudaSetDevice(cfg.device) != cudaSuccess) { delete h; return fail(ARMOUR_E_CUDA, "cudaSetDevice failed"); } }
     cudaGetDevice(&h->device);
     cudaDeviceProp prop;
@@ -431,6 +432,7 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     if (const char* e = getenv("ARMOUR_TUNE_MINB")) h->minb = atoi(e);
     if (const char* e = getenv("ARMOUR_TUNE_MCAP")) h->mcap = std::max(64, atoi(e));
     if (const char* e = getenv("ARMOUR_TUNE_EVAL_BPS")) h->eval_bps_host = atoi(e);
+    if (const char* e = getenv("ARMOUR_TUNE_NO_STRUCTURED")) no_structured_env = atoi(e) != 0;
     if (const char* e = getenv("ARMOUR_TUNE_HOST_WRITE")) h->host_write = std::min(2, std::max(0, atoi(e)));
     {
         void* fn = nullptr;
@@ -459,6 +461,8 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     tb.T = h->T; tb.P = h->P; tb.n_obs = 0;
     for (int i = 0; i < NF; i++) tb.k_range[i] = cfg.k_range[i];
     tb.mass_unc = cfg.mass_uncertainty; tb.inertia_unc = cfg.inertia_uncertainty; tb.thr = cfg.simplify_threshold;
+    tb.no_structured = no_structured_env ? 1 : 0;
+    if (const char* e = getenv("ARMOUR_TUNE_STATIC_STRIDE")) tb.static_stride = atoi(e) != 0;
     CU(dalloc(&h->d_state, P * 21)); CU(dalloc(&h->d_obs, P * O * 12));
     CU(dalloc(&h->d_jrs, (size_t)6 * NF * T)); CU(dalloc(&h->d_krange, (size_t)NF));
     CU(cudaMallocHost((void**)&h->h_jrs, sizeof(double) * 6 * NF * T)); CU(cudaMallocHost((void**)&h->h_krange, sizeof(double) * NF));

@@ -41,6 +41,8 @@ enum { TRAJ_COS = 0, TRAJ_SIN = 1, TRAJ_R = 2, TRAJ_RT = 3, TRAJ_QD = 4, TRAJ_QD
 struct Tables {
     int T, P, n_obs;
     int ucap, lcap;            // capacities of the k-only monomial tables below
+    int static_stride;         // 1: persistent CTAs take work items blockIdx + k * gridDim instead of a shared counter (experiments)
+    int no_structured;         // 1: every product takes the generic sort path (A/B measurements; ARMOUR_TUNE_NO_STRUCTURED)
     double k_range[NF];
     double mass_unc, inertia_unc, thr;
     // inputs

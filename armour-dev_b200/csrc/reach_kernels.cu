@@ -66,7 +66,7 @@ __device__ void small_scalar(PZ<1>& z, double center, u64 k0, double c0, u64 k1,
     if (norm1(&c0) > thr_sq) { z.keys[n] = k0; z.coef[n] = c0; abss = __dadd_ru(abss, fabs(c0)); n++; } else ind = __dadd_ru(ind, fabs(c0));
     if (norm1(&c1) > thr_sq) { z.keys[n] = k1; z.coef[n] = c1; abss = __dadd_ru(abss, fabs(c1)); n++; } else ind = __dadd_ru(ind, fabs(c1));
     ind = __dmul_ru(ind, 1.0 + 0x1p-40);   // a dropped coefficient built from device libm values may be an ulp below the host's
-    z.n = n; z.divM = FastDiv::magic(n); z.center[0] = center; z.ind[0][0] = ind; z.ind[1][0] = ind; z.abss[0] = abss;
+    z.n = n; z.divM = FastDiv::magic(n); z.center[0] = center; z.ind[0][0] = ind; z.ind[1][0] = ind; z.abss[0] = abss; z.ormask = k0 | k1;
 }
 template <int D>
 __device__ void export_small(SmallRec& r, const PZ<D>& z) {
@@ -139,10 +139,10 @@ __device__ void rotation_from_cos_sin(int i, double cos_center, double cos_c0, d
                 nr++;
             }
         }
-        R.n = nr; R.divM = FastDiv::magic(nr);
+        R.n = nr; R.divM = FastDiv::magic(nr); R.ormask = key_k(i) | key_cosqe(i) | key_sinqe(i);
         for (int c = 0; c < 9; c++) { R.center[c] = cen[c]; R.ind[0][c] = ind[c]; R.ind[1][c] = ind[c]; R.abss[c] = abss[c]; }
         // R_t = R.transpose()
-        Rt.n = nr; Rt.divM = FastDiv::magic(nr);
+        Rt.n = nr; Rt.divM = FastDiv::magic(nr); Rt.ormask = R.ormask;
         for (int r = 0; r < 3; r++)
             for (int c = 0; c < 3; c++) {
                 const int src = r + 3 * c, dstp = c + 3 * r;
@@ -387,7 +387,7 @@ size_t arena_bytes(int mcap, int ncap, int groups) {
 
 template <int D>
 __device__ __noinline__ char* carve(PZ<D>& z, char* p, int cap) {
-    z.cap = cap; z.n = 0; z.divM = FastDiv::magic(0);
+    z.cap = cap; z.n = 0; z.divM = FastDiv::magic(0); z.ormask = 0;
     z.keys = (u64*)p; p += (size_t)cap * 8;
     z.coef = (double*)p; p += (size_t)cap * 8 * D;
 #ifdef ARMOUR_ARENA_CANARY
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
         const size_t group_smem = Scratch::smem_bytes(scap, tcap, NT / 32);
         for (int k = 0; k < GROUPS; k++) {
             SS[k].bind(smem_raw + COLD_SMEM + (size_t)k * group_smem, scap, tcap, g + (size_t)k * Scratch::gmem_bytes(ncap), ncap);
-            SS[k].thr = tb.thr; SS[k].thr_sq = thr_sq; SS[k].gerr = tb.err;
+            SS[k].thr = tb.thr; SS[k].thr_sq = thr_sq; SS[k].gerr = tb.err; SS[k].no_structured = tb.no_structured;
         }
     }
     __syncthreads();
@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
             if (tb.mode == 1) {
                 make_poly_zono_armtd(tb, prob, s, i, Z.c.R[i], Z.c.Rt[i], Z.c.cosq[i], Z.c.sinq[i], S.thr_sq);
                 PZ<1>* unused[3] = {&Z.c.qd[i], &Z.c.qda[i], &Z.c.qdda[i]};
-                for (PZ<1>* z : unused) { z->n = 0; z->divM = FastDiv::magic(0); z->center[0] = 0; z->ind[0][0] = 0; z->ind[1][0] = 0; z->abss[0] = 0; }
+                for (PZ<1>* z : unused) { z->n = 0; z->divM = FastDiv::magic(0); z->ormask = 0; z->center[0] = 0; z->ind[0][0] = 0; z->ind[1][0] = 0; z->abss[0] = 0; }
             }
             else make_poly_zono_joint(tb, prob, s, i, Z.c.R[i], Z.c.Rt[i], Z.c.qd[i], Z.c.qda[i], Z.c.qdda[i], Z.c.cosq[i], Z.c.sinq[i], S.thr_sq);
             if (tb.traj) {
@@ -672,15 +672,15 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
                 }
                 else ind[j] = fabs(g);
             }
-            L0.n = n; L0.divM = FastDiv::magic(n);
+            L0.n = n; L0.divM = FastDiv::magic(n); L0.ormask = gk[0] | gk[1] | gk[2];
             for (int c = 0; c < 3; c++) { L0.center[c] = rm.link_c[i][c]; L0.ind[0][c] = ind[c]; L0.ind[1][c] = ind[c]; L0.abss[c] = abss[c]; }
         }
         if (threadIdx.x == NJ) {   // R(NUM_JOINTS) = identity; initial RNEA state (KPR/Dynamics.cu:87-99) in set 1 (= "before joint 0")
             PZ<9>& R = Z.c.R[NJ];
-            R.n = 0; R.divM = FastDiv::magic(0);
+            R.n = 0; R.divM = FastDiv::magic(0); R.ormask = 0;
             for (int c = 0; c < 9; c++) { R.center[c] = rm.R0[NJ][c]; R.ind[0][c] = 0; R.ind[1][c] = 0; R.abss[c] = 0; }
             PZ<3>* init[6] = {&Z.h.W[1], &Z.h.WD[1], &Z.h.WA[1], &Z.h.LA[1], &Z.h.Fv, &Z.h.Nv};
-            for (PZ<3>* z : init) { z->n = 0; z->divM = FastDiv::magic(0); for (int c = 0; c < 3; c++) { z->center[c] = 0; z->ind[0][c] = 0; z->ind[1][c] = 0; z->abss[c] = 0; } }
+            for (PZ<3>* z : init) { z->n = 0; z->divM = FastDiv::magic(0); z->ormask = 0; for (int c = 0; c < 3; c++) { z->center[c] = 0; z->ind[0][c] = 0; z->ind[1][c] = 0; z->abss[c] = 0; } }
             Z.h.LA[1].center[2] = rm.gravity;
         }
         __syncthreads();
@@ -787,7 +787,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
                 }
             }
         }
-        if (threadIdx.x == 0) next_work = (int)gridDim.x + atomicAdd(tb.err + 1, 1);
+        if (threadIdx.x == 0) next_work = tb.static_stride ? work + (int)gridDim.x : (int)gridDim.x + atomicAdd(tb.err + 1, 1);
         __syncthreads();
     }
 #ifdef ARMOUR_ARENA_CANARY
@@ -807,6 +807,8 @@ template <int D>
 __device__ void load_flat(PZ<D>& z, const FlatPZ& f) {
     if (threadIdx.x == 0) {
         z.n = f.n; z.divM = FastDiv::magic(f.n); z.cap = f.cap; z.keys = f.keys; z.coef = f.coef;
+        z.ormask = 0;
+        for (int i = 0; i < f.n; i++) z.ormask |= f.keys[i];
         for (int c = 0; c < D; c++) {
             z.center[c] = f.center[c]; z.ind[0][c] = f.ind[c]; z.ind[1][c] = f.ind[c];
             double s = 0.0;
@@ -883,7 +885,9 @@ static ReachVariant pick_reach_kernel(int nt, int minb, int groups) {
     }
     if (nt == 128) {
         if (minb >= 6) return {reach_build_kernel<128, 6, 1, true>, 128, 4, 1, true};
-        if (minb >= 4) return {reach_build_kernel<128, 4, 1, false>, 128, 4, 1, false};
+        if (minb == 5) return {reach_build_kernel<128, 5, 1, false>, 128, 4, 1, false};
+        if (minb == 4) return {reach_build_kernel<128, 4, 1, false>, 128, 4, 1, false};
+        if (minb == 3) return {reach_build_kernel<128, 3, 1, false>, 128, 4, 1, false};
         return {reach_build_kernel<128, 2, 1, false>, 128, 4, 1, false};
     }
     if (nt == 512) return {reach_build_kernel<512, 1, 1, false>, 512, 16, 1, false};

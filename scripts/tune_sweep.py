@@ -18,14 +18,10 @@ sys.path[:0] = [os.path.join(ROOT, "armour-dev_b200"), os.path.join(ROOT, "tests
 CONFIGS = [
     # (threads, CTAs/SM bound, scap, tcap, mcap)
     (128, 4, 1408, 300, 1024),   # round-1 sweep shape (reference digest)
-    (128, 4, 1408, 300, 512),
-    (64, 8, 768, 192, 512),
-    (64, 8, 1024, 128, 512),
-    (64, 12, 512, 96, 512),
-    (32, 12, 512, 128, 512),
-    (32, 16, 384, 64, 512),
-    (32, 16, 256, 64, 512),
-    (32, 24, 256, 32, 512),
+    (128, 5, 1408, 300, 1024),
+    (128, 5, 1024, 256, 1024),
+    (128, 3, 1408, 300, 1024),
+    (128, 3, 2048, 512, 1024),
 ]
 
 

@@ -456,3 +456,35 @@ def test_arena_guard_words_stay_intact(gpu_lib):
     assert len(single) == 2 and all(int(s[1]) >= 16 * 100 for s in single), r.stdout      # > 100 guard words per CTA, 16 CTAs
     assert single[0][2] == single[1][2]                                                  # the retried build gives the same numbers
     assert int([l.split()[1] for l in r.stdout.splitlines() if l.startswith("BATCH")][0]) >= 100
+
+
+@pytest.mark.parametrize("shape_a,shape_b,small_is_a,small_vars,n_large", [
+    ((3, 3), (3, 1), True, (5, 33, 40), 200),      # R_i^T * state: k_5, cosqe_5, sinqe_5 against a vector without joint-5 variables
+    ((3, 3), (3, 1), True, (2, 30), 1),            # two surviving monomials, one-monomial vector
+    ((3, 3), (3, 3), False, (6, 34, 41), 60),      # FK_R * R_i
+    ((3, 3), (3, 1), False, (7, 14, 21), 55),      # FK_R * link box: generator symbols qde_0, qdae_0, qddae_0
+    ((1, 1), (1, 1), True, (3,), 300),
+    ((3, 3), (3, 1), True, (0, 28, 35), 340),      # lowest variables of every group: the shifted runs interleave most
+])
+def test_structured_product_equals_the_oracle(shape_a, shape_b, small_is_a, small_vars, n_large, gpu_lib):
+    """Products whose operands share no variable and whose small operand has <= 3 single-variable monomials take the sort-free
+    path of the engine (pz_mul_structured: closed-form positions from group bounds); results must equal the reference
+    algorithm's sort + merge + threshold exactly like every other product."""
+    rng = np.random.default_rng(zlib.crc32(repr((shape_a, shape_b, small_is_a, small_vars, n_large)).encode()))
+    p = ab.Planner(T=2)
+    shift = lambda v: 2 * v if v < 7 else (14 + (v - 7)) if v < 28 else 35 + 2 * (v - 28)
+    for trial in range(3):
+        ss, ls = (shape_a, shape_b) if small_is_a else (shape_b, shape_a)
+        dim = ss[0] * ss[1]
+        keys = np.array(sorted(1 << shift(v) for v in small_vars), dtype=np.uint64)
+        mag = 10.0 ** rng.uniform(-4, 0, size=(len(keys), 1))
+        small = dict(rows=ss[0], cols=ss[1], keys=keys, coeffs=rng.standard_normal((len(keys), dim)) * mag, center=rng.standard_normal(dim),
+                     independent=np.abs(rng.standard_normal(dim)) * 1e-2)
+        large = random_pz(rng, ls[0], ls[1], n_large, one_bit=[v for v in range(7, 28) if v not in small_vars])
+        bad = np.zeros(len(large["keys"]), dtype=bool)          # drop monomials that use the small operand's variables
+        for v in small_vars:
+            bad |= ((large["keys"] >> np.uint64(shift(v))) & np.uint64(3 if (v < 7 or v >= 28) else 1)) != 0
+        large["keys"], large["coeffs"] = large["keys"][~bad], large["coeffs"][~bad]
+        a, b = (small, large) if small_is_a else (large, small)
+        assert_pz_equal(_oracle.pz_binary("mul", a, b), p.pz_binary("mul", a, b), "structured trial %d" % trial)
+    p.close()
