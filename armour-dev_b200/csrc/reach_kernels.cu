@@ -428,6 +428,22 @@ __device__ __forceinline__ bool group_ready(Scratch& S, volatile int* flag, int 
     return r;
 }
 
+// Opt-in experiment (-DARMOUR_SHARED_FK=1), measured SLOWER and therefore off: forward kinematics is a chain of its own (FK_R,
+// FK_T -> link PZs) that nothing else in the interval reads, so either group could advance it whenever it would otherwise wait
+// for the other one (by default group 0 runs it in its waits and at its tail; group 0 is busy 99 % of the kernel, group 1 85 %).
+// One joint at a time: a group claims the chain (fk_lock), runs the joint with its own temporaries, publishes fk_next and
+// releases.  Parity identical (51 GPU tests), but 0.69-0.73 ms against 0.655-0.695 ms per plan: a joint taken by group 1 in a
+// wait delays the force computations group 0 is about to need, and the chain itself stays sequential whoever runs it.
+#ifndef ARMOUR_SHARED_FK
+#define ARMOUR_SHARED_FK 0
+#endif
+template <int NT>
+__device__ __noinline__ bool try_fk(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0, volatile int* fk_next, int* fk_lock);
+template <int NT>
+__device__ __forceinline__ void wait_or_fk(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0, volatile int* flag, int needed, volatile int* fk_next, int* fk_lock);
+template <int NT>
+__device__ __forceinline__ void drain_fk(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0, volatile int* fk_next, int* fk_lock);
+
 // ---- the per-interval program, in four pieces --------------------------------------------------------------
 // RNEA forward recursion, joint chain (KPR/Dynamics.cu:102-137): state `p` (after joint i-1) -> state `c`
 template <int NT>
@@ -499,6 +515,52 @@ template <int NT>
 __device__ void forward_kinematics(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0) {
     #pragma unroll 1
     for (int i = 0; i < NJ; i++) fk_joint<NT>(S, Z, T, tb, rec0, i);
+}
+template <int NT>
+__device__ __noinline__ bool try_fk(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0, volatile int* fk_next, int* fk_lock) {
+    if (gtid<NT>() == 0) {
+        int i = -1;
+        if (*fk_next < NJ && atomicCAS(fk_lock, 0, 1) == 0) {
+            __threadfence_block();
+            i = *fk_next;
+            if (i >= NJ) { i = -1; atomicExch(fk_lock, 0); }
+        }
+        S.iscan[17] = i;
+    }
+    gsync<NT>();
+    const int i = S.iscan[17];
+    gsync<NT>();
+    if (i < 0) return false;
+    fk_joint<NT>(S, Z, T, tb, rec0, i);
+    if (gtid<NT>() == 0) { __threadfence_block(); *fk_next = i + 1; __threadfence_block(); atomicExch(fk_lock, 0); }
+    return true;
+}
+// wait for a hand-off counter, advancing the forward kinematics while it is not there yet
+template <int NT>
+__device__ __forceinline__ void wait_or_fk(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0, volatile int* flag, int needed, volatile int* fk_next, int* fk_lock) {
+    while (!group_ready<NT>(S, flag, needed)) {
+        if (!try_fk<NT>(S, Z, T, tb, rec0, fk_next, fk_lock)) { group_wait<NT>(S, flag, needed); return; }
+    }
+}
+// end of a group's program: the chain must be complete before the interval's results are used
+template <int NT>
+__device__ __forceinline__ void drain_fk(Scratch& S, Slots& Z, PZ<3>* T, const Tables& tb, size_t rec0, volatile int* fk_next, int* fk_lock) {
+    for (;;) {
+        if (try_fk<NT>(S, Z, T, tb, rec0, fk_next, fk_lock)) continue;
+        if (gtid<NT>() == 0) {   // nothing claimed: finished, or the other group is inside a joint — wait for it to release
+            const long long t0 = clock64();
+            bool lost = false;
+            while (*fk_next < NJ && *(volatile int*)fk_lock != 0) {
+                if (clock64() - t0 > (1ll << 32)) { set_err(S, ERR_SYNC); lost = true; break; }
+            }
+            __threadfence_block();
+            S.iscan[17] = (*fk_next >= NJ || lost) ? 1 : 0;
+        }
+        gsync<NT>();
+        const bool done = S.iscan[17] != 0;
+        gsync<NT>();
+        if (done) return;
+    }
 }
 // RNEA reverse recursion for joint i (KPR/Dynamics.cu:161-180)
 template <int NT>
@@ -593,7 +655,8 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
     __shared__ Scratch SS[GROUPS];
     __shared__ HotSlots ZH;
     __shared__ PZ<3> TT[GROUPS][5];                        // temporaries, one set per thread group
-    __shared__ volatile int sig_la, sig_state, sig_force, sig_side, sig_u;
+    __shared__ volatile int sig_la, sig_state, sig_force, sig_side, sig_u, fk_next_s;
+    __shared__ int fk_lock_s;
     const RobotModel& rm = c_robot;
     const int group = threadIdx.x / NT;
     Scratch& S = SS[group];
@@ -639,7 +702,7 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
     for (int work = blockIdx.x; work < n_work; work = next_work) {
         const int prob = work / tb.T, s = work - prob * tb.T;
         const size_t rec0 = ((size_t)prob * tb.T + s) * NJ;
-        if (threadIdx.x == 0) { sig_la = 0; sig_state = 0; sig_force = 0; sig_side = 0; sig_u = 0; }
+        if (threadIdx.x == 0) { sig_la = 0; sig_state = 0; sig_force = 0; sig_side = 0; sig_u = 0; fk_next_s = 0; fk_lock_s = 0; }
         __syncthreads();
         // ---- stage A: joint reach sets (one thread per joint; tiny scalar work) -------------------
         if (threadIdx.x < NJ) {
@@ -710,6 +773,27 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
         }
         else if (group == 0) {
             // angular recurrence, then the moment recursion; forward-kinematics joints fill the time spent waiting
+#if ARMOUR_SHARED_FK
+            #pragma unroll 1
+            for (int i = 0; i < NJ; i++) {
+                // set i&1 still holds the state of joint i-2, read by group 1 until its linear_acc step of joint i-1 is done
+                if (i >= 1) wait_or_fk<NT>(S, Z, T, tb, rec0, &sig_la, i, &fk_next_s, &fk_lock_s);
+                PIECE(pc_wait);
+                angular_joint<NT>(S, Z, T, i, (i + 1) & 1, i & 1);
+                group_signal<NT>(&sig_state, i + 1);
+                PIECE(pc_chain);
+            }
+            #pragma unroll 1
+            for (int i = NJ - 1; i >= 0; i--) {
+                wait_or_fk<NT>(S, Z, T, tb, rec0, &sig_side, NJ - i, &fk_next_s, &fk_lock_s);
+                PIECE(pc_wait);
+                moment_joint<NT>(S, Z, T, i);
+                group_signal<NT>(&sig_u, NJ - i);          // u_i is final: group 1 exports it (stage M) beside the next joint
+                PIECE(pc_back);
+            }
+            drain_fk<NT>(S, Z, T, tb, rec0, &fk_next_s, &fk_lock_s);
+            PIECE(pc_fk);
+#else
             int fk_next = 0;
             #pragma unroll 1
             for (int i = 0; i < NJ; i++) {
@@ -733,17 +817,26 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
                 PIECE(pc_back);
             }
             while (fk_next < NJ) { fk_joint<NT>(S, Z, T, tb, rec0, fk_next++); PIECE(pc_fk); }
+#endif
         }
         else {
             PZ<3>& LA = Z.h.LA[1];   // group 1's private linear_acc, initialised with gravity in stage A
             #pragma unroll 1
             for (int i = 0; i < NJ; i++) {
+#if ARMOUR_SHARED_FK
+                wait_or_fk<NT>(S, Z, T, tb, rec0, &sig_state, i, &fk_next_s, &fk_lock_s);          // state of joint i-1 (the initial state for i = 0)
+#else
                 group_wait<NT>(S, &sig_state, i);          // state of joint i-1 (the initial state for i = 0)
+#endif
                 PIECE(pc_wait);
                 linacc_joint<NT>(S, Z, T, i, (i + 1) & 1, LA);
                 group_signal<NT>(&sig_la, i + 1);
                 PIECE(pc_chain);
+#if ARMOUR_SHARED_FK
+                wait_or_fk<NT>(S, Z, T, tb, rec0, &sig_state, i + 1, &fk_next_s, &fk_lock_s);
+#else
                 group_wait<NT>(S, &sig_state, i + 1);
+#endif
                 PIECE(pc_wait);
                 force_joint<NT>(S, Z, T, tb, i, i & 1, LA);
                 group_signal<NT>(&sig_force, i + 1);
@@ -758,9 +851,16 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
             // stage M exports (disturbance radius, reduce(), torque table) in the time this group would idle
             #pragma unroll 1
             for (int i = NJ - 1; i >= 0; i--) {
+#if ARMOUR_SHARED_FK
+                wait_or_fk<NT>(S, Z, T, tb, rec0, &sig_u, NJ - i, &fk_next_s, &fk_lock_s);
+#else
                 group_wait<NT>(S, &sig_u, NJ - i);
+#endif
                 export_torque<NT>(S, tb, rec0 + i, Z.c.u[i]);
             }
+#if ARMOUR_SHARED_FK
+            drain_fk<NT>(S, Z, T, tb, rec0, &fk_next_s, &fk_lock_s);
+#endif
         }
 #ifdef ARMOUR_PHASE_TIMING
         if (blockIdx.x == 64 && gtid<NT>() == 0)
