@@ -423,9 +423,12 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     h->P = cfg.batch; h->T = cfg.num_time_steps; h->max_obs = cfg.max_obstacles;
     h->mcap = cfg.max_monomials; h->ncap = std::min(cfg.max_entries, 65534) & ~1; h->nt = cfg.threads_per_cta;
     // register budget: one plan is latency-bound (1 CTA/SM, all registers); a batch wants more resident CTAs
-    // (measured, scripts/tune_batch.py: 128 threads x 4 CTAs/SM with 1408-entry shared sort buffers is the fastest sweep shape)
+    // (measured, scripts/tune_sweep.py: 128 threads per interval with 1408-entry shared sort buffers is the fastest sweep shape;
+    // the narrow shapes — 64 / 32 threads per interval, 8-24 CTAs per SM — run 12 % / 48 % slower)
     const int nt = cfg.threads_per_cta;
-    h->minb = nt == 32 ? 16 : nt == 64 ? 8 : cfg.batch > 1 ? (nt == 128 ? 4 : 2) : 1;
+    // sweep shape: 128 threads x 3 CTAs per SM (168 registers, 12 resident warps): measured 2 % above 4 CTAs at 128 registers and
+    // 15 % above 2; the SM's throughput saturates near 12 warps (profiles/README.md, round-2 experiments)
+    h->minb = nt == 32 ? 16 : nt == 64 ? 8 : cfg.batch > 1 ? (nt == 128 ? 3 : 2) : 1;
     if (cfg.batch > 1 && nt == 128) { h->scap = 1408; h->tcap = 300; }
     if (nt == 64) { h->scap = 768; h->tcap = 192; }
     if (nt == 32) { h->scap = 512; h->tcap = 128; }

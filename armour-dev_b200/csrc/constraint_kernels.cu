@@ -201,8 +201,17 @@ __device__ __forceinline__ double slice_term(double coef, u64 key, const double*
 // mbarrier) issued before anything else, so the table streams in while the block slices its two polynomial zonotopes at k.
 constexpr int EVAL_NT = 128;
 constexpr int EVAL_MAX_OBS = 64;      // shared-memory slab of the half-space table: 64 x 1440 B = 90 KB
-constexpr int EVAL_UCHUNK = 16;       // torque monomials staged per pass (x 8 outputs)
 constexpr int EVAL_LCHUNK = 5;        // link monomials staged per pass (x 24 outputs)
+// torque monomials staged per pass (x 8 outputs): as many as fit beside the table slab while seven blocks stay resident per SM
+// (7 x (static + dynamic + 1 KB) <= 228 KB), between 16 and the table capacity
+__host__ __device__ inline int eval_uchunk(int n_obs, int ucap) {
+    const long budget = 32073 - 256 - (long)n_obs * COMB * 40 - 24 * EVAL_LCHUNK * 8;
+    long u = budget / 64;
+    u = u < 16 ? 16 : u;
+    u = u > ucap ? ucap : u;
+    u = u < 1 ? 1 : u;
+    return (int)(u > 16 ? (u & ~15L) : u);
+}
 struct XArg { double x[NF]; };        // k passed by value: no host-to-device copy on the per-iteration path
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -230,9 +239,9 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
 
 // dynamic shared memory of constraint_eval_kernel: the table slab, then a staging area used first for slice terms and then
 // for the block's output rows
-__host__ __device__ inline size_t eval_smem_bytes(int n_obs) {
+__host__ __device__ inline size_t eval_smem_bytes(int n_obs, int uchunk) {
     const size_t slab = (size_t)n_obs * COMB * 40;
-    const size_t terms = (size_t)(8 * EVAL_UCHUNK + 24 * EVAL_LCHUNK) * 8;
+    const size_t terms = (size_t)(8 * uchunk + 24 * EVAL_LCHUNK) * 8;
     const size_t rows = (size_t)n_obs * 8 * 8;
     return slab + (terms > rows ? terms : rows);
 }
@@ -244,8 +253,8 @@ __host__ __device__ inline size_t eval_smem_bytes(int n_obs) {
 // done_counter / done_flag: when done_flag != nullptr the last block to finish stores `seq` there (mapped pinned host memory)
 // after a system-wide fence — the host polls that word instead of synchronising the stream.
 __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, int prob, XArg xarg, double* __restrict__ g, double* __restrict__ jac,
-                                                                     double* __restrict__ link_center_out, int what, unsigned* done_counter,
-                                                                     volatile unsigned long long* done_flag, unsigned long long seq) {
+                                                                     double* __restrict__ link_center_out, int what, int uchunk, int lchunk,
+                                                                     unsigned* done_counter, volatile unsigned long long* done_flag, unsigned long long seq) {
     extern __shared__ __align__(128) unsigned char eval_smem[];
     __shared__ __align__(8) unsigned long long mbar_storage;
     __shared__ double lc[3], ldk[NF][3];
@@ -301,35 +310,45 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
             bulk_g2s(smem_u32(sdl), tb.delta + base, (unsigned)n_planes * 8u, mbar);
         }
         // ---- slices (PZsparse::slice, KPR/PZsparse.cu:404-555): terms in parallel, sums sequential in key order ----
+        const int UCAP = tb.ucap, LCAP = tb.lcap;
+        // operands of this thread's first torque / link term, requested BEFORE the monomial counts arrive: the tables are
+        // allocated to capacity, so any row below it is readable, and the dependent round trip (count, then operands) becomes one
+        const int um0 = tid >> 3, lm0 = tid / 24, lw0 = tid - lm0 * 24;
+        double uc0 = 0.0, lc0 = 0.0;
+        u64 uk0 = 0, lk0 = 0;
+        if (tb.mode == 0 && um0 < UCAP) { uc0 = tb.u_coef[rec * UCAP + um0]; uk0 = tb.u_keys[rec * UCAP + um0]; }
+        if (lm0 < LCAP) { lc0 = tb.l_coef[(rec * 3 + lw0 % 3) * LCAP + lm0]; lk0 = tb.l_keys[rec * LCAP + lm0]; }
         const int un = tb.mode == 0 ? tb.u_n[rec] : 0;
         const int ln = tb.l_n[rec];
-        const int UCAP = tb.ucap, LCAP = tb.lcap;
-        double* uterm = stage;                             // [8][EVAL_UCHUNK]
-        double* lterm = stage + 8 * EVAL_UCHUNK;           // [24][EVAL_LCHUNK]
+        double* uterm = stage;                      // [8][uchunk]
+        double* lterm = stage + 8 * uchunk;         // [24][lchunk]
         // threads 0..7: torque value + 7 derivatives; threads 32..55: link value (3) + derivatives (21)
         double acc = 0.0;
         const bool sum_u = tid < 8, sum_l = tid >= 32 && tid < 56;
         const int lw = tid - 32;
         if (sum_u && tid == 0 && tb.mode == 0) acc = tb.u_center[rec];
         if (sum_l && lw < 3) acc = tb.l_center[rec * 3 + lw];
-        const int u_passes = (un + EVAL_UCHUNK - 1) / EVAL_UCHUNK, l_passes = (ln + EVAL_LCHUNK - 1) / EVAL_LCHUNK;
+        const int u_passes = (un + uchunk - 1) / uchunk, l_passes = (ln + lchunk - 1) / lchunk;
         const int passes = u_passes > l_passes ? u_passes : l_passes;
         for (int ps = 0; ps < passes; ps++) {
-            const int ub = ps * EVAL_UCHUNK, uc = min(EVAL_UCHUNK, un - ub);
-            const int lb = ps * EVAL_LCHUNK, lcn = min(EVAL_LCHUNK, ln - lb);
-            // 8 * 16 torque terms on threads 0..127, 24 * 5 link terms on threads 0..119: two terms per thread and pass
-            if (tid < uc * 8 && (want_j || (tid & 7) == 0) && (want_g || (tid & 7) != 0)) {
-                const int m = tid >> 3, w = tid & 7;
-                uterm[w * EVAL_UCHUNK + m] = slice_term(tb.u_coef[rec * UCAP + ub + m], tb.u_keys[rec * UCAP + ub + m], x, w - 1);
+            const int ub = ps * uchunk, uc = min(uchunk, un - ub);
+            const int lb = ps * lchunk, lcn = min(lchunk, ln - lb);
+            for (int e = tid; e < uc * 8; e += EVAL_NT) {
+                const int m = e >> 3, w = e & 7;
+                if (!((want_j || w == 0) && (want_g || w != 0))) continue;
+                const bool pre = ps == 0 && e == tid;
+                uterm[w * uchunk + m] = slice_term(pre ? uc0 : tb.u_coef[rec * UCAP + ub + m], pre ? uk0 : tb.u_keys[rec * UCAP + ub + m], x, w - 1);
             }
-            if (tid < lcn * 24 && (want_j || (tid % 24) < 3)) {   // the link centre (value) is needed for both g and the arg-max of the Jacobian rows
-                const int m = tid / 24, w = tid - m * 24;
+            for (int e = tid; e < lcn * 24; e += EVAL_NT) {
+                const int m = e / 24, w = e - m * 24;
                 const int c = w % 3, which = w / 3;   // which 0: value, 1..7: d/dk_{which-1}
-                lterm[w * EVAL_LCHUNK + m] = slice_term(tb.l_coef[(rec * 3 + c) * LCAP + lb + m], tb.l_keys[rec * LCAP + lb + m], x, which - 1);
+                if (!(want_j || w < 3)) continue;     // the link centre (value) is needed for both g and the arg-max of the Jacobian rows
+                const bool pre = ps == 0 && e == tid;
+                lterm[w * lchunk + m] = slice_term(pre ? lc0 : tb.l_coef[(rec * 3 + c) * LCAP + lb + m], pre ? lk0 : tb.l_keys[rec * LCAP + lb + m], x, which - 1);
             }
             __syncthreads();
-            if (sum_u) for (int m = 0; m < uc; m++) acc = acc + uterm[tid * EVAL_UCHUNK + m];
-            if (sum_l) for (int m = 0; m < lcn; m++) acc = acc + lterm[lw * EVAL_LCHUNK + m];
+            if (sum_u) for (int m = 0; m < uc; m++) acc = acc + uterm[tid * uchunk + m];
+            if (sum_l) for (int m = 0; m < lcn; m++) acc = acc + lterm[lw * lchunk + m];
             __syncthreads();
         }
         if (sum_u && tb.mode == 0) {
@@ -437,19 +456,21 @@ cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* x_h
     if (tb.n_obs > EVAL_MAX_OBS) return cudaErrorInvalidValue;
     XArg xa;
     for (int i = 0; i < NF; i++) xa.x[i] = x_host[i];
-    size_t smem = eval_smem_bytes(tb.n_obs);
-    if (blocks_per_sm > 0) smem = std::max(smem, std::min((size_t)(227 * 1024) / blocks_per_sm - 1280, eval_smem_bytes(EVAL_MAX_OBS)));
+    const int uchunk = eval_uchunk(tb.n_obs, tb.ucap);
+    const size_t smem_max = eval_smem_bytes(EVAL_MAX_OBS, 128);
+    size_t smem = eval_smem_bytes(tb.n_obs, uchunk);
+    if (blocks_per_sm > 0) smem = std::max(smem, std::min((size_t)(227 * 1024) / blocks_per_sm - 1280, smem_max));
     if (smem > 48 * 1024) {   // opt in to a large dynamic shared-memory request, once per device
         static bool opted_in[64] = {};
         int dev = 0;
         cudaGetDevice(&dev);
         if (dev < 0 || dev >= 64 || !opted_in[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(constraint_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes(EVAL_MAX_OBS));
+            cudaError_t e = cudaFuncSetAttribute(constraint_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
             if (e != cudaSuccess) return e;
             if (dev >= 0 && dev < 64) opted_in[dev] = true;
         }
     }
-    constraint_eval_kernel<<<tb.T * NJ + 1, EVAL_NT, smem, stream>>>(tb, prob, xa, g, jac, link_center, what, done_counter, done_flag, seq);
+    constraint_eval_kernel<<<tb.T * NJ + 1, EVAL_NT, smem, stream>>>(tb, prob, xa, g, jac, link_center, what, uchunk, EVAL_LCHUNK, done_counter, done_flag, seq);
     return cudaGetLastError();
 }
 

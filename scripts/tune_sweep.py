@@ -18,10 +18,11 @@ sys.path[:0] = [os.path.join(ROOT, "armour-dev_b200"), os.path.join(ROOT, "tests
 CONFIGS = [
     # (threads, CTAs/SM bound, scap, tcap, mcap)
     (128, 4, 1408, 300, 1024),   # round-1 sweep shape (reference digest)
-    (128, 5, 1408, 300, 1024),
-    (128, 5, 1024, 256, 1024),
     (128, 3, 1408, 300, 1024),
-    (128, 3, 2048, 512, 1024),
+    (128, 2, 1408, 300, 1024),
+    (128, 3, 1664, 384, 1024),
+    (128, 3, 1152, 256, 1024),
+    (128, 3, 1408, 300, 512),
 ]
 
 
