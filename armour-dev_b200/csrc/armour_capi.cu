@@ -426,9 +426,10 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     // (measured, scripts/tune_sweep.py: 128 threads per interval with 1408-entry shared sort buffers is the fastest sweep shape;
     // the narrow shapes — 64 / 32 threads per interval, 8-24 CTAs per SM — run 12 % / 48 % slower)
     const int nt = cfg.threads_per_cta;
-    // sweep shape: 128 threads x 3 CTAs per SM (168 registers, 12 resident warps): measured 2 % above 4 CTAs at 128 registers and
-    // 15 % above 2; the SM's throughput saturates near 12 warps (profiles/README.md, round-2 experiments)
-    h->minb = nt == 32 ? 16 : nt == 64 ? 8 : cfg.batch > 1 ? (nt == 128 ? 3 : 2) : 1;
+    // sweep shape: 128 threads x 4 CTAs per SM (128 registers, 16 resident warps).  With the round-1 operation code 3 CTAs at 168
+    // registers were 2 % ahead (the sweep is bound by instruction fetch, not by resident warps); with the unified 3-vector
+    // operation 4 CTAs lead by 4.5 % (profiles/README.md, round-2 experiments)
+    h->minb = nt == 32 ? 16 : nt == 64 ? 8 : cfg.batch > 1 ? (nt == 128 ? 4 : 2) : 1;
     if (cfg.batch > 1 && nt == 128) { h->scap = 1408; h->tcap = 300; }
     if (nt == 64) { h->scap = 768; h->tcap = 192; }
     if (nt == 32) { h->scap = 512; h->tcap = 128; }

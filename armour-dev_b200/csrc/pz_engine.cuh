@@ -132,9 +132,22 @@ template <bool BIG> struct Buf {
     static __device__ __forceinline__ u16* idx(const Scratch& S, int b) { return BIG ? S.gidx[b] : S.sidx(b); }
 };
 
+// unified 3-vector operation (defined near the end of this file); the named operations below forward to it
+#ifndef ARMOUR_UNIFIED_OP3
+#define ARMOUR_UNIFIED_OP3 1
+#endif
+template <int NT> __device__ __forceinline__ void op3_mul93(Scratch& S, PZ<3>& dst, const PZ<9>& A, const PZ<3>& B);
+template <int NT> __device__ __forceinline__ void op3_add(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B);
+template <int NT> __device__ __forceinline__ void op3_add_one_dim(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<1>& s, int row);
+template <int NT> __device__ __forceinline__ void op3_cross(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B);
+template <int NT> __device__ __forceinline__ void op3_cross_const(Scratch& S, PZ<3>& dst, const PZ<3>& Z, const double* kvec, bool const_first);
+template <int NT> __device__ __forceinline__ void op3_const_left(Scratch& S, PZ<3>& dst, const double* Mc, const double* Mi0, const double* Mi1, bool scalar, const PZ<3>& V);
+template <int NT> __device__ __forceinline__ void op3_const_right(Scratch& S, PZ<3>& dst, const PZ<9>& R, const double* pvec);
+
 // exact n / d for n, d < 2^16 with one multiply: q = (n * M) >> 32, M = floor((2^32 - 1) / d) + 1
 struct FastDiv {
     u64 M;
+    // (a shared non-inlined copy of this 32-bit division was measured slower: the call's register traffic sits in every operation's epilogue)
     __device__ __forceinline__ static u64 magic(int d) { return (u64)(0xFFFFFFFFu / (unsigned)(d > 0 ? d : 1)) + 1; }
     __device__ __forceinline__ explicit FastDiv(u64 M_) : M(M_) {}
     __device__ __forceinline__ int div(int n) const { return (int)(((u64)(unsigned)n * M) >> 32); }
@@ -271,6 +284,7 @@ __device__ __forceinline__ int block_scan_sum(Scratch& S, int cnt, const double 
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    // (a plain xor-butterfly per value is a quarter of the code but three times the shuffles: measured 5 % slower in the sweep, 8 % on one plan)
     double v[VP];
 #pragma unroll
     for (int k = 0; k < VP; k++) v[k] = k < V ? red[k] : 0.0;
@@ -881,8 +895,29 @@ __device__ __forceinline__ bool structured_ok(const Scratch& S, const PZ<DSm>& S
 #ifndef ARMOUR_STRUCTURED_PRODUCTS
 #define ARMOUR_STRUCTURED_PRODUCTS 1
 #endif
+// R * v: the sort-free structured path when it applies (one-plan shapes), else the unified 3-vector operation; one copy per kernel
+template <int NT>
+__device__ __noinline__ void pz_mul93(Scratch& S, PZ<3>& dst, const PZ<9>& A, const PZ<3>& B) {
+    if (ARMOUR_STRUCTURED_PRODUCTS && NT >= 256 && !S.no_structured) {
+        if (structured_ok<9, 3>(S, A, B)) { pz_mul_structured<NT, 9, 3, 3, true>(S, dst, A, B, A.n, B.n); return; }
+        if (structured_ok<3, 9>(S, B, A)) { pz_mul_structured<NT, 9, 3, 3, false>(S, dst, A, B, B.n, A.n); return; }
+    }
+    op3_mul93<NT>(S, dst, A, B);
+}
+template <int NT, int DA, int DB, int DO, int CP>
+__device__ __noinline__ void pz_mul_cp(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, const PZ<DB>& B);
 template <int NT, int DA, int DB, int DO>
-__device__ __noinline__ void pz_mul(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, const PZ<DB>& B) {
+__device__ __forceinline__ void pz_mul(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, const PZ<DB>& B) {
+#if ARMOUR_UNIFIED_OP3
+    if constexpr (DA == 9 && DB == 3 && NT <= 128) { pz_mul93<NT>(S, dst, A, B); return; }
+#endif
+#ifdef ARMOUR_DUP_CODE
+    if (((size_t)&dst >> 7) & 1) { pz_mul_cp<NT, DA, DB, DO, 1>(S, dst, A, B); return; }
+#endif
+    pz_mul_cp<NT, DA, DB, DO, 0>(S, dst, A, B);
+}
+template <int NT, int DA, int DB, int DO, int CP>
+__device__ __noinline__ void pz_mul_cp(Scratch& S, PZ<DO>& dst, const PZ<DA>& A, const PZ<DB>& B) {
     // one-plan shapes only (256 threads per group): measured -3.3 % on one plan; in the 128-thread sweep shape the sort-free path
     // executes 7 % fewer instructions but runs 7 % slower (its per-candidate chain is longer and the extra code costs 1.5 % even
     // when unused), so it is compiled out there
@@ -1020,8 +1055,17 @@ __device__ __forceinline__ void pz_merge_impl(Scratch& S, PZ<DO>& dst, const Vie
     const int buf = merge_sort_runs<NT, BIG>(S, N, W, magicW);
     reduce_emit<NT, DO, BIG, MergeOp<DA, DB, DO>, MergeEpi<DA, DB>>(S, buf, N, op, dst, MergeEpi<DA, DB>{A, B, negb});
 }
+template <int NT, int DA, int DB, int DO, int CP>
+__device__ __noinline__ void pz_merge_cp(Scratch& S, PZ<DO>& dst, const View<DA> A, const View<DB> B, bool negb);
 template <int NT, int DA, int DB, int DO>
-__device__ __noinline__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA> A, const View<DB> B, bool negb) {
+__device__ __forceinline__ void pz_merge(Scratch& S, PZ<DO>& dst, const View<DA> A, const View<DB> B, bool negb) {
+#ifdef ARMOUR_DUP_CODE
+    if (((size_t)&dst >> 7) & 1) { pz_merge_cp<NT, DA, DB, DO, 1>(S, dst, A, B, negb); return; }
+#endif
+    pz_merge_cp<NT, DA, DB, DO, 0>(S, dst, A, B, negb);
+}
+template <int NT, int DA, int DB, int DO, int CP>
+__device__ __noinline__ void pz_merge_cp(Scratch& S, PZ<DO>& dst, const View<DA> A, const View<DB> B, bool negb) {
     int N = A.p->n + B.p->n;
     if (N > S.ncap || N > 65535) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
     if (N <= S.scap) pz_merge_impl<NT, DA, DB, DO, false>(S, dst, A, B, negb, N);
@@ -1056,9 +1100,17 @@ __device__ __noinline__ void pz_simplify(Scratch& S, PZ<D>& dst, const PZ<D>& A)
     if (N <= S.scap) pz_simplify_impl<NT, D, false>(S, dst, A, N);
     else pz_simplify_impl<NT, D, true>(S, dst, A, N);
 }
-template <int NT> __device__ __forceinline__ void pz_add3(Scratch& S, PZ<3>& dst, const PZ<3>& a, const PZ<3>& b) { pz_merge<NT, 3, 3, 3>(S, dst, view(a), view(b), false); }
+template <int NT> __device__ __forceinline__ void pz_add3(Scratch& S, PZ<3>& dst, const PZ<3>& a, const PZ<3>& b) {
+#if ARMOUR_UNIFIED_OP3
+    if constexpr (NT <= 128) { op3_add<NT>(S, dst, a, b); return; }
+#endif
+    pz_merge<NT, 3, 3, 3>(S, dst, view(a), view(b), false);
+}
 // dst = a with the scalar PZ s added into row `row`   (addOneDimPZ)
 template <int NT> __device__ __forceinline__ void pz_add_one_dim(Scratch& S, PZ<3>& dst, const PZ<3>& a, const PZ<1>& s, int row) {
+#if ARMOUR_UNIFIED_OP3
+    if constexpr (NT <= 128) { op3_add_one_dim<NT>(S, dst, a, s, row); return; }
+#endif
     pz_merge<NT, 3, 1, 3>(S, dst, view(a), view_place(s, row), false);
 }
 
@@ -1160,8 +1212,20 @@ __device__ __forceinline__ void pz_cross_pp_impl(Scratch& S, PZ<3>& dst, const P
     const int buf = merge_sort_runs<NT, BIG>(S, N, W, magicW);
     reduce_emit<NT, 3, BIG, CrossPPOp, CrossPPEpi>(S, buf, N, op, dst, CrossPPEpi{A, B});
 }
+template <int NT, int CP>
+__device__ __noinline__ void pz_cross_pp_cp(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B);
 template <int NT>
-__device__ __noinline__ void pz_cross_pp(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B) {
+__device__ __forceinline__ void pz_cross_pp(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B) {
+#if ARMOUR_UNIFIED_OP3
+    if constexpr (NT <= 128) { op3_cross<NT>(S, dst, A, B); return; }
+#endif
+#ifdef ARMOUR_DUP_CODE
+    if (((size_t)&dst >> 7) & 1) { pz_cross_pp_cp<NT, 1>(S, dst, A, B); return; }
+#endif
+    pz_cross_pp_cp<NT, 0>(S, dst, A, B);
+}
+template <int NT, int CP>
+__device__ __noinline__ void pz_cross_pp_cp(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B) {
     int N = A.n + B.n + A.n * B.n;
     if (N > S.ncap || N > 65535) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
     if (N <= S.scap) pz_cross_pp_impl<NT, false>(S, dst, A, B, N);
@@ -1223,8 +1287,20 @@ struct CrossConstEpi {
     }
     __device__ __forceinline__ u64 mask() const { return Z.ormask; }
 };
+template <int NT, int CP>
+__device__ __noinline__ void pz_cross_const_cp(Scratch& S, PZ<3>& dst, const PZ<3>& Z, const double* kvec, bool const_first);
 template <int NT>
-__device__ __noinline__ void pz_cross_const(Scratch& S, PZ<3>& dst, const PZ<3>& Z, const double* kvec, bool const_first) {
+__device__ __forceinline__ void pz_cross_const(Scratch& S, PZ<3>& dst, const PZ<3>& Z, const double* kvec, bool const_first) {
+#if ARMOUR_UNIFIED_OP3
+    if constexpr (NT <= 128) { op3_cross_const<NT>(S, dst, Z, kvec, const_first); return; }
+#endif
+#ifdef ARMOUR_DUP_CODE
+    if (((size_t)&dst >> 7) & 1) { pz_cross_const_cp<NT, 1>(S, dst, Z, kvec, const_first); return; }
+#endif
+    pz_cross_const_cp<NT, 0>(S, dst, Z, kvec, const_first);
+}
+template <int NT, int CP>
+__device__ __noinline__ void pz_cross_const_cp(Scratch& S, PZ<3>& dst, const PZ<3>& Z, const double* kvec, bool const_first) {
     CrossConstOp op{Z, {kvec[0], kvec[1], kvec[2]}, const_first, S.thr_sq};
     if (Z.n <= S.scap) elementwise_emit<NT, 3, false, CrossConstOp, CrossConstEpi>(S, Z.n, Z.keys, op, dst, CrossConstEpi{Z, {kvec[0], kvec[1], kvec[2]}, const_first});
     else elementwise_emit<NT, 3, true, CrossConstOp, CrossConstEpi>(S, Z.n, Z.keys, op, dst, CrossConstEpi{Z, {kvec[0], kvec[1], kvec[2]}, const_first});
@@ -1268,8 +1344,20 @@ struct ConstLeftEpi {
     }
     __device__ __forceinline__ u64 mask() const { return V.ormask; }
 };
+template <int NT, int CP>
+__device__ __noinline__ void pz_const_left_cp(Scratch& S, PZ<3>& dst, const double* Mc, const double* Mi0, const double* Mi1, bool scalar, const PZ<3>& V);
 template <int NT>
-__device__ __noinline__ void pz_const_left(Scratch& S, PZ<3>& dst, const double* Mc, const double* Mi0, const double* Mi1, bool scalar, const PZ<3>& V) {
+__device__ __forceinline__ void pz_const_left(Scratch& S, PZ<3>& dst, const double* Mc, const double* Mi0, const double* Mi1, bool scalar, const PZ<3>& V) {
+#if ARMOUR_UNIFIED_OP3
+    if constexpr (NT <= 128) { op3_const_left<NT>(S, dst, Mc, Mi0, Mi1, scalar, V); return; }
+#endif
+#ifdef ARMOUR_DUP_CODE
+    if (((size_t)&dst >> 7) & 1) { pz_const_left_cp<NT, 1>(S, dst, Mc, Mi0, Mi1, scalar, V); return; }
+#endif
+    pz_const_left_cp<NT, 0>(S, dst, Mc, Mi0, Mi1, scalar, V);
+}
+template <int NT, int CP>
+__device__ __noinline__ void pz_const_left_cp(Scratch& S, PZ<3>& dst, const double* Mc, const double* Mi0, const double* Mi1, bool scalar, const PZ<3>& V) {
     ConstLeftOp op{V, {0}, scalar, S.thr_sq};
     const int DM = scalar ? 1 : 9;
     for (int c = 0; c < DM; c++) op.M[c] = Mc[c];
@@ -1303,10 +1391,290 @@ struct ConstRightEpi {
     __device__ __forceinline__ u64 mask() const { return R.ormask; }
 };
 template <int NT>
-__device__ __noinline__ void pz_const_right(Scratch& S, PZ<3>& dst, const PZ<9>& R, const double* pvec) {
+__device__ __forceinline__ void pz_const_right(Scratch& S, PZ<3>& dst, const PZ<9>& R, const double* pvec) {
+#if ARMOUR_UNIFIED_OP3
+    if constexpr (NT <= 128) { op3_const_right<NT>(S, dst, R, pvec); return; }
+#endif
     ConstRightOp op{R, {pvec[0], pvec[1], pvec[2]}, S.thr_sq};
     if (R.n <= S.scap) elementwise_emit<NT, 3, false, ConstRightOp, ConstRightEpi>(S, R.n, R.keys, op, dst, ConstRightEpi{R, {pvec[0], pvec[1], pvec[2]}});
     else elementwise_emit<NT, 3, true, ConstRightOp, ConstRightEpi>(S, R.n, R.keys, op, dst, ConstRightEpi{R, {pvec[0], pvec[1], pvec[2]}});
+}
+
+// =============================================================================================
+// Unified 3-vector operation.  The sweep shape is bound by instruction fetch, not by issue slots or memory: with the hot code
+// of the kernel duplicated (same executed instructions, twice the footprint) it runs 32 % slower (profiles/README.md, round 2).
+// Every operation above inlines its own copy of the key fill, the merge sort, the segment walk and the compaction; here all
+// seven operations that produce a 3-vector — R * v, v + v, v + scalar-in-a-row, cross(v, v), cross with a constant, constant
+// matrix / scalar times v, R * constant — share ONE copy, and only the few instructions that differ (the term of a candidate,
+// the threshold stages, the scalar epilogue) are selected by `kind`.  Arithmetic, candidate order and results are those of the
+// dedicated operations (the element-wise ones become a single sorted run whose every key is its own segment).
+// =============================================================================================
+enum Op3Kind { K3_MUL93 = 0, K3_MERGE33 = 1, K3_MERGE31 = 2, K3_CROSS = 3, K3_CROSS_CONST = 4, K3_CONST_LEFT = 5, K3_CONST_RIGHT = 6 };
+struct Op3 {
+    int kind;
+    const void* A; const void* B;       // operand descriptors (PZ<9> / PZ<3> / PZ<1> by kind), for the scalar epilogue
+    const u64* ka; const u64* kb; int na, nb; u64 ma, mb;     // keys, counts, division magics
+    const double* pa; const double* pb; int cpa, cpb;          // coefficient planes and strides
+    double m[9];   // MUL93: centre of A; CROSS: centre of A; CROSS_CONST: the constant; CONST_LEFT: M (or the scalar in m[0]); CONST_RIGHT: p
+    double v[3];   // MUL93, CROSS: centre of B
+    int row;       // MERGE31: row that receives the scalar
+    bool flag;     // CROSS_CONST: constant first; CONST_LEFT: scalar
+    const double* Mc; const double* Mi0; const double* Mi1;   // CONST_LEFT: centre and the two radii of the constant operand
+};
+__device__ __forceinline__ void op3_term(const Op3& d, unsigned idx, double* o) {   // o[6]; entries 3..5 only for K3_CROSS
+    switch (d.kind) {
+    case K3_MUL93: {
+        double a[9], b[3];
+        if ((int)idx < d.na) { ldc<9>(d.pa, d.cpa, idx, a); matvec_rn(a, d.v, o); }
+        else if ((int)idx < d.na + d.nb) { ldc<3>(d.pb, d.cpb, idx - d.na, b); matvec_rn(d.m, b, o); }
+        else {
+            const int p = idx - d.na - d.nb;
+            const int i = FastDiv(d.mb).div(p), j = p - i * d.nb;
+            ldc<9>(d.pa, d.cpa, i, a); ldc<3>(d.pb, d.cpb, j, b);
+            matvec_rn(a, b, o);
+        }
+        break;
+    }
+    case K3_MERGE33: {
+        if ((int)idx < d.na) ldc<3>(d.pa, d.cpa, idx, o); else ldc<3>(d.pb, d.cpb, idx - d.na, o);
+        break;
+    }
+    case K3_MERGE31: {
+        if ((int)idx < d.na) ldc<3>(d.pa, d.cpa, idx, o);
+        else { const double s = d.pb[idx - d.na]; o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; if (d.row == 0) o[0] = s; else if (d.row == 1) o[1] = s; else o[2] = s; }
+        break;
+    }
+    case K3_CROSS: {
+        double a[3], b[3];
+        if ((int)idx < d.na) { ldc<3>(d.pa, d.cpa, idx, a); b[0] = d.v[0]; b[1] = d.v[1]; b[2] = d.v[2]; }
+        else if ((int)idx < d.na + d.nb) { ldc<3>(d.pb, d.cpb, idx - d.na, b); a[0] = d.m[0]; a[1] = d.m[1]; a[2] = d.m[2]; }
+        else {
+            const int p = idx - d.na - d.nb;
+            const int i = FastDiv(d.mb).div(p), j = p - i * d.nb;
+            ldc<3>(d.pa, d.cpa, i, a); ldc<3>(d.pb, d.cpb, j, b);
+        }
+        o[0] = mul_rn(a[1], b[2]); o[1] = mul_rn(a[2], b[1]);
+        o[2] = mul_rn(a[2], b[0]); o[3] = mul_rn(a[0], b[2]);
+        o[4] = mul_rn(a[0], b[1]); o[5] = mul_rn(a[1], b[0]);
+        break;
+    }
+    case K3_CROSS_CONST: { double z[3]; ldc<3>(d.pa, d.cpa, idx, z); cross_const_comp(d.m, d.flag, z, o); break; }
+    case K3_CONST_LEFT: {
+        double z[3];
+        ldc<3>(d.pa, d.cpa, idx, z);
+        if (d.flag) { o[0] = mul_rn(d.m[0], z[0]); o[1] = mul_rn(d.m[0], z[1]); o[2] = mul_rn(d.m[0], z[2]); }
+        else matvec_rn(d.m, z, o);
+        break;
+    }
+    default: { double r9[9]; ldc<9>(d.pa, d.cpa, idx, r9); matvec_rn(r9, d.m, o); break; }   // K3_CONST_RIGHT
+    }
+}
+// threshold stages of the operation's simplify() calls; out[3], drop[3] (drop = |dropped| per component)
+__device__ __forceinline__ bool op3_finish(const Op3& d, const double* acc, double* out, double* drop, double thr) {
+    if (d.kind == K3_CROSS) {   // each scalar product, then the difference, then the stacked vector (see CrossPPOp)
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double p = acc[2 * c], q = acc[2 * c + 1];
+            const bool kp = norm1(&p) > thr, kq = norm1(&q) > thr;
+            double dd = 0.0;
+            if (!kp) dd = __dadd_ru(dd, fabs(p));
+            if (!kq) dd = __dadd_ru(dd, fabs(q));
+            double vv = 0.0;
+            bool present = false;
+            if (kp || kq) {
+                vv = kp ? (kq ? add_rn(p, -q) : p) : -q;
+                if (norm1(&vv) > thr) present = true;
+                else { dd = __dadd_ru(dd, fabs(vv)); vv = 0.0; }
+            }
+            out[c] = vv; drop[c] = dd; any |= present;
+        }
+        if (!any) return false;
+        if (norm3(out) <= thr) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) drop[c] = __dadd_ru(drop[c], fabs(out[c]));
+            return false;
+        }
+        return true;
+    }
+    if (d.kind == K3_CROSS_CONST) {   // component-wise simplify of the scaled differences, then the stacked vector (see CrossConstOp)
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (norm1(&acc[c]) > thr) { out[c] = acc[c]; any = true; drop[c] = 0.0; }
+            else { out[c] = 0.0; drop[c] = fabs(acc[c]); }
+        }
+        if (!any) return false;
+        if (norm3(out) <= thr) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) drop[c] = __dadd_ru(drop[c], fabs(out[c]));
+            return false;
+        }
+        return true;
+    }
+    if (norm3(acc) <= thr) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) drop[c] = fabs(acc[c]);
+        return false;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) out[c] = acc[c];
+    return true;
+}
+template <int NT>
+__device__ __forceinline__ void op3_epilogue_begin(ScalarEpilogue<NT, 3>& se, const Op3& d) {
+    switch (d.kind) {
+    case K3_MUL93: se.begin(MulEpi<9, 3, 3>{*(const PZ<9>*)d.A, *(const PZ<3>*)d.B}); break;
+    case K3_MERGE33: se.begin(MergeEpi<3, 3>{view(*(const PZ<3>*)d.A), view(*(const PZ<3>*)d.B), false}); break;
+    case K3_MERGE31: se.begin(MergeEpi<3, 1>{view(*(const PZ<3>*)d.A), view_place(*(const PZ<1>*)d.B, d.row), false}); break;
+    case K3_CROSS: se.begin(CrossPPEpi{*(const PZ<3>*)d.A, *(const PZ<3>*)d.B}); break;
+    case K3_CROSS_CONST: se.begin(CrossConstEpi{*(const PZ<3>*)d.A, {d.m[0], d.m[1], d.m[2]}, d.flag}); break;
+    case K3_CONST_LEFT: se.begin(ConstLeftEpi{*(const PZ<3>*)d.A, d.Mc, d.Mi0, d.Mi1, d.flag}); break;
+    default: se.begin(ConstRightEpi{*(const PZ<9>*)d.A, {d.m[0], d.m[1], d.m[2]}}); break;
+    }
+}
+template <int NT, bool BIG>
+__device__ __forceinline__ void pz_op3_impl(Scratch& S, PZ<3>& dst, const Op3& d, int N) {
+    u64* key0 = Buf<BIG>::key(S, 0);
+    u16* idx0 = Buf<BIG>::idx(S, 0);
+    int W = 1;
+    u64 magicW = 0;
+    const int na = d.na, nb = d.nb;
+    if (N > 0) {
+        if (d.kind == K3_MUL93 || d.kind == K3_CROSS) fill_product_keys<NT, BIG>(S, d.ka, na, d.ma, d.kb, nb, d.mb, W, magicW);
+        else if (d.kind == K3_MERGE33 || d.kind == K3_MERGE31) {
+            if (na >= nb) {   // the longer run first: runs must have uniform width except the last
+                W = na > 0 ? na : 1; magicW = d.ma;
+                #pragma unroll 1
+                for (int i = gtid<NT>(); i < na; i += NT) { key0[i] = d.ka[i]; idx0[i] = (u16)i; }
+                #pragma unroll 1
+                for (int j = gtid<NT>(); j < nb; j += NT) { key0[na + j] = d.kb[j]; idx0[na + j] = (u16)(na + j); }
+            }
+            else {
+                W = nb; magicW = d.mb;
+                #pragma unroll 1
+                for (int j = gtid<NT>(); j < nb; j += NT) { key0[j] = d.kb[j]; idx0[j] = (u16)(na + j); }
+                #pragma unroll 1
+                for (int i = gtid<NT>(); i < na; i += NT) { key0[nb + i] = d.ka[i]; idx0[nb + i] = (u16)i; }
+            }
+        }
+        else {   // element-wise: one sorted run, every key its own segment
+            W = N; magicW = d.ma;
+            #pragma unroll 1
+            for (int i = gtid<NT>(); i < N; i += NT) { key0[i] = d.ka[i]; idx0[i] = (u16)i; }
+        }
+    }
+    gsync<NT>();
+    phase_mark(PH_FILL);
+    const int buf = merge_sort_runs<NT, BIG>(S, N, W, magicW);
+    const u64* key = Buf<BIG>::key(S, buf);
+    const u16* idx = Buf<BIG>::idx(S, buf);
+    u16* flag = Buf<BIG>::idx(S, buf ^ 1);
+    int ncap;
+    double* tmp = S.staging(N, 3, ncap);
+    double red[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) red[c] = 0.0;
+    ScalarEpilogue<NT, 3> se;
+    op3_epilogue_begin<NT>(se, d);
+    const double thr = S.thr_sq;
+    const bool six = d.kind == K3_CROSS;
+    #pragma unroll 1
+    for (int g = gtid<NT>(); g < N; g += NT) {
+        const u64 k = key[g];
+        u16 f = 0;
+        if (g == 0 || key[g - 1] != k) {
+            double acc[6];
+            op3_term(d, idx[g], acc);
+            #pragma unroll 1
+            for (int e = g + 1; e < N && key[e] == k; e++) {
+                double t[6];
+                op3_term(d, idx[e], t);
+#pragma unroll
+                for (int c = 0; c < 3; c++) acc[c] = add_rn(acc[c], t[c]);
+                if (six) {
+#pragma unroll
+                    for (int c = 3; c < 6; c++) acc[c] = add_rn(acc[c], t[c]);
+                }
+            }
+            double out[3], dr[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) dr[c] = 0.0;
+            const bool keep = op3_finish(d, acc, out, dr, thr);
+#pragma unroll
+            for (int c = 0; c < 3; c++) red[c] = __dadd_ru(red[c], dr[c]);
+            if (keep) {
+                f = 1;
+#pragma unroll
+                for (int c = 0; c < 3; c++) { tmp[c * ncap + g] = out[c]; red[3 + c] = __dadd_ru(red[3 + c], fabs(out[c])); }
+            }
+        }
+        flag[g] = f;
+    }
+    gsync<NT>();
+    phase_mark(PH_SEGMENT);
+    compact_emit<NT, 3>(S, N, key, flag, tmp, ncap, red, se, dst);
+}
+// The descriptor is assembled INSIDE the one non-inlined function, from a handful of scalar arguments: a struct handed across
+// the call boundary by reference would live in local memory, and every field access in the inner loops would be a load.
+template <int NT>
+__device__ __noinline__ void pz_op3(Scratch& S, PZ<3>& dst, int kind, const void* A, const void* B, const double* konst, int row, bool flag,
+                                    const double* Mi0, const double* Mi1) {
+    Op3 d;
+    d.kind = kind; d.A = A; d.B = B; d.row = row; d.flag = flag; d.Mc = konst; d.Mi0 = Mi0; d.Mi1 = Mi1;
+    d.kb = nullptr; d.nb = 0; d.mb = 0; d.pb = nullptr; d.cpb = 0;
+#pragma unroll
+    for (int c = 0; c < 9; c++) d.m[c] = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) d.v[c] = 0.0;
+    if (kind == K3_MUL93 || kind == K3_CONST_RIGHT) {
+        const PZ<9>& a = *(const PZ<9>*)A;
+        d.ka = a.keys; d.na = a.n; d.ma = a.divM; d.pa = a.coef; d.cpa = a.cap;
+        if (kind == K3_MUL93) {
+#pragma unroll
+            for (int c = 0; c < 9; c++) d.m[c] = a.center[c];
+        }
+    }
+    else {
+        const PZ<3>& a = *(const PZ<3>*)A;
+        d.ka = a.keys; d.na = a.n; d.ma = a.divM; d.pa = a.coef; d.cpa = a.cap;
+        if (kind == K3_CROSS) { d.m[0] = a.center[0]; d.m[1] = a.center[1]; d.m[2] = a.center[2]; }
+    }
+    if (kind == K3_MUL93 || kind == K3_MERGE33 || kind == K3_CROSS) {
+        const PZ<3>& b = *(const PZ<3>*)B;
+        d.kb = b.keys; d.nb = b.n; d.mb = b.divM; d.pb = b.coef; d.cpb = b.cap;
+        if (kind != K3_MERGE33) { d.v[0] = b.center[0]; d.v[1] = b.center[1]; d.v[2] = b.center[2]; }
+    }
+    else if (kind == K3_MERGE31) {
+        const PZ<1>& b = *(const PZ<1>*)B;
+        d.kb = b.keys; d.nb = b.n; d.mb = b.divM; d.pb = b.coef; d.cpb = b.cap;
+    }
+    if (kind == K3_CROSS_CONST || kind == K3_CONST_RIGHT) { d.m[0] = konst[0]; d.m[1] = konst[1]; d.m[2] = konst[2]; }
+    else if (kind == K3_CONST_LEFT) {
+        d.m[0] = konst[0];
+        if (!flag) {
+#pragma unroll
+            for (int c = 1; c < 9; c++) d.m[c] = konst[c];
+        }
+    }
+    int N = (kind == K3_MUL93 || kind == K3_CROSS) ? d.na + d.nb + d.na * d.nb : (kind == K3_MERGE33 || kind == K3_MERGE31) ? d.na + d.nb : d.na;
+    if (N > S.ncap || N > 65535) { if (gtid<NT>() == 0) set_err(S, ERR_ENTRY_CAP); N = 0; }
+    if (N <= S.scap) pz_op3_impl<NT, false>(S, dst, d, N);
+    else pz_op3_impl<NT, true>(S, dst, d, N);
+}
+// the seven operations
+template <int NT> __device__ __forceinline__ void op3_mul93(Scratch& S, PZ<3>& dst, const PZ<9>& A, const PZ<3>& B) { pz_op3<NT>(S, dst, K3_MUL93, &A, &B, nullptr, 0, false, nullptr, nullptr); }
+template <int NT> __device__ __forceinline__ void op3_add(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B) { pz_op3<NT>(S, dst, K3_MERGE33, &A, &B, nullptr, 0, false, nullptr, nullptr); }
+template <int NT> __device__ __forceinline__ void op3_add_one_dim(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<1>& s, int row) { pz_op3<NT>(S, dst, K3_MERGE31, &A, &s, nullptr, row, false, nullptr, nullptr); }
+template <int NT> __device__ __forceinline__ void op3_cross(Scratch& S, PZ<3>& dst, const PZ<3>& A, const PZ<3>& B) { pz_op3<NT>(S, dst, K3_CROSS, &A, &B, nullptr, 0, false, nullptr, nullptr); }
+template <int NT> __device__ __forceinline__ void op3_cross_const(Scratch& S, PZ<3>& dst, const PZ<3>& Z, const double* kvec, bool const_first) {
+    pz_op3<NT>(S, dst, K3_CROSS_CONST, &Z, nullptr, kvec, 0, const_first, nullptr, nullptr);
+}
+template <int NT> __device__ __forceinline__ void op3_const_left(Scratch& S, PZ<3>& dst, const double* Mc, const double* Mi0, const double* Mi1, bool scalar, const PZ<3>& V) {
+    pz_op3<NT>(S, dst, K3_CONST_LEFT, &V, nullptr, Mc, 0, scalar, Mi0, Mi1);
+}
+template <int NT> __device__ __forceinline__ void op3_const_right(Scratch& S, PZ<3>& dst, const PZ<9>& R, const double* pvec) {
+    pz_op3<NT>(S, dst, K3_CONST_RIGHT, &R, nullptr, pvec, 0, false, nullptr, nullptr);
 }
 
 // reset to a monomial-free PZ with centre c (all threads call; thread 0 writes)

@@ -16,13 +16,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "armour-dev_b200"), os.path.join(ROOT, "tests")]
 
 CONFIGS = [
-    # (threads, CTAs/SM bound, scap, tcap, mcap)
+    # (threads per interval, CTAs/SM bound, shared sort entries, shared staging entries, monomial capacity)
     (128, 4, 1408, 300, 1024),   # round-1 sweep shape (reference digest)
-    (128, 3, 1408, 300, 1024),
+    (128, 3, 1408, 300, 1024),   # round-2 default
+    (128, 5, 1408, 300, 1024),
     (128, 2, 1408, 300, 1024),
-    (128, 3, 1664, 384, 1024),
-    (128, 3, 1152, 256, 1024),
-    (128, 3, 1408, 300, 512),
+    (128, 3, 1408, 640, 1024),
+    (64, 8, 768, 192, 512),
+    (64, 12, 512, 96, 512),
+    (32, 12, 512, 128, 512),
+    (32, 16, 384, 64, 512),
+    (32, 24, 256, 32, 512),
 ]
 
 
