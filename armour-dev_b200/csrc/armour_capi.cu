@@ -430,7 +430,7 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     // registers were 2 % ahead (the sweep is bound by instruction fetch, not by resident warps); with the unified 3-vector
     // operation 4 CTAs lead by 4.5 % (profiles/README.md, round-2 experiments)
     h->minb = nt == 32 ? 16 : nt == 64 ? 8 : cfg.batch > 1 ? (nt == 128 ? 4 : 2) : 1;
-    if (cfg.batch > 1 && nt == 128) { h->scap = 1408; h->tcap = 300; }
+    if (cfg.batch > 1 && nt == 128) { h->scap = 1536; h->tcap = 300; }   // 1536: the largest operations of a heavy interval (~1400-1500 candidates) still sort in shared memory
     if (nt == 64) { h->scap = 768; h->tcap = 192; }
     if (nt == 32) { h->scap = 512; h->tcap = 128; }
     if (const char* e = getenv("ARMOUR_TUNE_MINB")) h->minb = atoi(e);

@@ -581,7 +581,9 @@ __device__ void backward_joint(Scratch& S, Slots& Z, PZ<3>* T, int i) {
     if (axis != 0) {
         // u = n(axis) + armature * qdda_des + damping * qd_des
         pz_merge<NT, 3, 1, 1>(S, Z.c.u[i], view_extract(Z.h.Nv, row), view_scaled(Z.c.qdda[i], rm.armature[i]), false);
-        pz_merge<NT, 1, 1, 1>(S, Z.c.u[i], view(Z.c.u[i]), view_scaled(Z.c.qd[i], rm.damping[i]), false);
+        // + damping * qd_des: with a damping of exactly zero (the Kinova model) the addend is all zeros — centre, coefficients and
+        // |scale| * radius — so u is unchanged bit for bit (its monomials are re-thresholded against the same values) and the pass is skipped
+        if (rm.damping[i] != 0.0) pz_merge<NT, 1, 1, 1>(S, Z.c.u[i], view(Z.c.u[i]), view_scaled(Z.c.qd[i], rm.damping[i]), false);
     }
 }
 
@@ -641,7 +643,9 @@ __device__ void moment_joint(Scratch& S, Slots& Z, PZ<3>* T, int i) {
     pz_add3<NT>(S, Z.h.Nv, T[1], Z.c.C2[i]);
     if (axis != 0) {
         pz_merge<NT, 3, 1, 1>(S, Z.c.u[i], view_extract(Z.h.Nv, row), view_scaled(Z.c.qdda[i], rm.armature[i]), false);
-        pz_merge<NT, 1, 1, 1>(S, Z.c.u[i], view(Z.c.u[i]), view_scaled(Z.c.qd[i], rm.damping[i]), false);
+        // + damping * qd_des: with a damping of exactly zero (the Kinova model) the addend is all zeros — centre, coefficients and
+        // |scale| * radius — so u is unchanged bit for bit (its monomials are re-thresholded against the same values) and the pass is skipped
+        if (rm.damping[i] != 0.0) pz_merge<NT, 1, 1, 1>(S, Z.c.u[i], view(Z.c.u[i]), view_scaled(Z.c.qd[i], rm.damping[i]), false);
     }
 }
 
