@@ -384,14 +384,15 @@ __device__ __forceinline__ int merge_sort_runs(Scratch& S, int N, int W, u64 mag
             const unsigned id = ii[g];
             int pos = g;
             if (sb < N) {
-                int lo = sb, hi = min(sb + w, N);
-                while (lo < hi) {
+                const int end = min(sb + w, N);
+                int lo = sb, hi = end;
+                while (lo < hi) {   // lower bound on the key alone
                     const int mid = (lo + hi) >> 1;
-                    const u64 km = ki[mid];
-                    bool less = km < k;
-                    if (km == k) less = ii[mid] < id;   // the index is only needed on an exact tie: no second dependent load otherwise
-                    if (less) lo = mid + 1; else hi = mid;
+                    if (ki[mid] < k) lo = mid + 1; else hi = mid;
                 }
+                // exact ties: equal keys of a run are adjacent and ordered by origin index, so the entries that precede
+                // (k, id) are a prefix of the equal range (one extra load per candidate instead of tie logic in every search step)
+                while (lo < end && ki[lo] == k && ii[lo] < id) lo++;
                 pos = min(base, sb) + (g - base) + (lo - sb);
             }
             ko[pos] = k;
