@@ -26,7 +26,7 @@ EXPORTS = [
     "armour_eval_grad_f", "armour_eval_g", "armour_eval_jac_g", "armour_eval_g_jac", "armour_jac_structure", "armour_release_host_buffers", "armour_check_feasible",
     "armour_get_torque_radius", "armour_get_link_generators", "armour_get_link_sliced_center", "armour_get_hyperplanes",
     "armour_get_taylor_remainders", "armour_get_pz", "armour_pz_binary", "armour_last_build_ms", "armour_last_eval_ms",
-    "armour_kernel_launches", "armour_set_kernel_timing", "armour_last_eval_host_us", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_eval_resident_burst", "armour_upload_x", "armour_standin_solve", "armour_debug_phase_cycles", "armour_debug_canaries_verified", "armour_measure_fp64_peak",
+    "armour_kernel_launches", "armour_set_kernel_timing", "armour_last_eval_host_us", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_eval_resident_burst", "armour_eval_batch", "armour_last_eval_batch_ms", "armour_upload_x", "armour_standin_solve", "armour_debug_phase_cycles", "armour_debug_canaries_verified", "armour_measure_fp64_peak",
 ]
 
 
@@ -289,6 +289,26 @@ class Planner:
         values = np.zeros(m * 7) if values is None else values
         self._ck(self.L.armour_eval_g_jac(self.h, _dp(_vec(x, 7)), _dp(g), _dp(values)))
         return g, values.reshape(m, 7)
+
+    def eval_batch(self, xs, g=None, values=None, first=0, want_jac=False):
+        """One launch for problems first .. first+len(xs)-1 of the last batch build, problem y at xs[y] (armour_eval_batch).
+        g: (count, m) array written in place (allocated when None); values: (count, m * 7) array, or allocated when
+        want_jac.  Under pin_user_buffers the arrays handed in must stay alive until release_host_buffers()/close()."""
+        xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(-1, 7)
+        n, m = xs.shape[0], self.m
+        if g is None:
+            g = np.zeros((n, m))
+        if values is None and want_jac:
+            values = np.zeros((n, m * 7))
+        assert g.dtype == np.float64 and g.flags.c_contiguous and g.size == n * m
+        assert values is None or (values.dtype == np.float64 and values.flags.c_contiguous and values.size == n * m * 7)
+        self._ck(self.L.armour_eval_batch(self.h, C.c_int(first), C.c_int(n), _dp(xs), _dp(g), _dp(values) if values is not None else None))
+        return (g, values) if values is not None else g
+
+    def last_eval_batch_ms(self):
+        v = C.c_float()
+        self._ck(self.L.armour_last_eval_batch_ms(self.h, C.byref(v)))
+        return v.value
 
     def eval_resident_burst(self, x, launches=20):
         """average device time (ms) of `launches` back-to-back device-resident evaluations"""

@@ -140,6 +140,9 @@ struct armour_handle {
     int host_write = 0;                            // how results reach host memory, see launch_eval
     double eval_host_us = 0.0;                     // wall-clock time spent inside the last evaluation call
     double *a_g = nullptr, *a_jac = nullptr;       // device aliases of the pinned staging buffers h_g / h_jac
+    double *d_bx = nullptr, *d_bg = nullptr, *d_bjac = nullptr, *h_bx = nullptr;   // armour_eval_batch: decision vectors and result rows of a whole batch
+    size_t bx_cap = 0, bg_cap = 0, bjac_cap = 0;
+    float batch_eval_ms = 0;
     int eval_bps_host = 0;                         // resident blocks per SM of the constraint kernel when it writes to host memory (waves overlap compute and PCIe)
     bool eval_timed = false;                       // events of the last evaluation are pending in ev[3], ev[4]
     bool time_kernels = false;                     // record CUDA events around the per-iteration kernel (armour_set_kernel_timing)
@@ -505,9 +508,9 @@ void armour_destroy(armour_handle* h) {
     cudaGetLastError();
     Tables& tb = h->tb;
     void* dev[] = {h->d_jrs, h->d_krange, h->d_state, h->d_obs, tb.traj, tb.cos_rem, tb.sin_rem, tb.u_n, tb.u_keys, tb.u_coef, tb.u_center, tb.u_ind, tb.dist_rad, tb.torque_radius,
-                   tb.l_n, tb.l_keys, tb.l_coef, tb.l_center, tb.l_ind, tb.gens, tb.A, tb.d, tb.delta, h->d_err, h->d_x, h->d_g, h->d_jac, h->d_link_center, h->arena, h->bin_buf, h->d_done};
+                   tb.l_n, tb.l_keys, tb.l_coef, tb.l_center, tb.l_ind, tb.gens, tb.A, tb.d, tb.delta, h->d_err, h->d_x, h->d_g, h->d_jac, h->d_link_center, h->arena, h->bin_buf, h->d_done, h->d_bx, h->d_bg, h->d_bjac};
     for (void* p : dev) if (p) cudaFree(p);
-    void* pinned[] = {h->h_jrs, h->h_krange, h->h_state, h->h_obs, h->h_x, h->h_g, h->h_jac, h->h_torque_radius, h->h_err, (void*)h->h_done};
+    void* pinned[] = {h->h_jrs, h->h_krange, h->h_state, h->h_obs, h->h_x, h->h_g, h->h_jac, h->h_torque_radius, h->h_err, (void*)h->h_done, h->h_bx};
     for (void* p : pinned) if (p) cudaFreeHost(p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -685,6 +688,60 @@ int armour_eval_resident_burst(armour_handle* h, const double* x, int launches, 
     cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]);
     *ms_per_launch = ms / launches;
     h->eval_timed = false;
+    return ARMOUR_OK;
+}
+// One launch for `count` problems of the last batch build, problem y evaluated at x[y][0..6]: the call a batched solver (or a
+// sweep that steps all its solvers in lockstep) makes once per iteration.  Rows of problem first + y go to g + y * m and
+// values + y * 7 m (either may be NULL).  With cfg.pin_user_buffers the kernel writes the caller's arrays; otherwise the rows
+// pass through device buffers and one copy each.
+int armour_eval_batch(armour_handle* h, int first, int count, const double* x, double* g, double* values) {
+    if (!h || !x || (!g && !values)) return fail(ARMOUR_E_INVALID, "null argument");
+    if (!h->built) return fail(ARMOUR_E_STATE, "eval before build");
+    if (first < 0 || count < 1 || first + count > h->count) return fail(ARMOUR_E_INVALID, "problem range outside the last batch build");
+    CU(cudaSetDevice(h->device));
+    NvtxRange range("armour_eval_batch");
+    const size_t m = (size_t)m_of(h), n = (size_t)count;
+    const int what = (g ? 1 : 0) | (values ? 2 : 0);
+    if (h->bx_cap < n) {
+        if (h->d_bx) cudaFree(h->d_bx);
+        if (h->h_bx) cudaFreeHost(h->h_bx);
+        h->d_bx = nullptr; h->h_bx = nullptr; h->bx_cap = 0;
+        CU(dalloc(&h->d_bx, n * NF));
+        CU(cudaMallocHost((void**)&h->h_bx, sizeof(double) * n * NF));
+        h->bx_cap = n;
+    }
+    double *kg = nullptr, *kj = nullptr;
+    if (h->cfg.pin_user_buffers) {
+        kg = g ? (double*)pinned_alias(h, g, sizeof(double) * m * n) : nullptr;
+        kj = values ? (double*)pinned_alias(h, values, sizeof(double) * m * NF * n, kg) : nullptr;
+    }
+    const bool copy_g = g && !kg, copy_j = values && !kj;
+    if (copy_g) {
+        if (h->bg_cap < n * m) { if (h->d_bg) cudaFree(h->d_bg); h->d_bg = nullptr; h->bg_cap = 0; CU(dalloc(&h->d_bg, n * m)); h->bg_cap = n * m; }
+        kg = h->d_bg;
+    }
+    if (copy_j) {
+        if (h->bjac_cap < n * m * NF) { if (h->d_bjac) cudaFree(h->d_bjac); h->d_bjac = nullptr; h->bjac_cap = 0; CU(dalloc(&h->d_bjac, n * m * NF)); h->bjac_cap = n * m * NF; }
+        kj = h->d_bjac;
+    }
+    memcpy(h->h_bx, x, sizeof(double) * n * NF);
+    Tables tb = h->tb;
+    tb.P = h->count; tb.n_obs = h->n_obs; tb.mode = h->mode; tb.jrs = h->d_jrs; tb.k_range_in = h->d_krange;
+    CU(cudaMemcpyAsync(h->d_bx, h->h_bx, sizeof(double) * n * NF, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaEventRecord(h->ev[3], h->stream));
+    CU(launch_constraint_eval_batch(tb, first, count, h->d_bx, kg, kj, nullptr, what, h->stream));
+    CU(cudaEventRecord(h->ev[4], h->stream));
+    if (copy_g) CU(cudaMemcpyAsync(g, h->d_bg, sizeof(double) * n * m, cudaMemcpyDeviceToHost, h->stream));
+    if (copy_j) CU(cudaMemcpyAsync(values, h->d_bjac, sizeof(double) * n * m * NF, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->launches += 1;
+    cudaEventElapsedTime(&h->batch_eval_ms, h->ev[3], h->ev[4]);
+    h->have_eval = false;          // the single-problem staging buffers and link_sliced_center were not touched
+    return ARMOUR_OK;
+}
+int armour_last_eval_batch_ms(armour_handle* h, float* ms) {
+    if (!h || !ms) return fail(ARMOUR_E_INVALID, "null argument");
+    *ms = h->batch_eval_ms;
     return ARMOUR_OK;
 }
 int armour_upload_x(armour_handle* h, const double* x) {

@@ -18,6 +18,7 @@ cudaError_t launch_hyperplanes(const Tables& tb, cudaStream_t stream);
 int eval_max_obstacles();
 cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* x_host, double* g, double* jac, double* link_center, int what, unsigned* done_counter,
                                    unsigned long long* done_flag, unsigned long long seq, int blocks_per_sm, cudaStream_t stream);
+cudaError_t launch_constraint_eval_batch(const Tables& tb, int first, int count, const double* x_dev, double* g, double* jac, double* link_center, int what, cudaStream_t stream);
 double measure_fp64_tflops(int sm_count);
 void read_phase_cycles(unsigned long long* cycles, unsigned long long* calls, bool reset);
 }  // namespace armour

@@ -252,7 +252,9 @@ __host__ __device__ inline size_t eval_smem_bytes(int n_obs, int uchunk) {
 // full-width posted writes while the rest of the grid is still computing (no device-to-host copy after the kernel).
 // done_counter / done_flag: when done_flag != nullptr the last block to finish stores `seq` there (mapped pinned host memory)
 // after a system-wide fence — the host polls that word instead of synchronising the stream.
-__global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, int prob, XArg xarg, double* __restrict__ g, double* __restrict__ jac,
+// Batched form (armour_eval_batch): gridDim.y problems starting at `prob`, each with its own decision vector x_batch[y][7]
+// and its own block of rows in g / jac / link_center_out (problem-major) — one launch steps every solver of a sweep.
+__global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, int prob, XArg xarg, const double* __restrict__ x_batch, double* __restrict__ g, double* __restrict__ jac,
                                                                      double* __restrict__ link_center_out, int what, int uchunk, int lchunk,
                                                                      unsigned* done_counter, volatile unsigned long long* done_flag, unsigned long long seq) {
     extern __shared__ __align__(128) unsigned char eval_smem[];
@@ -265,6 +267,15 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
 #pragma unroll
     for (int i = 0; i < NF; i++) x[i] = xarg.x[i];
     const size_t off_obs = tb.mode == 0 ? (size_t)NF * T : 0, off_lim = off_obs + (size_t)NJ * T * n_obs;
+    if (x_batch != nullptr) {
+        const size_t y = blockIdx.y, m_rows = off_lim + 4 * NF;
+        prob += (int)y;
+#pragma unroll
+        for (int i = 0; i < NF; i++) x[i] = x_batch[y * NF + i];
+        if (g) g += y * m_rows;
+        if (jac) jac += y * m_rows * NF;
+        if (link_center_out) link_center_out += y * (size_t)T * NJ * 3;
+    }
     const int n_planes = n_obs * COMB;
     double* sA = reinterpret_cast<double*>(eval_smem);
     double* sd = sA + (size_t)n_planes * 3;
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
             if (tid < NF) {
                 const double* st = tb.state + (size_t)prob * 21;
                 double ext[4], gr[4];
-                armtd_state_extremum(st[tid], st[7 + tid], tb.k_range_in[(size_t)prob * NF + tid] * xarg.x[tid], ext, gr);
+                armtd_state_extremum(st[tid], st[7 + tid], tb.k_range_in[(size_t)prob * NF + tid] * x[tid], ext, gr);
                 for (int r = 0; r < 4; r++) {
                     const size_t row = off_lim + r * NF + tid;
                     if (want_g) g[row] = ext[r];
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
             const double* st = tb.state + (size_t)prob * 21;
             const double kr = tb.k_range[i];
             double mn, mx, gmn, gmx;
-            joint_extremum(st[i], st[7 + i], st[14 + i], kr * xarg.x[i], velocity, &mn, &mx, &gmn, &gmx);
+            joint_extremum(st[i], st[7 + i], st[14 + i], kr * x[i], velocity, &mn, &mx, &gmn, &gmx);
             const size_t r0 = off_lim + (velocity ? 2 * NF : 0) + i, r1 = r0 + NF;
             if (want_g) { g[r0] = mn; g[r1] = mx; }   // DURATION == 1
             if (want_j) for (int j = 0; j < NF; j++) { jac[r0 * NF + j] = (i == j) ? gmn * kr : 0.0; jac[r1 * NF + j] = (i == j) ? gmx * kr : 0.0; }
@@ -432,7 +443,7 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
         __syncthreads();
         if (tid == 0) {
             const unsigned prev = atomicAdd(done_counter, 1u);
-            if (prev == gridDim.x - 1) {
+            if (prev == gridDim.x * gridDim.y - 1) {
                 *done_counter = 0;               // ready for the next launch (stream order)
                 __threadfence_system();
                 *done_flag = seq;
@@ -451,15 +462,7 @@ int eval_max_obstacles() { return EVAL_MAX_OBS; }
 // blocks_per_sm > 0 caps the resident blocks per SM by padding the dynamic shared-memory request.  With every block resident
 // at once (the default, best for device-resident results) all blocks finish together; when the results go to host memory
 // over PCIe it pays to run the grid in a few waves, so that the first rows are on the wire while later blocks still compute.
-cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* x_host, double* g, double* jac, double* link_center, int what, unsigned* done_counter,
-                                   unsigned long long* done_flag, unsigned long long seq, int blocks_per_sm, cudaStream_t stream) {
-    if (tb.n_obs > EVAL_MAX_OBS) return cudaErrorInvalidValue;
-    XArg xa;
-    for (int i = 0; i < NF; i++) xa.x[i] = x_host[i];
-    const int uchunk = eval_uchunk(tb.n_obs, tb.ucap);
-    const size_t smem_max = eval_smem_bytes(EVAL_MAX_OBS, 128);
-    size_t smem = eval_smem_bytes(tb.n_obs, uchunk);
-    if (blocks_per_sm > 0) smem = std::max(smem, std::min((size_t)(227 * 1024) / blocks_per_sm - 1280, smem_max));
+static cudaError_t eval_opt_in(size_t smem, size_t smem_max) {
     if (smem > 48 * 1024) {   // opt in to a large dynamic shared-memory request, once per device
         static bool opted_in[64] = {};
         int dev = 0;
@@ -470,7 +473,33 @@ cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* x_h
             if (dev >= 0 && dev < 64) opted_in[dev] = true;
         }
     }
-    constraint_eval_kernel<<<tb.T * NJ + 1, EVAL_NT, smem, stream>>>(tb, prob, xa, g, jac, link_center, what, uchunk, EVAL_LCHUNK, done_counter, done_flag, seq);
+    return cudaSuccess;
+}
+cudaError_t launch_constraint_eval(const Tables& tb, int prob, const double* x_host, double* g, double* jac, double* link_center, int what, unsigned* done_counter,
+                                   unsigned long long* done_flag, unsigned long long seq, int blocks_per_sm, cudaStream_t stream) {
+    if (tb.n_obs > EVAL_MAX_OBS) return cudaErrorInvalidValue;
+    XArg xa;
+    for (int i = 0; i < NF; i++) xa.x[i] = x_host[i];
+    const int uchunk = eval_uchunk(tb.n_obs, tb.ucap);
+    const size_t smem_max = eval_smem_bytes(EVAL_MAX_OBS, 128);
+    size_t smem = eval_smem_bytes(tb.n_obs, uchunk);
+    if (blocks_per_sm > 0) smem = std::max(smem, std::min((size_t)(227 * 1024) / blocks_per_sm - 1280, smem_max));
+    cudaError_t e = eval_opt_in(smem, smem_max);
+    if (e != cudaSuccess) return e;
+    constraint_eval_kernel<<<tb.T * NJ + 1, EVAL_NT, smem, stream>>>(tb, prob, xa, nullptr, g, jac, link_center, what, uchunk, EVAL_LCHUNK, done_counter, done_flag, seq);
+    return cudaGetLastError();
+}
+// `count` problems starting at `first` in one launch: x_dev[count][7] in device-visible memory, rows of problem y at
+// g + y * m, jac + y * 7 m, link_center + y * 21 T (device memory or mapped pinned host memory).
+cudaError_t launch_constraint_eval_batch(const Tables& tb, int first, int count, const double* x_dev, double* g, double* jac, double* link_center, int what, cudaStream_t stream) {
+    if (tb.n_obs > EVAL_MAX_OBS || count < 1 || count > 65535 || x_dev == nullptr) return cudaErrorInvalidValue;
+    XArg xa;
+    for (int i = 0; i < NF; i++) xa.x[i] = 0.0;
+    const int uchunk = eval_uchunk(tb.n_obs, tb.ucap);
+    const size_t smem_max = eval_smem_bytes(EVAL_MAX_OBS, 128), smem = eval_smem_bytes(tb.n_obs, uchunk);
+    cudaError_t e = eval_opt_in(smem, smem_max);
+    if (e != cudaSuccess) return e;
+    constraint_eval_kernel<<<dim3(tb.T * NJ + 1, count), EVAL_NT, smem, stream>>>(tb, first, xa, x_dev, g, jac, link_center, what, uchunk, EVAL_LCHUNK, nullptr, nullptr, 0ull);
     return cudaGetLastError();
 }
 

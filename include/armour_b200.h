@@ -181,6 +181,12 @@ int armour_upload_x(armour_handle* h, const double* x);
 /* `launches` device-resident evaluations back to back between two CUDA events: average kernel time without the ~6 us that
  * a single launch bracketed by two events reads high (roofline measurement of bench.py) */
 int armour_eval_resident_burst(armour_handle* h, const double* x, int launches, float* ms_per_launch);
+/* Batched evaluation after armour_build_batch / armour_build_resident: ONE launch evaluates problems first .. first+count-1
+ * of the last batch, problem y at x[7 y .. 7 y + 6] (the per-iteration call of a batched solver; the reference has no
+ * counterpart — it runs one armtd_NLP::eval_g / eval_jac_g (KPR/NLPclass.cu:272-396) per problem and process).  Rows of
+ * problem first + y land at g[y * m ..] and values[y * 7 m ..]; either may be NULL.  Bit-identical to `count` single calls. */
+int armour_eval_batch(armour_handle* h, int first, int count, const double* x, double* g, double* values);
+int armour_last_eval_batch_ms(armour_handle* h, float* ms); /* device time of the last armour_eval_batch kernel */
 /* profiling builds (-DARMOUR_PHASE_TIMING) only: cycles / calls per engine phase summed over CTAs; zeros otherwise.
  * phases: 0 fill, 1 sort level, 2 segment walk, 3 scan+compact, 4 element-wise, 5 stage A, 6 export, 7 other */
 int armour_debug_phase_cycles(uint64_t* cycles8, uint64_t* calls8, int reset);

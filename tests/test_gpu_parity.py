@@ -194,6 +194,33 @@ def test_batch_equals_single_builds(gpu_lib):
             assert np.array_equal(a["keys"], b["keys"]) and np.array_equal(a["coeffs"], b["coeffs"])
 
 
+@pytest.mark.parametrize("pin", [False, True])
+def test_eval_batch_equals_single_evals(gpu_lib, pin):
+    """armour_eval_batch (one launch, one decision vector per problem) against one armour_eval_g_jac call per problem:
+    constraint values and Jacobian rows bit-identical, through device staging and through page-locked caller arrays; a
+    sub-range of the batch addresses the same problems."""
+    n_obs, T, B = 5, 16, 4
+    probs = [make_problem(s, n_obs) for s in (31, 32, 33, 34)]
+    pb = ab.Planner(T=T, batch=B, pin_user_buffers=pin)
+    pb.build_batch(np.concatenate([q[0] for q in probs]), np.concatenate([q[1] for q in probs]), np.concatenate([q[2] for q in probs]),
+                   np.concatenate([q[4] for q in probs]), n_obs)
+    rng = np.random.default_rng(77)
+    xs = rng.uniform(-1, 1, (B, 7))
+    G, V = pb.eval_batch(xs, want_jac=True)
+    g_only = pb.eval_batch(xs)
+    assert G.shape == (B, pb.m) and V.shape == (B, pb.m * 7) and np.array_equal(g_only, G)
+    sub = pb.eval_batch(xs[1:3], first=1)
+    assert np.array_equal(sub, G[1:3])
+    for i in range(B):
+        pb.select_problem(i)
+        g, J = pb.eval_g_jac(xs[i])
+        assert np.array_equal(g, G[i]) and np.array_equal(J.ravel(), V[i]), i
+    with pytest.raises(ab.ArmourError):
+        pb.eval_batch(xs, first=1)        # range runs past the batch
+    assert pb.last_eval_batch_ms() > 0
+    pb.close()
+
+
 def test_build_is_deterministic(gpu_lib):
     q0, qd0, qdd0, _, obs = make_problem(21, 10)
     p = ab.Planner(T=128)
