@@ -102,6 +102,9 @@ struct Scratch {
     double thr_sq;    // largest x with RN(sqrt(x)) <= thr: "norm <= thr" is tested as "squared norm <= thr_sq", exactly
     int* gerr;        // global error word
     int iscan[18];         // per-warp scan totals (<= 16 warps); [17] is a group-uniform flag (group_ready)
+#ifdef ARMOUR_KEYHASH
+    int dbg_work, dbg_seq;   // measurement build: work item and running operation number (see g_keyhash)
+#endif
     __device__ __forceinline__ u64* skey(int b) const { return (u64*)__cvta_shared_to_generic((size_t)skey_a[b]); }
     __device__ __forceinline__ u16* sidx(int b) const { return (u16*)__cvta_shared_to_generic((size_t)sidx_a[b]); }
     __device__ __forceinline__ double* stmp() const { return (double*)__cvta_shared_to_generic((size_t)stmp_a); }
@@ -451,6 +454,22 @@ struct ScalarEpilogue {
 
 // Shared tail of every operation: compaction of the kept keys (blocked ranges keep the order), block-wide radius sums,
 // descriptor update.  key / flag / tmp are indexed by sorted candidate position; one barrier inside, one at the end.
+#ifdef ARMOUR_KEYHASH
+// Measurement build (scripts/keyhash_experiment.py): per (work item, operation number) a hash of the RESULT's key list and the
+// candidate count, to measure how often consecutive intervals of one problem produce identical key lists (the condition under
+// which a cached sort order of the previous interval could be reused).
+constexpr int KEYHASH_OPS = 512, KEYHASH_WORK = 512;
+__device__ u64 g_keyhash[KEYHASH_WORK][KEYHASH_OPS][2];
+template <int NT, int D>
+__device__ __forceinline__ void keyhash_record(Scratch& S, const PZ<D>& dst, int N, int total) {
+    if (gtid<NT>() == 0) {
+        u64 hsh = 1469598103934665603ull ^ (u64)total;
+        for (int i = 0; i < total; i++) hsh = (hsh ^ dst.keys[i]) * 1099511628211ull;
+        if (S.dbg_work < KEYHASH_WORK && S.dbg_seq < KEYHASH_OPS) { g_keyhash[S.dbg_work][S.dbg_seq][0] = hsh; g_keyhash[S.dbg_work][S.dbg_seq][1] = (u64)N; }
+        S.dbg_seq++;
+    }
+}
+#endif
 template <int NT, int DOUT>
 __device__ __forceinline__ void compact_emit(Scratch& S, int N, const u64* key, const u16* flag, const double* tmp, int ncap, const double (&red)[2 * DOUT],
                                              const ScalarEpilogue<NT, DOUT>& se, PZ<DOUT>& dst) {
@@ -480,6 +499,9 @@ __device__ __forceinline__ void compact_emit(Scratch& S, int N, const u64* key, 
     TR(6);
     gsync<NT>();
     TR(7);
+#ifdef ARMOUR_KEYHASH
+    keyhash_record<NT, DOUT>(S, dst, N, total);
+#endif
     phase_mark(PH_COMPACT);
 }
 

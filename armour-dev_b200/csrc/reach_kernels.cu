@@ -707,6 +707,9 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
         const int prob = work / tb.T, s = work - prob * tb.T;
         const size_t rec0 = ((size_t)prob * tb.T + s) * NJ;
         if (threadIdx.x == 0) { sig_la = 0; sig_state = 0; sig_force = 0; sig_side = 0; sig_u = 0; fk_next_s = 0; fk_lock_s = 0; }
+#ifdef ARMOUR_KEYHASH
+        if (threadIdx.x == 0) for (int k = 0; k < GROUPS; k++) { SS[k].dbg_work = work; SS[k].dbg_seq = 0; }
+#endif
         __syncthreads();
         // ---- stage A: joint reach sets (one thread per joint; tiny scalar work) -------------------
         if (threadIdx.x < NJ) {
@@ -1019,6 +1022,12 @@ cudaError_t launch_pz_binary(int op, const FlatPZ& a, const FlatPZ& b, const Fla
 }
 
 // profiling builds only: cycles and call counts per phase, summed over CTAs (zeros otherwise)
+#ifdef ARMOUR_KEYHASH
+extern "C" int armour_debug_keyhash(unsigned long long* out, int work_items) {   // out[work][KEYHASH_OPS][2]
+    if (work_items > KEYHASH_WORK) work_items = KEYHASH_WORK;
+    return (int)cudaMemcpyFromSymbol(out, g_keyhash, sizeof(u64) * (size_t)work_items * KEYHASH_OPS * 2);
+}
+#endif
 void read_phase_cycles(unsigned long long* cycles, unsigned long long* calls, bool reset) {
 #ifdef ARMOUR_PHASE_TIMING
     cudaMemcpyFromSymbol(cycles, armour_phase_cycles, sizeof(unsigned long long) * PH_COUNT);
