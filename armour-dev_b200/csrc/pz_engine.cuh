@@ -470,6 +470,9 @@ __device__ __forceinline__ void keyhash_record(Scratch& S, const PZ<D>& dst, int
     }
 }
 #endif
+#ifndef ARMOUR_PREFETCH_DST
+#define ARMOUR_PREFETCH_DST 0
+#endif
 template <int NT, int DOUT>
 __device__ __forceinline__ void compact_emit(Scratch& S, int N, const u64* key, const u16* flag, const double* tmp, int ncap, const double (&red)[2 * DOUT],
                                              const ScalarEpilogue<NT, DOUT>& se, PZ<DOUT>& dst) {
@@ -494,6 +497,14 @@ __device__ __forceinline__ void compact_emit(Scratch& S, int N, const u64* key, 
                 off++;
             }
         }
+#if ARMOUR_PREFETCH_DST
+        // stores go through to L2; pull the lines just written into L1, where the next operation (usually the consumer) reads them
+        if (cnt > 0) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(dk + off - 1));
+#pragma unroll
+            for (int c = 0; c < DOUT; c++) asm volatile("prefetch.global.L1 [%0];" ::"l"(dc + c * dcap + off - 1));
+        }
+#endif
     }
     se.finish(S, dst, N, total);
     TR(6);
