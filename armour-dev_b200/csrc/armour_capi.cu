@@ -142,6 +142,7 @@ struct armour_handle {
     double *a_g = nullptr, *a_jac = nullptr;       // device aliases of the pinned staging buffers h_g / h_jac
     double *d_bx = nullptr, *d_bg = nullptr, *d_bjac = nullptr, *h_bx = nullptr;   // armour_eval_batch: decision vectors and result rows of a whole batch
     size_t bx_cap = 0, bg_cap = 0, bjac_cap = 0;
+    bool fuse_planes = false;  // ARMOUR_TUNE_FUSE_PLANES=1: stage D inside reach_build_kernel instead of the separate hyperplane_kernel launch
     float batch_eval_ms = 0;
     int eval_bps_host = 0;                         // resident blocks per SM of the constraint kernel when it writes to host memory (waves overlap compute and PCIe)
     bool eval_timed = false;                       // events of the last evaluation are pending in ev[3], ev[4]
@@ -213,11 +214,13 @@ int run_build(armour_handle* h) {   // kernels only; inputs already on the devic
         tb.u_keys = h->tb.u_keys; tb.u_coef = h->tb.u_coef; tb.l_keys = h->tb.l_keys; tb.l_coef = h->tb.l_coef; tb.ucap = h->tb.ucap; tb.lcap = h->tb.lcap;
         CU(cudaMemsetAsync(h->d_err, 0, 3 * sizeof(int), h->stream));   // error word, work counter, guard words verified
         CU(cudaEventRecord(h->ev[0], h->stream));
+        // opt-in experiment: stage D in the tail of each interval's CTA (no second launch) when its staging fits the CTA's sort buffers
+        tb.fuse_planes = (h->fuse_planes && (size_t)(NJ * 18 + 12 * h->n_obs) * sizeof(double) <= (size_t)h->scap * 20) ? 1 : 0;
         CU(launch_reach_build(tb, h->arena, h->arena_stride, h->mcap, h->ncap, h->scap, h->tcap, n_work, std::min(h->grid, n_work), h->nt, h->minb, h->groups, h->stream));
         CU(cudaEventRecord(h->ev[1], h->stream));
-        CU(launch_hyperplanes(tb, h->stream));
+        if (!tb.fuse_planes) CU(launch_hyperplanes(tb, h->stream));
         CU(cudaEventRecord(h->ev[2], h->stream));
-        h->launches += (h->n_obs > 0) ? 2 : 1;
+        h->launches += (h->n_obs > 0 && !tb.fuse_planes) ? 2 : 1;
         CU(cudaMemcpyAsync(h->h_err, h->d_err, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaMemcpyAsync(h->h_torque_radius, h->tb.torque_radius, sizeof(double) * (size_t)h->count * h->T * NF, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -418,6 +421,7 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     armour_handle* h = new armour_handle();
     h->cfg = cfg;
     bool no_structured_env = false;
+    bool fuse_planes_env = false;   // measured: no gain for one plan (the ~20 us move into the reach kernel's tail), -4.5 % on the sweep
     if (cfg.device >= 0) { if (cudaSetDevice(cfg.device) != cudaSuccess) { delete h; return fail(ARMOUR_E_CUDA, "cudaSetDevice failed"); } }
     cudaGetDevice(&h->device);
     cudaDeviceProp prop;
@@ -440,6 +444,7 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     if (const char* e = getenv("ARMOUR_TUNE_MCAP")) h->mcap = std::max(64, atoi(e));
     if (const char* e = getenv("ARMOUR_TUNE_EVAL_BPS")) h->eval_bps_host = atoi(e);
     if (const char* e = getenv("ARMOUR_TUNE_NO_STRUCTURED")) no_structured_env = atoi(e) != 0;
+    if (const char* e = getenv("ARMOUR_TUNE_FUSE_PLANES")) fuse_planes_env = atoi(e) != 0;
     if (const char* e = getenv("ARMOUR_TUNE_HOST_WRITE")) h->host_write = std::min(2, std::max(0, atoi(e)));
     {
         void* fn = nullptr;
@@ -469,6 +474,7 @@ int armour_create(const armour_config* cfg_in, armour_handle** out) {
     for (int i = 0; i < NF; i++) tb.k_range[i] = cfg.k_range[i];
     tb.mass_unc = cfg.mass_uncertainty; tb.inertia_unc = cfg.inertia_uncertainty; tb.thr = cfg.simplify_threshold;
     tb.no_structured = no_structured_env ? 1 : 0;
+    h->fuse_planes = fuse_planes_env;
     if (const char* e = getenv("ARMOUR_TUNE_STATIC_STRIDE")) tb.static_stride = atoi(e) != 0;
     CU(dalloc(&h->d_state, P * 21)); CU(dalloc(&h->d_obs, P * O * 12));
     CU(dalloc(&h->d_jrs, (size_t)6 * NF * T)); CU(dalloc(&h->d_krange, (size_t)NF));

@@ -43,6 +43,7 @@ struct Tables {
     int ucap, lcap;            // capacities of the k-only monomial tables below
     int static_stride;         // 1: persistent CTAs take work items blockIdx + k * gridDim instead of a shared counter (experiments)
     int no_structured;         // 1: every product takes the generic sort path (A/B measurements; ARMOUR_TUNE_NO_STRUCTURED)
+    int fuse_planes;           // 1: reach_build_kernel also writes the interval's half-space tables (stage D) instead of a separate hyperplane_kernel launch
     double k_range[NF];
     double mass_unc, inertia_unc, thr;
     // inputs

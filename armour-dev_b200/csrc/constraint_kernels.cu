@@ -8,6 +8,7 @@
 //                           (KPR/Trajectory.cu:256-540), one launch per Ipopt iteration.
 #include <algorithm>
 #include "armour_types.cuh"
+#include "hyperplane.cuh"
 
 namespace armour {
 
@@ -15,11 +16,6 @@ typedef unsigned long long u64;
 
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
-
-// pair (a, b), a < b, of the 9 buffered generators in the reference's enumeration order
-// (KPR/CollisionChecking.cu:26-39): (0,1) (0,2) ... (0,8) (1,2) ... (7,8)
-__constant__ unsigned char c_pair_a[COMB] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 6, 6, 7};
-__constant__ unsigned char c_pair_b[COMB] = {1, 2, 3, 4, 5, 6, 7, 8, 2, 3, 4, 5, 6, 7, 8, 3, 4, 5, 6, 7, 8, 4, 5, 6, 7, 8, 5, 6, 7, 8, 6, 7, 8, 7, 8, 8};
 
 // One block per (problem, t, link, group of 8 obstacles), one thread per (obstacle, pair) plane: no loops, no 64-bit index
 // arithmetic (the round-1 kernel decomposed a flat 64-bit index with five 64-bit divisions per thread).  The nine buffered
@@ -45,22 +41,7 @@ __global__ void __launch_bounds__(HYPER_NT) hyperplane_kernel(Tables tb) {
     __syncthreads();
     const int p = threadIdx.x % COMB, ol = threadIdx.x / COMB;
     if (ol >= n_here) return;
-    const int ia = c_pair_a[p], ib = c_pair_b[p];
-    const double ga0 = G[ol][ia][0], ga1 = G[ol][ia][1], ga2 = G[ol][ia][2];
-    const double gb0 = G[ol][ib][0], gb1 = G[ol][ib][1], gb2 = G[ol][ib][2];
-    const double cr0 = dadd(dmul(ga1, gb2), -dmul(ga2, gb1));
-    const double cr1 = dadd(dmul(ga2, gb0), -dmul(ga0, gb2));
-    const double cr2 = dadd(dmul(ga0, gb1), -dmul(ga1, gb0));
-    const double nrm = __dsqrt_rn(dadd(dadd(dmul(cr0, cr0), dmul(cr1, cr1)), dmul(cr2, cr2)));
-    double C0 = 0, C1 = 0, C2 = 0;
-    if (nrm > 0) { C0 = __ddiv_rn(cr0, nrm); C1 = __ddiv_rn(cr1, nrm); C2 = __ddiv_rn(cr2, nrm); }
-    const size_t idx = (rec * n_obs + o_base + ol) * COMB + p;
-    tb.A[idx * 3 + 0] = C0; tb.A[idx * 3 + 1] = C1; tb.A[idx * 3 + 2] = C2;
-    tb.d[idx] = dadd(dadd(dmul(C0, cen[ol][0]), dmul(C1, cen[ol][1])), dmul(C2, cen[ol][2]));
-    double dl = 0.0;
-#pragma unroll
-    for (int j = 0; j < 9; j++) dl = dadd(dl, fabs(dadd(dadd(dmul(C0, G[ol][j][0]), dmul(C1, G[ol][j][1])), dmul(C2, G[ol][j][2]))));
-    tb.delta[idx] = dl;
+    write_half_space(tb, (rec * n_obs + o_base + ol) * COMB + p, &G[ol][0][0], &G[ol][3][0], cen[ol], p);
 }
 
 // ---- Bezier curve pieces used by the limit rows (KPR/Trajectory.cu:542-599) -----------------------

@@ -14,6 +14,7 @@
 #include "armour_launch.h"
 #include "pz_engine.cuh"
 #include "interval.cuh"
+#include "hyperplane.cuh"
 
 namespace armour {
 
@@ -894,6 +895,8 @@ __global__ void __launch_bounds__(NT * GROUPS, MINB) reach_build_kernel(Tables t
                 }
             }
         }
+        // ---- stage D fused: this interval's half-space tables, from the generator blocks stage B just exported -----------
+        if (tb.fuse_planes && tb.n_obs > 0) interval_half_spaces(tb, prob, rec0, reinterpret_cast<double*>(smem_raw + COLD_SMEM));
         if (threadIdx.x == 0) next_work = tb.static_stride ? work + (int)gridDim.x : (int)gridDim.x + atomicAdd(tb.err + 1, 1);
         __syncthreads();
     }

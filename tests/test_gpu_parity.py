@@ -221,6 +221,32 @@ def test_eval_batch_equals_single_evals(gpu_lib, pin):
     pb.close()
 
 
+def test_fused_half_space_tables_equal_the_separate_kernel(gpu_lib, monkeypatch):
+    """Stage D is its own launch (hyperplane_kernel); ARMOUR_TUNE_FUSE_PLANES=1 runs it in the tail of reach_build_kernel
+    instead (opt-in, measured not faster).  Same per-plane code: A, d, delta bit-identical, for one plan (two thread groups)
+    and for a batch."""
+    q0, qd0, qdd0, _, obs = make_problem(52, 20)
+    p0 = ab.Planner(T=32)
+    p0.build(q0, qd0, qdd0, obs)
+    probs = [make_problem(s, 7) for s in (61, 62, 63)]
+    args = [np.concatenate([q[k] for q in probs]) for k in (0, 1, 2, 4)]
+    b0 = ab.Planner(T=16, batch=3)
+    b0.build_batch(*args, 7)
+    monkeypatch.setenv("ARMOUR_TUNE_FUSE_PLANES", "1")
+    p1 = ab.Planner(T=32)
+    p1.build(q0, qd0, qdd0, obs)
+    b1 = ab.Planner(T=16, batch=3)
+    b1.build_batch(*args, 7)
+    assert p0.kernel_launches() == p1.kernel_launches() + 1
+    for x, y in zip(p1.hyperplanes(), p0.hyperplanes()):
+        assert x.size > 0 and np.array_equal(x, y)
+    for i in range(3):
+        b0.select_problem(i); b1.select_problem(i)
+        for x, y in zip(b1.hyperplanes(), b0.hyperplanes()):
+            assert np.array_equal(x, y)
+        assert np.array_equal(b1.eval_g(DEBUG_K), b0.eval_g(DEBUG_K))
+
+
 def test_build_is_deterministic(gpu_lib):
     q0, qd0, qdd0, _, obs = make_problem(21, 10)
     p = ab.Planner(T=128)
