@@ -23,7 +23,7 @@ PZ_OPS = {"mul": 0, "add": 1, "sub": 2, "cross": 3, "simplify": 4, "add_one_dim0
 EXPORTS = [
     "armour_default_config", "armour_create", "armour_destroy", "armour_last_error", "armour_build", "armour_build_batch",
     "armour_select_problem", "armour_build_armtd", "armour_get_nlp_info", "armour_get_bounds_info", "armour_get_starting_point", "armour_eval_f",
-    "armour_eval_grad_f", "armour_eval_g", "armour_eval_jac_g", "armour_eval_g_jac", "armour_jac_structure", "armour_release_host_buffers", "armour_check_feasible",
+    "armour_eval_grad_f", "armour_eval_g", "armour_eval_jac_g", "armour_eval_g_jac", "armour_jac_structure", "armour_release_host_buffers", "armour_pinned_buffer_count", "armour_check_feasible",
     "armour_get_torque_radius", "armour_get_link_generators", "armour_get_link_sliced_center", "armour_get_hyperplanes",
     "armour_get_taylor_remainders", "armour_get_pz", "armour_pz_binary", "armour_last_build_ms", "armour_last_eval_ms",
     "armour_kernel_launches", "armour_set_kernel_timing", "armour_last_eval_host_us", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_eval_resident_burst", "armour_eval_batch", "armour_last_eval_batch_ms", "armour_upload_x", "armour_standin_solve", "armour_debug_phase_cycles", "armour_debug_canaries_verified", "armour_measure_fp64_peak",
@@ -308,6 +308,11 @@ class Planner:
     def last_eval_batch_ms(self):
         v = C.c_float()
         self._ck(self.L.armour_last_eval_batch_ms(self.h, C.byref(v)))
+        return v.value
+
+    def pinned_buffer_count(self):
+        v = C.c_int()
+        self._ck(self.L.armour_pinned_buffer_count(self.h, C.byref(v)))
         return v.value
 
     def eval_resident_burst(self, x, launches=20):

@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 using namespace armour;
@@ -348,9 +349,12 @@ void* pinned_alias(armour_handle* h, void* host, size_t bytes, const void* keep 
         cudaHostUnregister((void*)h->pinned[victim].host); cudaGetLastError();
         h->pinned.erase(h->pinned.begin() + victim);
     }
-    if (cudaHostRegister(host, bytes, cudaHostRegisterMapped) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    static const bool debug = getenv("ARMOUR_DEBUG_PINNING") != nullptr;
+    cudaError_t e = cudaHostRegister(host, bytes, cudaHostRegisterMapped);
+    if (e != cudaSuccess) { if (debug) fprintf(stderr, "armour: cudaHostRegister(%p, %zu): %s\n", host, bytes, cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
     void* dev = nullptr;
-    if (cudaHostGetDevicePointer(&dev, host, 0) != cudaSuccess) { cudaGetLastError(); cudaHostUnregister(host); return nullptr; }
+    e = cudaHostGetDevicePointer(&dev, host, 0);
+    if (e != cudaSuccess) { if (debug) fprintf(stderr, "armour: cudaHostGetDevicePointer(%p): %s\n", host, cudaGetErrorString(e)); cudaGetLastError(); cudaHostUnregister(host); return nullptr; }
     h->pinned.push_back({host, bytes, dev});
     return dev;
 }
@@ -624,6 +628,11 @@ int armour_eval_grad_f(armour_handle* h, const double* q_des, double t_plan, con
     }
     return ARMOUR_OK;
 }
+int armour_pinned_buffer_count(armour_handle* h, int* count) {
+    if (!h || !count) return fail(ARMOUR_E_INVALID, "null argument");
+    *count = (int)h->pinned.size();
+    return ARMOUR_OK;
+}
 int armour_release_host_buffers(armour_handle* h) {
     if (!h) return fail(ARMOUR_E_INVALID, "null argument");
     cudaSetDevice(h->device);
@@ -696,6 +705,20 @@ int armour_eval_resident_burst(armour_handle* h, const double* x, int launches, 
     h->eval_timed = false;
     return ARMOUR_OK;
 }
+// Device -> caller array.  A direct copy fails ("invalid argument") when part of the destination is still page-locked by a
+// stale registration — memory that some handle registered under cfg.pin_user_buffers and the caller freed without
+// armour_release_host_buffers; in that case the rows go through the handle's own pinned staging buffer in pieces.
+static int copy_out(armour_handle* h, double* dst, const double* src_dev, size_t bytes) {
+    if (cudaMemcpy(dst, src_dev, bytes, cudaMemcpyDeviceToHost) == cudaSuccess) return ARMOUR_OK;
+    cudaGetLastError();
+    const size_t piece = sizeof(double) * (size_t)m_of(h) * NF;   // capacity of h_jac for the current problem shape
+    for (size_t off = 0; off < bytes; off += piece) {
+        const size_t nb = std::min(piece, bytes - off);
+        CU(cudaMemcpy(h->h_jac, (const char*)src_dev + off, nb, cudaMemcpyDeviceToHost));
+        memcpy((char*)dst + off, h->h_jac, nb);
+    }
+    return ARMOUR_OK;
+}
 // One launch for `count` problems of the last batch build, problem y evaluated at x[y][0..6]: the call a batched solver (or a
 // sweep that steps all its solvers in lockstep) makes once per iteration.  Rows of problem first + y go to g + y * m and
 // values + y * 7 m (either may be NULL).  With cfg.pin_user_buffers the kernel writes the caller's arrays; otherwise the rows
@@ -737,9 +760,9 @@ int armour_eval_batch(armour_handle* h, int first, int count, const double* x, d
     CU(cudaEventRecord(h->ev[3], h->stream));
     CU(launch_constraint_eval_batch(tb, first, count, h->d_bx, kg, kj, nullptr, what, h->stream));
     CU(cudaEventRecord(h->ev[4], h->stream));
-    if (copy_g) CU(cudaMemcpyAsync(g, h->d_bg, sizeof(double) * n * m, cudaMemcpyDeviceToHost, h->stream));
-    if (copy_j) CU(cudaMemcpyAsync(values, h->d_bjac, sizeof(double) * n * m * NF, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (copy_g) { int rc = copy_out(h, g, h->d_bg, sizeof(double) * n * m); if (rc != ARMOUR_OK) return rc; }
+    if (copy_j) { int rc = copy_out(h, values, h->d_bjac, sizeof(double) * n * m * NF); if (rc != ARMOUR_OK) return rc; }
     h->launches += 1;
     cudaEventElapsedTime(&h->batch_eval_ms, h->ev[3], h->ev[4]);
     h->have_eval = false;          // the single-problem staging buffers and link_sliced_center were not touched
@@ -960,11 +983,20 @@ int armour_standin_solve(armour_handle* h, const double* q_des, double t_plan, d
     nlp.set_time_steps(h->T);
     if (!nlp.set_parameters(q_des, t_plan, h)) return fail(ARMOUR_E_STATE, "set_parameters failed");
     // the solver's own g / Jacobian vectors live for the whole solve: page-lock them so that every callback is a direct write
+    // ... and unregister exactly those afterwards: they are freed when the solver returns, and a registration left behind on
+    // freed heap memory makes a later registration of whatever the allocator places there fail ("already mapped")
     const int saved_pin = h->cfg.pin_user_buffers;
+    std::vector<const void*> before;
+    for (auto& e : h->pinned) before.push_back(e.host);
     h->cfg.pin_user_buffers = 1;
     StandinResult r = standin_solve(nlp, k_opt);
     h->cfg.pin_user_buffers = saved_pin;
-    if (!saved_pin) armour_release_host_buffers(h);
+    for (size_t i = h->pinned.size(); i-- > 0;) {
+        if (std::find(before.begin(), before.end(), (const void*)h->pinned[i].host) != before.end()) continue;
+        cudaHostUnregister((void*)h->pinned[i].host);
+        h->pinned.erase(h->pinned.begin() + i);
+    }
+    cudaGetLastError();
     if (feasible) *feasible = nlp.feasible ? 1 : 0;
     if (iterations) *iterations = r.iterations;
     if (evaluations) *evaluations = r.evaluations;

@@ -119,6 +119,9 @@ int armour_eval_g_jac(armour_handle* h, const double* x, double* g, double* valu
 int armour_jac_structure(armour_handle* h, int* iRow, int* jCol);
 /* undo the page-locking done under cfg.pin_user_buffers (call before freeing those arrays) */
 int armour_release_host_buffers(armour_handle* h);
+/* caller arrays currently page-locked by this handle (cfg.pin_user_buffers); arrays that the library itself pinned for the
+ * duration of a call (armour_standin_solve) are released before that call returns */
+int armour_pinned_buffer_count(armour_handle* h, int* count);
 /* armtd_NLP::finalize_solution's feasibility re-check (:446-537): *feasible = 1 or 0 */
 int armour_check_feasible(armour_handle* h, const double* g, int* feasible);
 

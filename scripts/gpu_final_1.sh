@@ -16,3 +16,7 @@ python scripts/run_sweep.py --problems 1024 --batch 256 > gpurun_out/r2_sweep_st
 python scripts/run_sweep.py --problems 4096 --batch 256 --no-solve > gpurun_out/r2_sweep_nosolve_1gpu.json 2>&1
 python scripts/tune_sweep.py 256 10 > gpurun_out/r2_tune_sweep.log 2>&1
 tail -n 2 gpurun_out/r2_episode.json gpurun_out/r2_sweep_standin_1gpu.json gpurun_out/r2_sweep_nosolve_1gpu.json; cat gpurun_out/r2_tune_sweep.log
+# sweep shape: plain run, then one full capture of the batched reach kernel (16 problems x 128 intervals)
+python scripts/tune_sweep.py one 16 10 > gpurun_out/f1_sweep_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:reach_build -s 1 -c 1 -o gpurun_out/r2_final_sweep python scripts/tune_sweep.py one 16 10 > gpurun_out/f1_ncu3.log 2>&1
+python scripts/phase_timing.py sweep > /dev/null 2>&1 || true

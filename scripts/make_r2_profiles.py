@@ -13,12 +13,14 @@ def source_digest():
     h = hashlib.sha256()
     d = os.path.join(ROOT, "armour-dev_b200", "csrc")
     for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh", ".h")):
+        if name.endswith((".cu", ".cuh", ".h")) and name != "armour_capi.cu":   # device code only: the host-side C ABI file does not change the kernels
             h.update(open(os.path.join(d, name), "rb").read())
     return h.hexdigest()[:16]
 
 
 rep = os.path.join(G, "r2_final.ncu-rep")
+if not os.path.exists(rep):
+    rep = os.path.join(ROOT, "ncu_raw", "r2_final.ncu-rep")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[0]
@@ -39,8 +41,9 @@ traffic = {"source": "profiles/r2_ncu_full_summary.csv (ncu --set full --clock-c
 ir, iw, iu = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), None
 units = rows[1]
 scale = lambda u: {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+ik = hdr.index("Kernel Name")
 for r in rows[2:]:
-    name = "reach_build_kernel" if "reach_build" in r[0] else "constraint_eval_kernel" if "constraint_eval" in r[0] else "hyperplane_kernel" if "hyperplane" in r[0] else None
+    name = "reach_build_kernel" if "reach_build" in r[ik] else "constraint_eval_kernel" if "constraint_eval" in r[ik] else "hyperplane_kernel" if "hyperplane" in r[ik] else None
     if name:
         traffic[name] = float(r[ir].replace(",", "")) * scale(units[ir]) + float(r[iw].replace(",", "")) * scale(units[iw])
 json.dump(traffic, open(os.path.join(P, "r2_traffic.json"), "w"), indent=1)
