@@ -26,7 +26,7 @@ EXPORTS = [
     "armour_eval_grad_f", "armour_eval_g", "armour_eval_jac_g", "armour_eval_g_jac", "armour_jac_structure", "armour_release_host_buffers", "armour_pinned_buffer_count", "armour_check_feasible",
     "armour_get_torque_radius", "armour_get_link_generators", "armour_get_link_sliced_center", "armour_get_hyperplanes",
     "armour_get_taylor_remainders", "armour_get_pz", "armour_pz_binary", "armour_last_build_ms", "armour_last_eval_ms",
-    "armour_kernel_launches", "armour_set_kernel_timing", "armour_last_eval_host_us", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_eval_resident_burst", "armour_eval_batch", "armour_last_eval_batch_ms", "armour_upload_x", "armour_standin_solve", "armour_debug_phase_cycles", "armour_debug_canaries_verified", "armour_measure_fp64_peak",
+    "armour_kernel_launches", "armour_set_kernel_timing", "armour_last_eval_host_us", "armour_upload_problems", "armour_build_resident", "armour_eval_resident", "armour_eval_resident_burst", "armour_eval_batch", "armour_last_eval_batch_ms", "armour_eval_batch_resident", "armour_batch_jacobian_device", "armour_get_batch_jacobian", "armour_upload_x", "armour_standin_solve", "armour_debug_phase_cycles", "armour_debug_canaries_verified", "armour_measure_fp64_peak",
 ]
 
 
@@ -304,6 +304,18 @@ class Planner:
         assert values is None or (values.dtype == np.float64 and values.flags.c_contiguous and values.size == n * m * 7)
         self._ck(self.L.armour_eval_batch(self.h, C.c_int(first), C.c_int(n), _dp(xs), _dp(g), _dp(values) if values is not None else None))
         return (g, values) if values is not None else g
+
+    def eval_batch_resident(self, xs, g=None, first=0):
+        """eval_batch with the Jacobians left on the device (armour_eval_batch_resident); g: (count, m) array or None."""
+        xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(-1, 7)
+        assert g is None or (g.dtype == np.float64 and g.flags.c_contiguous and g.size == xs.shape[0] * self.m)
+        self._ck(self.L.armour_eval_batch_resident(self.h, C.c_int(first), C.c_int(xs.shape[0]), _dp(xs), _dp(g) if g is not None else None))
+        return g
+
+    def get_batch_jacobian(self, y):
+        v = np.zeros(self.m * 7)
+        self._ck(self.L.armour_get_batch_jacobian(self.h, C.c_int(y), _dp(v)))
+        return v
 
     def last_eval_batch_ms(self):
         v = C.c_float()

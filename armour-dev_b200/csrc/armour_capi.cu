@@ -142,7 +142,7 @@ struct armour_handle {
     double eval_host_us = 0.0;                     // wall-clock time spent inside the last evaluation call
     double *a_g = nullptr, *a_jac = nullptr;       // device aliases of the pinned staging buffers h_g / h_jac
     double *d_bx = nullptr, *d_bg = nullptr, *d_bjac = nullptr, *h_bx = nullptr;   // armour_eval_batch: decision vectors and result rows of a whole batch
-    size_t bx_cap = 0, bg_cap = 0, bjac_cap = 0;
+    size_t bx_cap = 0, bg_cap = 0, bjac_cap = 0, bjac_rows = 0;   // bjac_rows: problems whose Jacobian the last batched evaluation left in d_bjac
     bool fuse_planes = false;  // ARMOUR_TUNE_FUSE_PLANES=1: stage D inside reach_build_kernel instead of the separate hyperplane_kernel launch
     float batch_eval_ms = 0;
     int eval_bps_host = 0;                         // resident blocks per SM of the constraint kernel when it writes to host memory (waves overlap compute and PCIe)
@@ -723,14 +723,14 @@ static int copy_out(armour_handle* h, double* dst, const double* src_dev, size_t
 // sweep that steps all its solvers in lockstep) makes once per iteration.  Rows of problem first + y go to g + y * m and
 // values + y * 7 m (either may be NULL).  With cfg.pin_user_buffers the kernel writes the caller's arrays; otherwise the rows
 // pass through device buffers and one copy each.
-int armour_eval_batch(armour_handle* h, int first, int count, const double* x, double* g, double* values) {
-    if (!h || !x || (!g && !values)) return fail(ARMOUR_E_INVALID, "null argument");
+static int eval_batch_impl(armour_handle* h, int first, int count, const double* x, double* g, double* values, bool jac_resident) {
+    if (!h || !x || (!g && !values && !jac_resident)) return fail(ARMOUR_E_INVALID, "null argument");
     if (!h->built) return fail(ARMOUR_E_STATE, "eval before build");
     if (first < 0 || count < 1 || first + count > h->count) return fail(ARMOUR_E_INVALID, "problem range outside the last batch build");
     CU(cudaSetDevice(h->device));
     NvtxRange range("armour_eval_batch");
     const size_t m = (size_t)m_of(h), n = (size_t)count;
-    const int what = (g ? 1 : 0) | (values ? 2 : 0);
+    const int what = (g ? 1 : 0) | ((values || jac_resident) ? 2 : 0);
     if (h->bx_cap < n) {
         if (h->d_bx) cudaFree(h->d_bx);
         if (h->h_bx) cudaFreeHost(h->h_bx);
@@ -749,7 +749,7 @@ int armour_eval_batch(armour_handle* h, int first, int count, const double* x, d
         if (h->bg_cap < n * m) { if (h->d_bg) cudaFree(h->d_bg); h->d_bg = nullptr; h->bg_cap = 0; CU(dalloc(&h->d_bg, n * m)); h->bg_cap = n * m; }
         kg = h->d_bg;
     }
-    if (copy_j) {
+    if (copy_j || jac_resident) {
         if (h->bjac_cap < n * m * NF) { if (h->d_bjac) cudaFree(h->d_bjac); h->d_bjac = nullptr; h->bjac_cap = 0; CU(dalloc(&h->d_bjac, n * m * NF)); h->bjac_cap = n * m * NF; }
         kj = h->d_bjac;
     }
@@ -766,7 +766,30 @@ int armour_eval_batch(armour_handle* h, int first, int count, const double* x, d
     h->launches += 1;
     cudaEventElapsedTime(&h->batch_eval_ms, h->ev[3], h->ev[4]);
     h->have_eval = false;          // the single-problem staging buffers and link_sliced_center were not touched
+    h->bjac_rows = (jac_resident || copy_j) ? n : 0;
     return ARMOUR_OK;
+}
+int armour_eval_batch(armour_handle* h, int first, int count, const double* x, double* g, double* values) {
+    if (!g && !values) return fail(ARMOUR_E_INVALID, "null argument");
+    return eval_batch_impl(h, first, count, x, g, values, false);
+}
+// Same launch with the Jacobians left on the device (count x 7 m doubles, problem-major) for a device-side consumer; only the
+// constraint values (8 m bytes per problem instead of 64 m) cross PCIe.  g may be NULL.
+int armour_eval_batch_resident(armour_handle* h, int first, int count, const double* x, double* g) {
+    return eval_batch_impl(h, first, count, x, g, nullptr, true);
+}
+int armour_batch_jacobian_device(armour_handle* h, const double** values_dev, int* problems) {
+    if (!h || !values_dev || !problems) return fail(ARMOUR_E_INVALID, "null argument");
+    *values_dev = h->bjac_rows ? h->d_bjac : nullptr;
+    *problems = (int)h->bjac_rows;
+    return ARMOUR_OK;
+}
+int armour_get_batch_jacobian(armour_handle* h, int y, double* values) {
+    if (!h || !values) return fail(ARMOUR_E_INVALID, "null argument");
+    if (y < 0 || (size_t)y >= h->bjac_rows) return fail(ARMOUR_E_STATE, "no device-resident Jacobian for that problem (armour_eval_batch_resident first)");
+    CU(cudaSetDevice(h->device));
+    const size_t mj = (size_t)m_of(h) * NF;
+    return copy_out(h, values, h->d_bjac + (size_t)y * mj, sizeof(double) * mj);
 }
 int armour_last_eval_batch_ms(armour_handle* h, float* ms) {
     if (!h || !ms) return fail(ARMOUR_E_INVALID, "null argument");

@@ -245,7 +245,7 @@ def run_reference(args):
     _emit(json.dumps(line))
 
 
-def run_sweep_config3(ab, dist, torch, rank, world, local_rank):
+def run_sweep_config3(ab, dist, torch, rank, world, local_rank, jac_to_host=False):
     """BASELINE.json configs[2] / SURVEY.md §8e: 4096 independent problems, block-sharded, one all_gather of result records.
     Timed on the wall clock from the first upload to the end of the collective; max over ranks."""
     from armour_b200 import sweep
@@ -274,8 +274,12 @@ def run_sweep_config3(ab, dist, torch, rank, world, local_rank):
         stats["eval_dev_ms"] += pb.last_eval_batch_ms()
         for row in range(n):
             out[row, 7] = float(pb.check_feasible(G[row]))
-        for _ in range(SWEEP_EVALS - 1):                     # further iterations: constraints AND Jacobians to the host (no solver in the loop: Ipopt is absent)
-            pb.eval_batch(rng.uniform(-1, 1, (n, 7)), g=G[:n], values=V[:n])
+        for _ in range(SWEEP_EVALS - 1):                     # further iterations (no solver in the loop: Ipopt is absent)
+            xs_it = rng.uniform(-1, 1, (n, 7))
+            if jac_to_host:
+                pb.eval_batch(xs_it, g=G[:n], values=V[:n])  # constraints AND Jacobians to the host: a host-side solver's iteration (64 m bytes per problem)
+            else:
+                pb.eval_batch_resident(xs_it, g=G[:n])       # constraints to the host, Jacobians stay on the device: a device-side solver's iteration
             stats["eval_dev_ms"] += pb.last_eval_batch_ms()
         out[:, 8] = pb.last_build_ms()[0] / n
         out[:, 10] = SWEEP_EVALS
@@ -307,7 +311,8 @@ def run_sweep_config3(ab, dist, torch, rank, world, local_rank):
             "device_builds_per_s": world * per_rank / (dev_ms * 1e-3),
             "slowest_rank": {"build_device_s": dev_ms * 1e-3, "build_wall_s": bw, "eval_wall_s": ew, "eval_device_s": edev * 1e-3, "other_s": max(0.0, wall - bw - ew)},
             "feasible_at_k0": int(np.nansum(res[:, 7])), "collective": "one all_gather of %d x %d doubles" % (SWEEP_PROBLEMS, sweep.RECORD_WIDTH),
-            "note": "no solver in the loop (Ipopt is not installed): per batch one armour_eval_batch launch for g at k = 0 and %d launches for g + Jacobian at random k, all rows written to page-locked host arrays" % (SWEEP_EVALS - 1)}
+            "jacobian": "to page-locked host arrays every iteration (host-side solver)" if jac_to_host else "left on the device (device-side solver); constraint values go to the host",
+            "note": "no solver in the loop (Ipopt is not installed): per batch one armour_eval_batch launch over all its problems for g at k = 0 (feasibility flag of the record) and %d launches for g + Jacobian at random k" % (SWEEP_EVALS - 1)}
 
 
 def run_ours(args):
@@ -447,6 +452,7 @@ def run_ours(args):
         ps.close()
     # ---- config 3: 4096-problem strong-scaling sweep ----
     sweep_out = run_sweep_config3(ab, dist, torch, rank, world, local_rank) if args.sweep else None
+    sweep_host = run_sweep_config3(ab, dist, torch, rank, world, local_rank, jac_to_host=True) if args.sweep else None
     clocks = sampler.stop()
 
     if rank == 0:
@@ -519,6 +525,7 @@ def run_ours(args):
                                     "oracle_port_ms_per_step_unbound_threads": 1e3 * float(np.mean(port_t))}
         if sweep_out:
             line["sweep"] = sweep_out
+            line["sweep_host_jacobian"] = sweep_host
         line.update(extra)
         _emit(json.dumps(line))
     p.close()

@@ -190,6 +190,13 @@ int armour_eval_resident_burst(armour_handle* h, const double* x, int launches, 
  * problem first + y land at g[y * m ..] and values[y * 7 m ..]; either may be NULL.  Bit-identical to `count` single calls. */
 int armour_eval_batch(armour_handle* h, int first, int count, const double* x, double* g, double* values);
 int armour_last_eval_batch_ms(armour_handle* h, float* ms); /* device time of the last armour_eval_batch kernel */
+/* The same launch with the Jacobians left on the device for a device-side consumer (a batched QP / line search): only the
+ * constraint values cross PCIe (8 m instead of 64 m bytes per problem).  g may be NULL.  armour_batch_jacobian_device hands
+ * out the device array ([problems][7 m] doubles, valid until the next batched evaluation or build);
+ * armour_get_batch_jacobian copies one problem's rows to the host (tests, debugging). */
+int armour_eval_batch_resident(armour_handle* h, int first, int count, const double* x, double* g);
+int armour_batch_jacobian_device(armour_handle* h, const double** values_dev, int* problems);
+int armour_get_batch_jacobian(armour_handle* h, int y, double* values);
 /* profiling builds (-DARMOUR_PHASE_TIMING) only: cycles / calls per engine phase summed over CTAs; zeros otherwise.
  * phases: 0 fill, 1 sort level, 2 segment walk, 3 scan+compact, 4 element-wise, 5 stage A, 6 export, 7 other */
 int armour_debug_phase_cycles(uint64_t* cycles8, uint64_t* calls8, int reset);

@@ -215,6 +215,13 @@ def test_eval_batch_equals_single_evals(gpu_lib, pin):
         pb.select_problem(i)
         g, J = pb.eval_g_jac(xs[i])
         assert np.array_equal(g, G[i]) and np.array_equal(J.ravel(), V[i]), i
+    G2 = np.zeros_like(G)
+    pb.eval_batch_resident(xs, g=G2)      # Jacobians stay on the device, only g crosses PCIe
+    assert np.array_equal(G2, G)
+    for i in range(B):
+        assert np.array_equal(pb.get_batch_jacobian(i), V[i]), i
+    with pytest.raises(ab.ArmourError):
+        pb.get_batch_jacobian(B)
     with pytest.raises(ab.ArmourError):
         pb.eval_batch(xs, first=1)        # range runs past the batch
     assert pb.last_eval_batch_ms() > 0
