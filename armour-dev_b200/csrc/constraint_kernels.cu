@@ -17,31 +17,28 @@ typedef unsigned long long u64;
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 
-// One block per (problem, t, link, group of 8 obstacles), one thread per (obstacle, pair) plane: no loops, no 64-bit index
-// arithmetic (the round-1 kernel decomposed a flat 64-bit index with five 64-bit divisions per thread).  The nine buffered
-// generators of each obstacle of the group — its own three and the link's 3x6 block (bufferObstaclesKernel) — are staged in
-// shared memory and read from there (broadcast loads), which keeps the kernel at 40 registers.
-constexpr int HYPER_OBS = 8;
-constexpr int HYPER_NT = HYPER_OBS * COMB;   // 288
-__global__ void __launch_bounds__(HYPER_NT) hyperplane_kernel(Tables tb) {
-    __shared__ double G[HYPER_OBS][9][3];
-    __shared__ double cen[HYPER_OBS][3];
+// One block per (problem, t, link) record, HYPER_OBS obstacles x 36 generator pairs per pass, looping over the obstacles: the link's
+// 3x6 generator block and all obstacles of the problem are staged in shared memory once (one barrier), then every thread computes
+// one plane per pass with no further synchronisation — 896 blocks for one plan, i.e. a single wave at 10 resident blocks per SM.
+// (Round 1: a flat 64-bit index decomposed with five 64-bit divisions per thread; first round-2 version: one block per record
+// AND group of 8 obstacles, 3.6 waves of one-plane threads, 22 us for 20 obstacles.)
+constexpr int EVAL_MAX_OBS = 64;      // shared-memory slab of the half-space table: 64 x 1440 B = 90 KB
+constexpr int HYPER_OBS = 4;
+constexpr int HYPER_NT = HYPER_OBS * COMB;   // 144
+__global__ void __launch_bounds__(HYPER_NT, 7) hyperplane_kernel(Tables tb) {
+    __shared__ double Lg[18];                       // the link's six generators (bufferObstaclesKernel appends them to the obstacle's three)
+    __shared__ double Ob[EVAL_MAX_OBS * 12];        // centre + three generators of every obstacle of this problem
     const int n_obs = tb.n_obs;
     const size_t rec = blockIdx.x;                      // (prob * T + t) * NJ + link
     const int prob = (int)(rec / ((size_t)tb.T * NJ));
-    const int o_base = blockIdx.y * HYPER_OBS;
-    const int n_here = min(HYPER_OBS, n_obs - o_base);
-    for (int e = threadIdx.x; e < n_here * 30; e += HYPER_NT) {
-        const int ol = e / 30, r = e - ol * 30;
-        const double* ob = tb.obstacles + ((size_t)prob * n_obs + o_base + ol) * 12;
-        if (r < 3) cen[ol][r] = ob[r];
-        else if (r < 12) G[ol][(r - 3) / 3][(r - 3) % 3] = ob[r];
-        else G[ol][3 + (r - 12) / 3][(r - 12) % 3] = tb.gens[rec * 18 + (r - 12)];
-    }
+    for (int e = threadIdx.x; e < 18; e += HYPER_NT) Lg[e] = tb.gens[rec * 18 + e];
+    for (int e = threadIdx.x; e < n_obs * 12; e += HYPER_NT) Ob[e] = tb.obstacles[(size_t)prob * n_obs * 12 + e];
     __syncthreads();
+    // (transposing the normals through shared memory for fully coalesced stores was measured slower: one barrier per pass)
     const int p = threadIdx.x % COMB, ol = threadIdx.x / COMB;
-    if (ol >= n_here) return;
-    write_half_space(tb, (rec * n_obs + o_base + ol) * COMB + p, &G[ol][0][0], &G[ol][3][0], cen[ol], p);
+    #pragma unroll 2
+    for (int o = ol; o < n_obs; o += HYPER_OBS)
+        write_half_space(tb, (rec * n_obs + o) * COMB + p, Ob + o * 12 + 3, Lg, Ob + o * 12, p);
 }
 
 // ---- Bezier curve pieces used by the limit rows (KPR/Trajectory.cu:542-599) -----------------------
@@ -181,7 +178,6 @@ __device__ __forceinline__ double slice_term(double coef, u64 key, const double*
 // (n_obs x 36 planes x 40 B, contiguous in A, d and delta) is fetched by three bulk asynchronous copies (TMA, completion on an
 // mbarrier) issued before anything else, so the table streams in while the block slices its two polynomial zonotopes at k.
 constexpr int EVAL_NT = 128;
-constexpr int EVAL_MAX_OBS = 64;      // shared-memory slab of the half-space table: 64 x 1440 B = 90 KB
 constexpr int EVAL_LCHUNK = 5;        // link monomials staged per pass (x 24 outputs)
 // torque monomials staged per pass (x 8 outputs): as many as fit beside the table slab while seven blocks stay resident per SM
 // (7 x (static + dynamic + 1 KB) <= 228 KB), between 16 and the table capacity
@@ -436,7 +432,8 @@ __global__ void __launch_bounds__(EVAL_NT, 7) constraint_eval_kernel(Tables tb, 
 cudaError_t launch_hyperplanes(const Tables& tb, cudaStream_t stream) {
     const size_t recs = (size_t)tb.P * tb.T * NJ;
     if (recs == 0 || tb.n_obs == 0) return cudaSuccess;
-    hyperplane_kernel<<<dim3((unsigned)recs, (tb.n_obs + HYPER_OBS - 1) / HYPER_OBS), HYPER_NT, 0, stream>>>(tb);
+    if (tb.n_obs > EVAL_MAX_OBS) return cudaErrorInvalidValue;
+    hyperplane_kernel<<<(unsigned)recs, HYPER_NT, 0, stream>>>(tb);
     return cudaGetLastError();
 }
 int eval_max_obstacles() { return EVAL_MAX_OBS; }

@@ -14,7 +14,7 @@ static __constant__ unsigned char c_pair_b[COMB] = {1, 2, 3, 4, 5, 6, 7, 8, 2, 3
 // The nine generators of one (link, obstacle) pair: the obstacle's three (Go[3][3]) and the link's six (Gl[6][3]); cen: the
 // obstacle centre.  Writes A (unit normal or zero), d = A . c and delta = sum_j |A . g_j| of plane `p` at table index idx.
 __device__ __forceinline__ const double* buffered_generator(const double* Go, const double* Gl, int k) { return k < 3 ? Go + 3 * k : Gl + 3 * (k - 3); }
-__device__ __forceinline__ void write_half_space(const Tables& tb, size_t idx, const double* Go, const double* Gl, const double* cen, int p) {
+__device__ __forceinline__ void compute_half_space(const double* Go, const double* Gl, const double* cen, int p, double& C0, double& C1, double& C2, double& d, double& delta) {
     const double* ga = buffered_generator(Go, Gl, c_pair_a[p]);
     const double* gb = buffered_generator(Go, Gl, c_pair_b[p]);
     const double ga0 = ga[0], ga1 = ga[1], ga2 = ga[2];
@@ -23,16 +23,22 @@ __device__ __forceinline__ void write_half_space(const Tables& tb, size_t idx, c
     const double cr1 = __dadd_rn(__dmul_rn(ga2, gb0), -__dmul_rn(ga0, gb2));
     const double cr2 = __dadd_rn(__dmul_rn(ga0, gb1), -__dmul_rn(ga1, gb0));
     const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(cr0, cr0), __dmul_rn(cr1, cr1)), __dmul_rn(cr2, cr2)));
-    double C0 = 0, C1 = 0, C2 = 0;
+    C0 = 0; C1 = 0; C2 = 0;
     if (nrm > 0) { C0 = __ddiv_rn(cr0, nrm); C1 = __ddiv_rn(cr1, nrm); C2 = __ddiv_rn(cr2, nrm); }
-    tb.A[idx * 3 + 0] = C0; tb.A[idx * 3 + 1] = C1; tb.A[idx * 3 + 2] = C2;
-    tb.d[idx] = __dadd_rn(__dadd_rn(__dmul_rn(C0, cen[0]), __dmul_rn(C1, cen[1])), __dmul_rn(C2, cen[2]));
+    d = __dadd_rn(__dadd_rn(__dmul_rn(C0, cen[0]), __dmul_rn(C1, cen[1])), __dmul_rn(C2, cen[2]));
     double dl = 0.0;
 #pragma unroll
     for (int j = 0; j < 9; j++) {
         const double* gj = buffered_generator(Go, Gl, j);
         dl = __dadd_rn(dl, fabs(__dadd_rn(__dadd_rn(__dmul_rn(C0, gj[0]), __dmul_rn(C1, gj[1])), __dmul_rn(C2, gj[2]))));
     }
+    delta = dl;
+}
+__device__ __forceinline__ void write_half_space(const Tables& tb, size_t idx, const double* Go, const double* Gl, const double* cen, int p) {
+    double C0, C1, C2, d, dl;
+    compute_half_space(Go, Gl, cen, p, C0, C1, C2, d, dl);
+    tb.A[idx * 3 + 0] = C0; tb.A[idx * 3 + 1] = C1; tb.A[idx * 3 + 2] = C2;
+    tb.d[idx] = d;
     tb.delta[idx] = dl;
 }
 
