@@ -143,6 +143,8 @@ struct armour_handle {
     double *a_g = nullptr, *a_jac = nullptr;       // device aliases of the pinned staging buffers h_g / h_jac
     double *d_bx = nullptr, *d_bg = nullptr, *d_bjac = nullptr, *h_bx = nullptr;   // armour_eval_batch: decision vectors and result rows of a whole batch
     size_t bx_cap = 0, bg_cap = 0, bjac_cap = 0, bjac_rows = 0;   // bjac_rows: problems whose Jacobian the last batched evaluation left in d_bjac
+    double *h_ws = nullptr, *a_ws = nullptr;   // page-locked solver workspace (armour_standin_solve) and its device alias
+    size_t ws_doubles = 0;
     bool fuse_planes = false;  // ARMOUR_TUNE_FUSE_PLANES=1: stage D inside reach_build_kernel instead of the separate hyperplane_kernel launch
     float batch_eval_ms = 0;
     int eval_bps_host = 0;                         // resident blocks per SM of the constraint kernel when it writes to host memory (waves overlap compute and PCIe)
@@ -520,7 +522,7 @@ void armour_destroy(armour_handle* h) {
     void* dev[] = {h->d_jrs, h->d_krange, h->d_state, h->d_obs, tb.traj, tb.cos_rem, tb.sin_rem, tb.u_n, tb.u_keys, tb.u_coef, tb.u_center, tb.u_ind, tb.dist_rad, tb.torque_radius,
                    tb.l_n, tb.l_keys, tb.l_coef, tb.l_center, tb.l_ind, tb.gens, tb.A, tb.d, tb.delta, h->d_err, h->d_x, h->d_g, h->d_jac, h->d_link_center, h->arena, h->bin_buf, h->d_done, h->d_bx, h->d_bg, h->d_bjac};
     for (void* p : dev) if (p) cudaFree(p);
-    void* pinned[] = {h->h_jrs, h->h_krange, h->h_state, h->h_obs, h->h_x, h->h_g, h->h_jac, h->h_torque_radius, h->h_err, (void*)h->h_done, h->h_bx};
+    void* pinned[] = {h->h_jrs, h->h_krange, h->h_state, h->h_obs, h->h_x, h->h_g, h->h_jac, h->h_torque_radius, h->h_err, (void*)h->h_done, h->h_bx, h->h_ws};
     for (void* p : pinned) if (p) cudaFreeHost(p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -645,13 +647,19 @@ int armour_release_host_buffers(armour_handle* h) {
 // iterate), so each entry point computes what it is asked for: `what` bit 0 = g, bit 1 = Jacobian.  With cfg.pin_user_buffers
 // the kernel writes the caller's page-locked arrays directly; otherwise results pass through the handle's pinned staging
 // buffers, and a repeated request at the same x is served from there.
+// device alias of an address inside the handle's own page-locked solver workspace (nullptr otherwise)
+static double* ws_alias(armour_handle* h, double* host, size_t bytes) {
+    if (!h->h_ws || host < h->h_ws || (char*)host + bytes > (char*)(h->h_ws + h->ws_doubles)) return nullptr;
+    return h->a_ws + (host - h->h_ws);
+}
 static int eval_into(armour_handle* h, const double* x, double* g, double* values) {
     const int what = (g ? 1 : 0) | (values ? 2 : 0);
     if (!h->built) return fail(ARMOUR_E_STATE, "eval before build");
     const int m = m_of(h);
-    if (h->cfg.pin_user_buffers) {   // zero staging: the kernel writes the caller's arrays
-        double* dg = g ? (double*)pinned_alias(h, g, sizeof(double) * m) : nullptr;
-        double* dj = values ? (double*)pinned_alias(h, values, sizeof(double) * (size_t)m * NF, dg) : nullptr;
+    const bool in_ws = (!g || ws_alias(h, g, sizeof(double) * m)) && (!values || ws_alias(h, values, sizeof(double) * (size_t)m * NF));
+    if (h->cfg.pin_user_buffers || in_ws) {   // zero staging: the kernel writes the caller's arrays
+        double* dg = !g ? nullptr : in_ws ? ws_alias(h, g, sizeof(double) * m) : (double*)pinned_alias(h, g, sizeof(double) * m);
+        double* dj = !values ? nullptr : in_ws ? ws_alias(h, values, sizeof(double) * (size_t)m * NF) : (double*)pinned_alias(h, values, sizeof(double) * (size_t)m * NF, dg);
         if ((!g || dg) && (!values || dj)) {
             int rc = launch_eval(h, x, g, values, dg, dj, what);
             if (rc != ARMOUR_OK) return rc;
@@ -1005,15 +1013,22 @@ int armour_standin_solve(armour_handle* h, const double* q_des, double t_plan, d
     armtd_NLP nlp;
     nlp.set_time_steps(h->T);
     if (!nlp.set_parameters(q_des, t_plan, h)) return fail(ARMOUR_E_STATE, "set_parameters failed");
-    // the solver's own g / Jacobian vectors live for the whole solve: page-lock them so that every callback is a direct write
-    // ... and unregister exactly those afterwards: they are freed when the solver returns, and a registration left behind on
-    // freed heap memory makes a later registration of whatever the allocator places there fail ("already mapped")
-    const int saved_pin = h->cfg.pin_user_buffers;
+    // the solver's g / trial-g / Jacobian arrays are the handle's page-locked workspace: every callback is a direct device write
+    // (eval_into resolves workspace addresses without registering anything), whatever cfg.pin_user_buffers says
+    const size_t need = (size_t)m_of(h) * (NF + 2);
+    if (h->ws_doubles < need) {
+        if (h->h_ws) cudaFreeHost(h->h_ws);
+        h->h_ws = nullptr; h->a_ws = nullptr; h->ws_doubles = 0;
+        CU(cudaHostAlloc((void**)&h->h_ws, sizeof(double) * need, cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer((void**)&h->a_ws, h->h_ws, 0));
+        h->ws_doubles = need;
+    }
+    // arrays of the adapter object itself (g_copy in finalize_solution) are registered under cfg.pin_user_buffers like any caller
+    // array; the adapter dies with this call, so those registrations go with it (a registration left on freed memory makes a
+    // later registration of whatever the allocator places there fail: "already mapped")
     std::vector<const void*> before;
     for (auto& e : h->pinned) before.push_back(e.host);
-    h->cfg.pin_user_buffers = 1;
-    StandinResult r = standin_solve(nlp, k_opt);
-    h->cfg.pin_user_buffers = saved_pin;
+    StandinResult r = standin_solve(nlp, k_opt, 60, h->h_ws);
     for (size_t i = h->pinned.size(); i-- > 0;) {
         if (std::find(before.begin(), before.end(), (const void*)h->pinned[i].host) != before.end()) continue;
         cudaHostUnregister((void*)h->pinned[i].host);

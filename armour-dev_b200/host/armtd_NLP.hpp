@@ -117,6 +117,9 @@ public:
         armour_eval_g(handle, x, gtmp.data());
         link_sliced_center.assign((size_t)num_time_steps() * ARMOUR_NUM_JOINTS * 3, 0.0);
         armour_get_link_sliced_center(handle, link_sliced_center.data());
+        // Under cfg.pin_user_buffers the library page-locked the arrays the solver handed to the callbacks (and gtmp above).  The
+        // solver frees them once the solve returns, so their registrations end here.
+        armour_release_host_buffers(handle);
     }
 
     int num_time_steps() const { return (constraint_number - 4 * ARMOUR_NUM_FACTORS) > 0 ? time_steps : 0; }

@@ -255,21 +255,22 @@ def test_fused_half_space_tables_equal_the_separate_kernel(gpu_lib, monkeypatch)
 
 
 def test_solver_scratch_is_not_left_page_locked(gpu_lib):
-    """armour_standin_solve page-locks its own g / Jacobian vectors for the duration of the solve.  They are freed when it
-    returns, so their registrations must go too — also under cfg.pin_user_buffers (a registration left on freed heap memory made
-    cudaHostRegister fail for whatever array the allocator placed there next: the 8-GPU sweep of bench.py found it)."""
+    """Under cfg.pin_user_buffers every array handed to a callback is page-locked.  A solver frees its arrays when the solve
+    returns, so the adapter's finalize_solution releases the registrations (armtd_NLP.hpp), and armour_standin_solve runs on the
+    handle's own page-locked workspace.  A registration left on freed heap memory made cudaHostRegister fail for whatever array
+    the allocator placed there next: the 8-GPU sweep of bench.py found it."""
     q0, qd0, qdd0, q_des, obs = make_problem(3, 5)
     for pin in (True, False):
         p = ab.Planner(T=16, pin_user_buffers=pin)
         p.build(q0, qd0, qdd0, obs)
         g, J = np.zeros(p.m), np.zeros(p.m * 7)
         p.eval_g_jac(DEBUG_K, g, J)
-        n0 = p.pinned_buffer_count()
-        assert n0 == (2 if pin else 0)
+        assert p.pinned_buffer_count() == (2 if pin else 0)
         p.standin_solve(q_des, 0.5)
-        assert p.pinned_buffer_count() == n0
+        assert p.pinned_buffer_count() == 0
         g2, J2 = np.zeros(p.m), np.zeros(p.m * 7)
-        p.eval_g_jac(DEBUG_K, g2, J2)
+        p.eval_g_jac(DEBUG_K, g2, J2)          # caller arrays are registered again on next use
+        assert p.pinned_buffer_count() == (2 if pin else 0)
         assert np.array_equal(g, g2) and np.array_equal(J, J2)
         p.close()
 
