@@ -48,6 +48,11 @@ int main(int argc, char** argv) {
     armour_config cfg;
     armour_default_config(&cfg);
     cfg.num_time_steps = NUM_TIME_STEPS;
+#ifdef ARMOUR_HAVE_IPOPT
+    // Ipopt hands the same g / Jacobian arrays to every callback of a solve: let the kernels write them directly (page-locked on
+    // first sight, released by armtd_NLP::finalize_solution) instead of staging each result through a 1.2 MB host copy
+    cfg.pin_user_buffers = 1;
+#endif
     armour_handle* h = nullptr;
     if (armour_create(&cfg, &h) != ARMOUR_OK) { printf("        CUDA & C++: %s\n", armour_last_error()); out1 << -1 << '\n'; out1.close(); armour_destroy(h); return 1; }
 
