@@ -470,6 +470,24 @@ __device__ __forceinline__ void keyhash_record(Scratch& S, const PZ<D>& dst, int
     }
 }
 #endif
+#ifdef ARMOUR_SEGSTAT
+// Measurement build (scripts/segstat_experiment.py): how unevenly the per-key segment walk loads the lanes of a warp.  Per warp
+// iteration: candidates, segment heads, longest segment (= the iteration's duration in term computations today) — summed in
+// g_segstat[0..3] = {warp iterations, candidates, heads, sum of longest segment}.
+__device__ unsigned long long g_segstat[4];
+__device__ __forceinline__ void segstat_record(int N, int g, bool head, const u64* key) {
+    const unsigned act = __activemask();
+    int len = 0;
+    if (head) { const u64 k = key[g]; len = 1; for (int e = g + 1; e < N && key[e] == k; e++) len++; }
+    int mx = len;
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(act, mx, o));   // partial masks only in an operation's last iteration: approximate there
+    const unsigned heads = __ballot_sync(act, head);
+    if ((threadIdx.x & 31) == (__ffs(act) - 1)) {
+        atomicAdd(&g_segstat[0], 1ull); atomicAdd(&g_segstat[1], (unsigned long long)__popc(act));
+        atomicAdd(&g_segstat[2], (unsigned long long)__popc(heads)); atomicAdd(&g_segstat[3], (unsigned long long)mx);
+    }
+}
+#endif
 #ifndef ARMOUR_PREFETCH_DST
 #define ARMOUR_PREFETCH_DST 0
 #endif
@@ -535,6 +553,9 @@ __device__ __forceinline__ void reduce_emit(Scratch& S, int buf, int N, Op& op, 
     for (int g = gtid<NT>(); g < N; g += NT) {
         const u64 k = key[g];
         u16 f = 0;
+#ifdef ARMOUR_SEGSTAT
+        segstat_record(N, g, g == 0 || key[g - 1] != k, key);
+#endif
         if (g == 0 || key[g - 1] != k) {
             double acc[Op::NACC];
             op.first(idx[g], acc);
@@ -1617,6 +1638,9 @@ __device__ __forceinline__ void pz_op3_impl(Scratch& S, PZ<3>& dst, const Op3& d
     for (int g = gtid<NT>(); g < N; g += NT) {
         const u64 k = key[g];
         u16 f = 0;
+#ifdef ARMOUR_SEGSTAT
+        segstat_record(N, g, g == 0 || key[g - 1] != k, key);
+#endif
         if (g == 0 || key[g - 1] != k) {
             double acc[6];
             op3_term(d, idx[g], acc);

@@ -1031,6 +1031,13 @@ extern "C" int armour_debug_keyhash(unsigned long long* out, int work_items) {  
     return (int)cudaMemcpyFromSymbol(out, g_keyhash, sizeof(u64) * (size_t)work_items * KEYHASH_OPS * 2);
 }
 #endif
+#ifdef ARMOUR_SEGSTAT
+extern "C" int armour_debug_segstat(unsigned long long* out4, int reset) {
+    int rc = (int)cudaMemcpyFromSymbol(out4, g_segstat, sizeof(unsigned long long) * 4);
+    if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_segstat, z, sizeof(z)); }
+    return rc;
+}
+#endif
 void read_phase_cycles(unsigned long long* cycles, unsigned long long* calls, bool reset) {
 #ifdef ARMOUR_PHASE_TIMING
     cudaMemcpyFromSymbol(cycles, armour_phase_cycles, sizeof(unsigned long long) * PH_COUNT);
