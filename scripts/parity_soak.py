@@ -2,7 +2,8 @@
 own sources compiled in oracle/_ref (host reach-set build + its CUDA constraint kernels).  Same bars as tests/test_reference_pin.py:
 monomial keys bit-exact on every sampled table, coefficients / centres 1e-9, radii device >= reference and within 1e-9, torque
 radius, generator blocks, g and Jacobian rows 1e-8 (rows that differ beyond it must be exact half-space ties), feasibility verdict.
-usage: python scripts/parity_soak.py [N=400] [first_seed=1000]"""
+usage: python scripts/parity_soak.py [N=400] [first_seed=1000] [batch=0]     batch > 0: the device builds `batch` problems per launch
+(the sweep-shaped kernel: 128-thread CTAs, unified 3-vector operation) with a fixed number of obstacles per batch"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "armour-dev_b200"), os.path.join(ROOT, "tests")]
@@ -13,19 +14,28 @@ from problems import make_problem
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 400
 first = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+BATCH = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 ref, rh = _oracle.ReferenceCuda(), _oracle.Reference()
-p = ab.Planner(T=128, max_obstacles=40, device=0)
+p = ab.Planner(T=128, max_obstacles=40, device=0, batch=max(BATCH, 1))
 rng = np.random.default_rng(first)
 rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-12))) if a.size else 0.0
 stats = dict(problems=0, tables=0, monomials=0, key_mismatches=0, radius_below_reference=0, max_rel_coeff=0.0, max_rel_radius=0.0, max_rel_torque_radius=0.0,
              max_abs_g=0.0, jacobian_rows=0, jacobian_rows_beyond_1e8=0, verdict_mismatches=0, feasible=0)
 t0 = time.time()
 for seed in range(first, first + N):
-    n_obs = int(rng.integers(0, 41))
-    q0, qd0, qdd0, q_des, obs = make_problem(seed, n_obs)
+    if BATCH:
+        if (seed - first) % BATCH == 0:
+            n_obs = int(rng.integers(0, 41))
+            cur = [make_problem(s2, n_obs) for s2 in range(seed, min(seed + BATCH, first + N))]
+            p.build_batch(*[np.concatenate([q[k2] for q in cur]) for k2 in (0, 1, 2, 4)], n_obs)
+        q0, qd0, qdd0, q_des, obs = cur[(seed - first) % BATCH]
+        p.select_problem((seed - first) % BATCH)
+    else:
+        n_obs = int(rng.integers(0, 41))
+        q0, qd0, qdd0, q_des, obs = make_problem(seed, n_obs)
+        p.build(q0, qd0, qdd0, obs)
     ref.build(q0, qd0, qdd0, q_des, obs)
     rh.build(q0, qd0, qdd0)
-    p.build(q0, qd0, qdd0, obs)
     for name in ("links", "u_nom"):
         for s in range(seed % 7, 128, 7):
             for j in range(7):
@@ -50,6 +60,7 @@ for seed in range(first, first + N):
     stats["verdict_mismatches"] += int(f_dev != f_ref); stats["feasible"] += int(f_ref)
     stats["problems"] += 1
 stats["seconds"] = time.time() - t0
+stats["device_builds"] = "batches of %d problems per launch (sweep-shaped kernel)" % BATCH if BATCH else "one plan per launch"
 stats["note"] = ("Jacobian rows beyond 1e-8 are rows where two half-spaces tie to rounding and the reference's kernels (built with FMA contraction) pick the "
                  "other one; tests/test_reference_pin.py asserts that property row by row and shows 0 such rows against the FMA-free reference build")
 print(json.dumps(stats))
