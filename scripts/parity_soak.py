@@ -2,7 +2,7 @@
 own sources compiled in oracle/_ref (host reach-set build + its CUDA constraint kernels).  Same bars as tests/test_reference_pin.py:
 monomial keys bit-exact on every sampled table, coefficients / centres 1e-9, radii device >= reference and within 1e-9, torque
 radius, generator blocks, g and Jacobian rows 1e-8 (rows that differ beyond it must be exact half-space ties), feasibility verdict.
-usage: python scripts/parity_soak.py [N=400] [first_seed=1000] [batch=0]     batch > 0: the device builds `batch` problems per launch
+usage: python scripts/parity_soak.py [N=400] [first_seed=1000] [batch=0] [variant]     batch > 0: the device builds `batch` problems per launch
 (the sweep-shaped kernel: 128-thread CTAs, unified 3-vector operation) with a fixed number of obstacles per batch"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -15,8 +15,13 @@ from problems import make_problem
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 400
 first = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 BATCH = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-ref, rh = _oracle.ReferenceCuda(), _oracle.Reference()
-p = ab.Planner(T=128, max_obstacles=40, device=0, batch=max(BATCH, 1))
+VARIANT = sys.argv[4] if len(sys.argv) > 4 else None     # T512u5 (BASELINE configs[3]) or k24: the reference compiled at those sizes
+VARIANTS = {None: dict(T=128, k_range=np.pi / 48, unc=0.03), "T512u5": dict(T=512, k_range=np.pi / 48, unc=0.05), "k24": dict(T=128, k_range=np.pi / 24, unc=0.03)}
+V = VARIANTS[VARIANT]
+T = V["T"]
+ref, rh = (_oracle.ReferenceCuda(variant=VARIANT), _oracle.Reference(variant=VARIANT)) if VARIANT else (_oracle.ReferenceCuda(), _oracle.Reference())
+assert ref.T == T
+p = ab.Planner(T=T, max_obstacles=40, device=0, batch=max(BATCH, 1), k_range=[V["k_range"]] * 7, mass_uncertainty=V["unc"], inertia_uncertainty=V["unc"])
 rng = np.random.default_rng(first)
 rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-12))) if a.size else 0.0
 stats = dict(problems=0, tables=0, monomials=0, key_mismatches=0, radius_below_reference=0, max_rel_coeff=0.0, max_rel_radius=0.0, max_rel_torque_radius=0.0,
@@ -37,7 +42,7 @@ for seed in range(first, first + N):
     ref.build(q0, qd0, qdd0, q_des, obs)
     rh.build(q0, qd0, qdd0)
     for name in ("links", "u_nom"):
-        for s in range(seed % 7, 128, 7):
+        for s in range(seed % 7, T, 7):
             for j in range(7):
                 a, b = rh.get_pz(name, j, s), p.get_pz(name, j, s)
                 stats["tables"] += 1; stats["monomials"] += len(a["keys"])
@@ -60,6 +65,7 @@ for seed in range(first, first + N):
     stats["verdict_mismatches"] += int(f_dev != f_ref); stats["feasible"] += int(f_ref)
     stats["problems"] += 1
 stats["seconds"] = time.time() - t0
+stats["reference_build"] = "oracle/_ref stock sizes (T = 128, pi/48, 3 %)" if not VARIANT else "oracle/_ref variant %s (T = %d, k_range = %.4f, uncertainty %.2f)" % (VARIANT, T, V["k_range"], V["unc"])
 stats["device_builds"] = "batches of %d problems per launch (sweep-shaped kernel)" % BATCH if BATCH else "one plan per launch"
 stats["note"] = ("Jacobian rows beyond 1e-8 are rows where two half-spaces tie to rounding and the reference's kernels (built with FMA contraction) pick the "
                  "other one; tests/test_reference_pin.py asserts that property row by row and shows 0 such rows against the FMA-free reference build")
